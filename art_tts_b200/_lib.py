@@ -1,0 +1,131 @@
+"""ctypes binding of libmas_sm100.so (the C ABI declared in include/mas_b200.h).
+
+There is no CPU fallback: if the library is missing this module raises, loudly, at first
+use.  Build it with `python -m art_tts_b200.build` (or `__graft_entry__.build()`).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import torch
+
+from . import build as _build
+
+MAS_F32, MAS_F16, MAS_BF16, MAS_F64, MAS_I32, MAS_U8, MAS_I64 = range(7)
+FLAG_FORCE_GENERAL = 1
+FLAG_NO_TMA = 2
+
+_DTYPES = {
+    torch.float32: MAS_F32,
+    torch.float16: MAS_F16,
+    torch.bfloat16: MAS_BF16,
+    torch.float64: MAS_F64,
+    torch.int32: MAS_I32,
+    torch.uint8: MAS_U8,
+    torch.bool: MAS_U8,
+    torch.int64: MAS_I64,
+}
+
+EXPORTS = (
+    "mas_abi_version", "mas_strerror", "mas_lengths_from_mask", "mas_workspace_bytes",
+    "mas_maximum_path", "mas_from_prior_f32", "mas_from_prior_plan", "mas_generate_path", "mas_plan",
+    "mas_launch_count",
+)
+
+_lib = None
+
+
+class MasError(RuntimeError):
+    pass
+
+
+def lib_path() -> str:
+    return _build.LIB
+
+
+def load() -> ctypes.CDLL:
+    """Load (never build) the CUDA library; raise if it is not there."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if not os.path.exists(path):
+        raise MasError(
+            f"{path} is missing: art_tts_b200 has no CPU fallback. Build the sm_100a library with "
+            "`python -m art_tts_b200.build` (needs nvcc) before using it.")
+    lib = ctypes.CDLL(path)
+    vp, ci, i64, sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_size_t
+    lib.mas_abi_version.restype = ci
+    lib.mas_abi_version.argtypes = []
+    lib.mas_strerror.restype = ctypes.c_char_p
+    lib.mas_strerror.argtypes = [ci]
+    lib.mas_lengths_from_mask.restype = ci
+    lib.mas_lengths_from_mask.argtypes = [vp, ci, ci, ci, ci, i64, i64, i64, vp, vp, vp]
+    lib.mas_workspace_bytes.restype = sz
+    lib.mas_workspace_bytes.argtypes = [ci, ci, ci]
+    lib.mas_maximum_path.restype = ci
+    lib.mas_maximum_path.argtypes = [vp, ci, vp, vp, vp, vp, ci, vp, vp, ci, ci, ci, vp, sz, ci, vp]
+    lib.mas_from_prior_f32.restype = ci
+    lib.mas_from_prior_f32.argtypes = [vp, vp, vp, vp, vp, vp, ci, vp, vp, vp, vp, ci, ci, ci, ci,
+                                       vp, sz, ci, vp]
+    lib.mas_from_prior_plan.restype = ci
+    lib.mas_from_prior_plan.argtypes = [ci, ci, ci, ci, ci]
+    lib.mas_generate_path.restype = ci
+    lib.mas_generate_path.argtypes = [vp, ci, vp, vp, vp, ci, ci, ci, ci, vp]
+    lib.mas_plan.restype = ci
+    lib.mas_plan.argtypes = [ci, ci, ci, ci]
+    lib.mas_launch_count.restype = ctypes.c_uint64
+    lib.mas_launch_count.argtypes = []
+    if lib.mas_abi_version() != 1:
+        raise MasError("libmas_sm100.so ABI version mismatch; rebuild it")
+    _lib = lib
+    return lib
+
+
+def check(code: int, what: str) -> None:
+    if code == 0:
+        return
+    msg = load().mas_strerror(code).decode()
+    if code < 0:
+        raise ValueError(f"{what}: {msg} (MAS error {code})")
+    raise MasError(f"{what}: CUDA error {code}: {msg}")
+
+
+def dtype_code(dt: torch.dtype) -> int:
+    try:
+        return _DTYPES[dt]
+    except KeyError:
+        raise TypeError(f"unsupported dtype {dt}") from None
+
+
+def ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def stream_ptr(device) -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def require_cuda(t: torch.Tensor, name: str) -> None:
+    if not t.is_cuda:
+        raise MasError(
+            f"{name} is on {t.device}: art_tts_b200 runs MAS on a CUDA (sm_100a) device only and "
+            "has no CPU fallback (the reference's host Cython path is what it replaces).")
+
+
+_workspaces = {}
+
+
+def workspace(device, nbytes: int) -> torch.Tensor:
+    """Per (device, stream) scratch buffer, grown on demand, reused across calls."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    buf = _workspaces.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 1 << 16), dtype=torch.uint8, device=device)
+        _workspaces[key] = buf
+    return buf
+
+
+def launch_count() -> int:
+    return int(load().mas_launch_count())

@@ -1,0 +1,290 @@
+// mas_api.cu -- the C ABI of libmas_sm100.so (see include/mas_b200.h for the contract and the
+// reference interfaces each entry point replaces).  Host-side only: argument validation,
+// plan selection, launches.  No allocation, no host synchronisation, no CPU fallback.
+#include <atomic>
+#include <cstdlib>
+
+#include "mas_internal.h"
+
+namespace mas {
+
+static std::atomic<uint64_t> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+int element_size(int dtype)
+{
+    switch (dtype) {
+    case MAS_F32: return 4;
+    case MAS_F16: return 2;
+    case MAS_BF16: return 2;
+    case MAS_F64: return 8;
+    case MAS_I32: return 4;
+    case MAS_U8: return 1;
+    case MAS_I64: return 8;
+    default: return 0;
+    }
+}
+
+unsigned long long one_pattern(int dtype)
+{
+    switch (dtype) {
+    case MAS_F32: return 0x3f800000ull;
+    case MAS_F16: return 0x3c00ull;
+    case MAS_BF16: return 0x3f80ull;
+    case MAS_F64: return 0x3ff0000000000000ull;
+    default: return 1ull;
+    }
+}
+
+static int env_int(const char *name, int dflt)
+{
+    const char *s = std::getenv(name);
+    return (s && *s) ? std::atoi(s) : dflt;
+}
+
+// Shared-memory carve-up of the fast kernels and the plan that follows from it.
+// `extra_smem` = bytes the caller needs besides ring + bits (the fused kernel's operands).
+Plan choose_plan(int T_x, int T_y, int flags, FastLayout *lay, size_t extra_smem, int max_stages)
+{
+    FastLayout L{};
+    L.xrows = ((T_x + 31) / 32) * 32;
+    L.nch = (T_y + 31) / 32;
+    const size_t stage_bytes = (size_t)L.xrows * 128;
+    const size_t bits_bytes = (size_t)L.nch * L.xrows * 4;
+    const size_t misc = (((size_t)T_x * 8 + 15) & ~(size_t)15) + 128 + extra_smem;
+    Plan plan = kPlanGeneral;
+    auto total = [&](int S, bool bits_smem) {
+        return (size_t)S * stage_bytes + (bits_smem ? bits_bytes : 0) + misc;
+    };
+    if (T_x <= kMaxFastTx && !(flags & MAS_FLAG_FORCE_GENERAL)) {
+        const bool fits = total(2, true) <= (size_t)kSmemBudget;
+        L.bits_in_smem = fits ? 1 : 0;
+        plan = fits ? kPlanFastSmemBits : kPlanFastSpillBits;
+        if (total(2, fits) > (size_t)kSmemBudget) plan = kPlanGeneral;  // cannot happen for T_x<=512
+        // ring depth: deepest ring that does not cost a resident CTA (or leaves >= 3 per SM)
+        int S = 2;
+        const int forced = env_int("MAS_STAGES", 0);
+        auto occ = [&](int s) { return (int)((size_t)(kSmemBudget + 1024) / (total(s, fits) + 1024)); };
+        for (int s = 3; s <= max_stages; ++s)
+            if (total(s, fits) <= (size_t)kSmemBudget && (occ(s) >= occ(2) || occ(s) >= 3)) S = s;
+        if (forced >= 2 && forced <= 8 && total(forced, fits) <= (size_t)kSmemBudget) S = forced;
+        L.nstages = S;
+    }
+    if (plan == kPlanGeneral) {
+        L.nstages = 0;
+        L.bits_in_smem = 0;
+    }
+    L.off_stages = 0;
+    L.off_bits = (size_t)L.nstages * stage_bytes;
+    L.off_first = L.off_bits + (L.bits_in_smem ? bits_bytes : 0);
+    L.off_dur = L.off_first + (size_t)T_x * 4;
+    L.off_bars = (L.off_dur + (size_t)T_x * 4 + 15) & ~(size_t)15;
+    L.total = L.off_bars + 128 + extra_smem;
+    if (lay) *lay = L;
+    return plan;
+}
+
+static size_t bits_workspace_bytes(int B, int T_x, int T_y)
+{
+    const size_t xrows = (size_t)((T_x + 31) / 32) * 32, nch = (size_t)(T_y + 31) / 32;
+    return (size_t)B * nch * xrows * 4;
+}
+
+}  // namespace mas
+
+using namespace mas;
+
+extern "C" {
+
+int mas_abi_version(void) { return MAS_ABI_VERSION; }
+
+const char *mas_strerror(int code)
+{
+    switch (code) {
+    case MAS_OK: return "ok";
+    case MAS_ERR_NULL: return "required pointer is NULL";
+    case MAS_ERR_SHAPE: return "shape out of range";
+    case MAS_ERR_DTYPE: return "unsupported element type";
+    case MAS_ERR_WORKSPACE: return "workspace missing or too small";
+    case MAS_ERR_ALIGN: return "pointer not aligned to its element size";
+    case MAS_ERR_NO_DEVICE: return "no usable CUDA device";
+    default: break;
+    }
+    if (code > 0) return cudaGetErrorString(static_cast<cudaError_t>(code));
+    return "unknown error";
+}
+
+uint64_t mas_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+size_t mas_workspace_bytes(int B, int T_x, int T_y)
+{
+    if (B < 0 || T_x < 1 || T_y < 1) return 256;
+    return bits_workspace_bytes(B, T_x, T_y) + 256;
+}
+
+int mas_plan(int B, int T_x, int T_y, int flags)
+{
+    (void)B;
+    if (T_x < 1 || T_y < 1) return MAS_ERR_SHAPE;
+    FastLayout lay;
+    return (int)choose_plan(T_x, T_y, flags, &lay);
+}
+
+static bool shape_ok(int B, int T_x, int T_y)
+{
+    if (B < 0 || T_x < 1 || T_y < 1) return false;
+    const double cells = (double)B * T_x * T_y;
+    return cells < 9.0e18 / 8.0 && T_x <= (1 << 24) && T_y <= (1 << 24);
+}
+
+int mas_lengths_from_mask(const void *mask, int mask_dtype, int B, int T_x, int T_y,
+                          int64_t stride_b, int64_t stride_x, int64_t stride_y, int32_t *t_x_out,
+                          int32_t *t_y_out, void *stream)
+{
+    if (!mask || !t_x_out || !t_y_out) return MAS_ERR_NULL;
+    if (!shape_ok(B, T_x, T_y)) return MAS_ERR_SHAPE;
+    if (element_size(mask_dtype) == 0) return MAS_ERR_DTYPE;
+    if (B == 0) return MAS_OK;
+    return (int)launch_lengths_from_mask(mask, mask_dtype, B, T_x, T_y, stride_b, stride_x, stride_y,
+                                         t_x_out, t_y_out, static_cast<cudaStream_t>(stream));
+}
+
+int mas_maximum_path(const void *value, int value_dtype, const float *cell_mask, const int32_t *t_x,
+                     const int32_t *t_y, void *path, int path_dtype, int32_t *durations,
+                     float *score, int B, int T_x, int T_y, void *workspace, size_t workspace_bytes,
+                     int flags, void *stream)
+{
+    if (!value || !t_x || !t_y) return MAS_ERR_NULL;
+    if (!path && !durations && !score) return MAS_ERR_NULL;
+    if (!shape_ok(B, T_x, T_y)) return MAS_ERR_SHAPE;
+    if (value_dtype != MAS_F32 && value_dtype != MAS_F16 && value_dtype != MAS_BF16 &&
+        value_dtype != MAS_F64)
+        return MAS_ERR_DTYPE;
+    const int esize = element_size(path_dtype);
+    if (path && (esize == 0 || path_dtype == MAS_I64)) return MAS_ERR_DTYPE;
+    if ((uintptr_t)value % element_size(value_dtype) || (path && (uintptr_t)path % esize) ||
+        (uintptr_t)t_x % 4 || (uintptr_t)t_y % 4 || (uintptr_t)durations % 4 ||
+        (uintptr_t)score % 4 || (uintptr_t)cell_mask % 4)
+        return MAS_ERR_ALIGN;
+    if (B == 0) return MAS_OK;
+
+    MasArgs a{};
+    const Plan plan = choose_plan(T_x, T_y, flags, &a.lay);
+    if (plan != kPlanFastSmemBits) {
+        if (!workspace || workspace_bytes < mas_workspace_bytes(B, T_x, T_y)) return MAS_ERR_WORKSPACE;
+        if ((uintptr_t)workspace % 16) return MAS_ERR_ALIGN;
+    }
+    if (plan == kPlanGeneral && (size_t)T_x * 16 > (size_t)kSmemBudget) return MAS_ERR_SHAPE;
+    a.value = value;
+    a.cell_mask = cell_mask;
+    a.t_x = t_x;
+    a.t_y = t_y;
+    a.path = path;
+    a.durations = durations;
+    a.score = score;
+    a.bits_ws = static_cast<uint32_t *>(workspace);
+    a.B = B;
+    a.T_x = T_x;
+    a.T_y = T_y;
+    a.path_esize = path ? esize : 4;
+    a.one = one_pattern(path_dtype);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const cudaError_t e = (plan == kPlanGeneral) ? launch_general(a, value_dtype, st)
+                                                 : launch_fast(a, value_dtype, st);
+    return (int)e;
+}
+
+int mas_from_prior_plan(int B, int F, int T_x, int T_y, int flags)
+{
+    (void)B;
+    if (T_x < 1 || T_y < 1 || F < 1) return MAS_ERR_SHAPE;
+    FastLayout lay;
+    const Plan plan = choose_plan(T_x, T_y, flags, &lay, prior_extra_smem(F, T_x), 3);
+    return plan == kPlanGeneral ? 1 : 0;
+}
+
+int mas_from_prior_f32(const float *mu_x, const float *logs, const float *y, const int32_t *t_x,
+                       const int32_t *t_y, void *path, int path_dtype, int32_t *durations,
+                       int32_t *frame_idx, float *score, float *log_prior_out, int B, int F, int T_x,
+                       int T_y, void *workspace, size_t workspace_bytes, int flags, void *stream)
+{
+    if (!mu_x || !y || !t_x || !t_y) return MAS_ERR_NULL;
+    if (!path && !durations && !frame_idx && !score) return MAS_ERR_NULL;
+    if (logs) return MAS_ERR_DTYPE;  // unit-variance prior only (tts.py:483-495 has no logs term)
+    if (!shape_ok(B, T_x, T_y) || F < 1 || F > 4096) return MAS_ERR_SHAPE;
+    const int esize = element_size(path_dtype);
+    if (path && (esize == 0 || path_dtype == MAS_I64)) return MAS_ERR_DTYPE;
+    if ((uintptr_t)mu_x % 4 || (uintptr_t)y % 4 || (path && (uintptr_t)path % esize) ||
+        (uintptr_t)t_x % 4 || (uintptr_t)t_y % 4 || (uintptr_t)durations % 4 ||
+        (uintptr_t)frame_idx % 4 || (uintptr_t)score % 4 || (uintptr_t)log_prior_out % 4)
+        return MAS_ERR_ALIGN;
+    if (B == 0) return MAS_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+
+    PriorArgs a{};
+    const Plan plan = choose_plan(T_x, T_y, flags, &a.lay, prior_extra_smem(F, T_x), 3);
+    const bool fused = plan != kPlanGeneral;
+    if (!workspace || workspace_bytes < mas_workspace_bytes(B, T_x, T_y)) return MAS_ERR_WORKSPACE;
+    if ((uintptr_t)workspace % 16) return MAS_ERR_ALIGN;
+    if (!fused && !log_prior_out) return MAS_ERR_WORKSPACE;  // unfused plan needs the lp buffer
+    if (log_prior_out) {
+        const cudaError_t e = launch_log_prior(mu_x, y, log_prior_out, B, F, T_x, T_y, st);
+        if (e != cudaSuccess) return (int)e;
+    }
+    if (!fused) {
+        // operands do not fit next to the tile ring: prior to HBM once, then the drop-in kernel
+        MasArgs m{};
+        const Plan p2 = choose_plan(T_x, T_y, flags, &m.lay);
+        if (p2 == kPlanGeneral && (size_t)T_x * 16 > (size_t)kSmemBudget) return MAS_ERR_SHAPE;
+        m.value = log_prior_out;
+        m.t_x = t_x;
+        m.t_y = t_y;
+        m.path = path;
+        m.durations = durations;
+        m.score = score;
+        m.frame_idx = frame_idx;
+        m.bits_ws = static_cast<uint32_t *>(workspace);
+        m.B = B;
+        m.T_x = T_x;
+        m.T_y = T_y;
+        m.path_esize = path ? esize : 4;
+        m.one = one_pattern(path_dtype);
+        return (int)((p2 == kPlanGeneral) ? launch_general(m, MAS_F32, st) : launch_fast(m, MAS_F32, st));
+    }
+    a.mu_x = mu_x;
+    a.y = y;
+    a.t_x = t_x;
+    a.t_y = t_y;
+    a.path = path;
+    a.durations = durations;
+    a.frame_idx = frame_idx;
+    a.score = score;
+    a.bits_ws = static_cast<uint32_t *>(workspace);
+    a.B = B;
+    a.F = F;
+    a.T_x = T_x;
+    a.T_y = T_y;
+    a.path_esize = path ? esize : 4;
+    a.one = one_pattern(path_dtype);
+    return (int)launch_from_prior(a, st);
+}
+
+int mas_generate_path(const void *durations, int dur_dtype, const int32_t *t_x, const int32_t *t_y,
+                      void *path, int path_dtype, int B, int T_x, int T_y, void *stream)
+{
+    if (!durations || !path) return MAS_ERR_NULL;
+    if (!shape_ok(B, T_x, T_y)) return MAS_ERR_SHAPE;
+    if (dur_dtype != MAS_I32 && dur_dtype != MAS_F32) return MAS_ERR_DTYPE;
+    const int esize = element_size(path_dtype);
+    if (esize == 0 || path_dtype == MAS_I64) return MAS_ERR_DTYPE;
+    if ((uintptr_t)durations % 4 || (uintptr_t)path % esize || (uintptr_t)t_x % 4 ||
+        (uintptr_t)t_y % 4)
+        return MAS_ERR_ALIGN;
+    if ((size_t)(T_x + 1) * 4 > (size_t)kSmemBudget) return MAS_ERR_SHAPE;
+    if (B == 0) return MAS_OK;
+    return (int)launch_generate_path(durations, dur_dtype, t_x, t_y, path, esize,
+                                     one_pattern(path_dtype), B, T_x, T_y,
+                                     static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

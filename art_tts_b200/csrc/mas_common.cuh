@@ -1,0 +1,136 @@
+// mas_common.cuh -- device helpers shared by the MAS kernels (sm_100a only).
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/mas_b200.h"
+
+namespace mas {
+
+constexpr float kNeg = -1e9f;   // max_neg_val, core.pyx:40 (exactly representable)
+constexpr int kTileY = 32;      // frames per staged tile: one 128-byte row segment per token
+constexpr unsigned kFull = 0xffffffffu;
+
+// ---------------------------------------------------------------- mbarrier (shared::cta)
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+
+// ---------------------------------------------------------------- streaming global access
+template <typename T>
+__device__ __forceinline__ float load_as_f32(const T *p);
+
+template <>
+__device__ __forceinline__ float load_as_f32<float>(const float *p)
+{
+    float v;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+template <>
+__device__ __forceinline__ float load_as_f32<__half>(const __half *p)
+{
+    unsigned short u;
+    asm volatile("ld.global.nc.L1::no_allocate.u16 %0, [%1];" : "=h"(u) : "l"(p));
+    return __half2float(__ushort_as_half(u));
+}
+template <>
+__device__ __forceinline__ float load_as_f32<__nv_bfloat16>(const __nv_bfloat16 *p)
+{
+    unsigned short u;
+    asm volatile("ld.global.nc.L1::no_allocate.u16 %0, [%1];" : "=h"(u) : "l"(p));
+    return __uint_as_float(static_cast<uint32_t>(u) << 16);
+}
+template <>
+__device__ __forceinline__ float load_as_f32<double>(const double *p)
+{
+    double v;
+    asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return __double2float_rn(v);  // == numpy .astype(float32)
+}
+
+__device__ __forceinline__ void st_zero16(void *p)
+{
+    asm volatile("st.global.v4.u32 [%0], {%1, %1, %1, %1};" ::"l"(p), "r"(0u) : "memory");
+}
+
+// store the element "1" of the path dtype (esize bytes, bit pattern `one`)
+__device__ __forceinline__ void st_one(void *base, int64_t elem, int esize, uint64_t one)
+{
+    switch (esize) {
+    case 1: reinterpret_cast<uint8_t *>(base)[elem] = static_cast<uint8_t>(one); break;
+    case 2: reinterpret_cast<uint16_t *>(base)[elem] = static_cast<uint16_t>(one); break;
+    case 4: reinterpret_cast<uint32_t *>(base)[elem] = static_cast<uint32_t>(one); break;
+    default: reinterpret_cast<uint64_t *>(base)[elem] = one; break;
+    }
+}
+
+// Zero `nbytes` at `base` cooperatively: thread `tid` of `nthr`, touching only the slice
+// [part, part+1)/nparts of the 16-byte body (head/tail bytes are done with part 0).
+__device__ __forceinline__ void zero_fill_part(char *base, int64_t nbytes, int part, int nparts,
+                                               int tid, int nthr)
+{
+    if (nbytes <= 0) return;
+    int64_t head = (16 - (reinterpret_cast<uintptr_t>(base) & 15)) & 15;
+    if (head > nbytes) head = nbytes;
+    const int64_t body16 = (nbytes - head) >> 4;
+    const int64_t tail0 = head + (body16 << 4);
+    if (part == 0) {
+        for (int64_t i = tid; i < head; i += nthr) base[i] = 0;
+        for (int64_t i = tail0 + tid; i < nbytes; i += nthr) base[i] = 0;
+    }
+    const int64_t per = (body16 + nparts - 1) / nparts;
+    int64_t lo = per * part, hi = lo + per;
+    if (hi > body16) hi = body16;
+    char *b16 = base + head;
+    for (int64_t i = lo + tid; i < hi; i += nthr) st_zero16(b16 + (i << 4));
+}
+
+// physical float index of (token row x, frame s in tile) inside a staged tile: rows are
+// 128 B, the 16-byte chunk index is XOR-ed with (x & 7) -- the TMA SWIZZLE_128B pattern, so
+// the same consumer code reads tiles written by LDG/STS loaders and by cp.async.bulk.tensor.
+__device__ __forceinline__ int tile_index(int x, int s)
+{
+    return (x << 5) + ((((s >> 2) ^ (x & 7))) << 2) + (s & 3);
+}
+
+}  // namespace mas

@@ -1,0 +1,238 @@
+// mas_dp.cuh -- the single-warp MAS recurrence, direction-bit packing and the backtrack.
+//
+// Reference semantics being reproduced (paths relative to /root/reference/):
+//   forward   src/model/monotonic_align/core.pyx:17-30
+//   backtrack src/model/monotonic_align/core.pyx:15,32-35
+//
+// Formulation (validated against the reference kernel on CPU in
+// oracle.maximum_path_rowsweep):  one fp32 score per token lives in a register and is
+// updated once per frame,
+//     V[x] <- ((V[x-1] > V[x]) ? V[x-1] : V[x]) + value[x,y],     V[x] == -1e9 while x > y,
+// and the only thing that outlives a frame is the backtrack predicate
+//     d[x,y] = (x != 0) && (x == y || V[x,y-1] < V[x-1,y-1]).
+// A lane owns tokens x = lane + 32*j (j < XPL), so the x-1 neighbour is always one
+// shuffle away and a 32-frame tile of d packs into one 32-bit word per token without any
+// cross-lane traffic (bit s of word [chunk][x] is frame 32*chunk+s).
+#pragma once
+
+#include "mas_common.cuh"
+
+namespace mas {
+
+template <int K>
+__device__ __forceinline__ float f4_get(const float4 &v)
+{
+    if constexpr (K == 0) return v.x;
+    if constexpr (K == 1) return v.y;
+    if constexpr (K == 2) return v.z;
+    return v.w;
+}
+
+// One frame.  `v[j]` is value[x_j, y]; `bit` = 1 << (y & 31).
+template <int XPL, bool DIAG>
+__device__ __forceinline__ void dp_step(float (&V)[XPL], uint32_t (&acc)[XPL],
+                                        const float (&v)[XPL], int lane, int y, uint32_t bit)
+{
+    float r[XPL];
+#pragma unroll
+    for (int j = 0; j < XPL; ++j) r[j] = __shfl_sync(kFull, V[j], (lane + 31) & 31);
+    // token 0 has no predecessor: v_prev = 0 at the first frame, -1e9 after (core.pyx:23-27)
+    const float bnd = (y == 0) ? 0.0f : kNeg;
+#pragma unroll
+    for (int j = 0; j < XPL; ++j) {
+        const float wrap = (j == 0) ? bnd : r[j > 0 ? j - 1 : 0];  // lane 31's previous group
+        const float up = (lane == 0) ? wrap : r[j];                 // V[x-1, y-1]
+        const bool take_prev = up > V[j];                           // core.pyx:30 max()
+        const float m = take_prev ? up : V[j];
+        float nv = __fadd_rn(m, v[j]);
+        if (DIAG) nv = (lane + 32 * j <= y) ? nv : kNeg;            // x > y: not reachable yet
+        if (take_prev) acc[j] |= bit;
+        V[j] = nv;
+    }
+}
+
+// One staged tile of up to 32 frames (frames y0 .. y0+nsteps-1, y0 % 32 == 0).
+// `stage` is the swizzled [token][32 frames] tile in shared memory (see tile_index()).
+template <int XPL, bool DIAG>
+__device__ __forceinline__ void dp_tile(float (&V)[XPL], uint32_t (&acc)[XPL],
+                                        const float *__restrict__ stage, int lane, int y0,
+                                        int nsteps)
+{
+    const float *rowbase = stage + (lane << 5);
+    const int sw = lane & 7;
+#pragma unroll 1
+    for (int g = 0; g < 8; ++g) {
+        const int s0 = g << 2;
+        if (s0 >= nsteps) break;
+        float4 vv[XPL];
+#pragma unroll
+        for (int j = 0; j < XPL; ++j)
+            vv[j] = *reinterpret_cast<const float4 *>(rowbase + (j << 10) + ((g ^ sw) << 2));
+        float v[XPL];
+#pragma unroll
+        for (int j = 0; j < XPL; ++j) v[j] = f4_get<0>(vv[j]);
+        dp_step<XPL, DIAG>(V, acc, v, lane, y0 + s0, 1u << s0);
+        if (s0 + 1 < nsteps) {
+#pragma unroll
+            for (int j = 0; j < XPL; ++j) v[j] = f4_get<1>(vv[j]);
+            dp_step<XPL, DIAG>(V, acc, v, lane, y0 + s0 + 1, 2u << s0);
+        }
+        if (s0 + 2 < nsteps) {
+#pragma unroll
+            for (int j = 0; j < XPL; ++j) v[j] = f4_get<2>(vv[j]);
+            dp_step<XPL, DIAG>(V, acc, v, lane, y0 + s0 + 2, 4u << s0);
+        }
+        if (s0 + 3 < nsteps) {
+#pragma unroll
+            for (int j = 0; j < XPL; ++j) v[j] = f4_get<3>(vv[j]);
+            dp_step<XPL, DIAG>(V, acc, v, lane, y0 + s0 + 3, 8u << s0);
+        }
+    }
+}
+
+// Producer/consumer ring shared by the drop-in kernel (tiles = value) and the fused kernel
+// (tiles = log-prior computed on the fly).
+struct TileRing {
+    float *stages;       // nstages x (xrows*32) floats, 1024-byte aligned
+    uint64_t *full;      // [nstages] producers -> DP warp
+    uint64_t *empty;     // [nstages] DP warp -> producers
+    int nstages;
+    int stage_floats;    // xrows * 32
+};
+
+// Forward pass of one utterance by ONE warp.  Consumes ceil(t_y/32) tiles from the ring,
+// writes the direction words to bits[chunk*xrows + x] (shared or global memory) and
+// returns V[t_x-1, t_y-1].  Requires 1 <= t_x <= t_y and t_x <= 32*XPL.
+template <int XPL>
+__device__ __noinline__ float dp_forward(const TileRing ring, uint32_t *bits, int xrows, int tx,
+                                         int ty, int lane)
+{
+    float V[XPL];
+    uint32_t acc[XPL];
+#pragma unroll
+    for (int j = 0; j < XPL; ++j) {
+        V[j] = kNeg;
+        acc[j] = 0u;
+    }
+    const int ntiles = (ty + kTileY - 1) / kTileY;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int t = 0; t < ntiles; ++t) {
+        mbar_wait(&ring.full[stage], phase);
+        const float *tile = ring.stages + stage * ring.stage_floats;
+        const int y0 = t * kTileY;
+        const int nsteps = min(kTileY, ty - y0);
+        const bool diag = y0 < tx;  // some token x > y still exists in this tile
+        if (diag)
+            dp_tile<XPL, true>(V, acc, tile, lane, y0, nsteps);
+        else
+            dp_tile<XPL, false>(V, acc, tile, lane, y0, nsteps);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ring.empty[stage]);
+        if (++stage == ring.nstages) {
+            stage = 0;
+            phase ^= 1u;
+        }
+        // x == y always steps down (core.pyx:34 `index == y`), token 0 never does.
+        if (diag) {
+#pragma unroll
+            for (int j = 0; j < XPL; ++j)
+                if (j == t) acc[j] |= (1u << lane);
+        }
+        if (lane == 0) acc[0] = 0u;
+        uint32_t *dst = bits + (size_t)t * xrows + lane;
+#pragma unroll
+        for (int j = 0; j < XPL; ++j) {
+            dst[j << 5] = acc[j];
+            acc[j] = 0u;
+        }
+    }
+    // total alignment score sits in lane (tx-1)%32, group (tx-1)/32
+    float s = 0.0f;
+#pragma unroll
+    for (int j = 0; j < XPL; ++j)
+        if (j == ((tx - 1) >> 5)) s = V[j];
+    return __shfl_sync(kFull, s, (tx - 1) & 31);
+}
+
+// Backtrack over the packed direction words (core.pyx:32-35), executed by one lane.
+// Instead of one step per frame it jumps from token boundary to token boundary: inside a
+// 32-frame word the next decrement is the highest set bit at or below the current frame.
+// Records, per visited token, its first frame and its duration.
+__device__ __forceinline__ void backtrack_bits(const uint32_t *bits, int xrows, int tx, int ty,
+                                               int *first, int *dur)
+{
+    int idx = tx - 1, y = ty - 1, top = ty - 1;
+    while (y >= 0) {
+        const int c = y >> 5, s = y & 31;
+        const uint32_t w = (idx != 0) ? bits[(size_t)c * xrows + idx] : 0u;
+        const uint32_t m = w & (0xffffffffu >> (31 - s));
+        if (m == 0u) {
+            y = (c << 5) - 1;  // stays on this token down to the chunk start
+        } else {
+            const int ys = (c << 5) + (31 - __clz(m));
+            first[idx] = ys;
+            dur[idx] = top - ys + 1;
+            --idx;
+            y = ys - 1;
+            top = y;
+        }
+    }
+    if (top >= 0) {
+        first[idx] = 0;
+        dur[idx] = top + 1;
+    }
+}
+
+// The reference's degenerate case t_x > t_y: the band of core.pyx:18 is empty, the
+// forward pass changes nothing and the backtrack compares RAW (masked) values.  Rare, so
+// one lane simply evaluates the two cells it needs per frame (`val(x, y)`).  index never
+// reaches y or 0 here.
+template <typename ValFn>
+__device__ __forceinline__ void backtrack_degenerate(ValFn val, int tx, int ty, int *first, int *dur)
+{
+    int idx = tx - 1, top = ty - 1;
+    for (int y = ty - 1; y > 0 && idx > 0; --y) {
+        const float a = val(idx, y - 1), b = val(idx - 1, y - 1);
+        if (a < b) {
+            first[idx] = y;
+            dur[idx] = top - y + 1;
+            --idx;
+            top = y - 1;
+        }
+    }
+    if (top >= 0) {
+        first[idx] = 0;
+        dur[idx] = top + 1;
+    }
+}
+
+// After the block-wide barrier: every thread publishes durations and the 1-cells of the
+// (already zero-filled) dense path.
+__device__ __forceinline__ void write_path_ones(void *path_b, int32_t *dur_out_b, const int *first,
+                                                const int *dur, int T_x, int64_t T_y, int esize,
+                                                uint64_t one, int tid, int nthr)
+{
+    for (int x = tid; x < T_x; x += nthr) {
+        const int d = dur[x];
+        if (dur_out_b) dur_out_b[x] = d;
+        if (path_b && d > 0) {
+            const int64_t e0 = (int64_t)x * T_y + first[x];
+            for (int k = 0; k < d; ++k) st_one(path_b, e0 + k, esize, one);
+        }
+    }
+}
+
+// token index of every frame (-1 on padding) from the per-token runs
+__device__ __forceinline__ void write_frame_idx(int32_t *fi, const int *first, const int *dur,
+                                                int T_x, int ty, int T_y, int tid, int nthr)
+{
+    if (!fi) return;
+    for (int y = ty + tid; y < T_y; y += nthr) fi[y] = -1;
+    for (int x = tid; x < T_x; x += nthr) {
+        const int d = dur[x], f0 = first[x];
+        for (int k = 0; k < d; ++k) fi[f0 + k] = x;
+    }
+}
+
+}  // namespace mas

@@ -1,0 +1,79 @@
+// mas_internal.h -- host-side declarations shared by the .cu files of libmas_sm100.so.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "../../include/mas_b200.h"
+
+namespace mas {
+
+constexpr int kMaxFastTx = 512;            // single-warp DP: 16 tokens per lane
+constexpr int kSmemBudget = 227 * 1024;    // opt-in dynamic shared memory per CTA on sm_100
+constexpr int kFastThreads = 160;          // 1 DP warp + 4 staging warps
+constexpr int kGeneralThreads = 256;
+
+enum Plan { kPlanFastSmemBits = 0, kPlanFastSpillBits = 1, kPlanGeneral = 2 };
+
+struct FastLayout {       // dynamic shared memory carve-up of the fast kernels
+    int xrows;            // 32 * ceil(T_x / 32)
+    int nch;              // ceil(T_y / 32) direction words per token
+    int nstages;
+    int bits_in_smem;
+    size_t off_stages, off_bits, off_first, off_dur, off_bars, total;
+};
+
+struct MasArgs {
+    const void *value;
+    const float *cell_mask;
+    const int32_t *t_x;
+    const int32_t *t_y;
+    void *path;
+    int32_t *durations;
+    float *score;
+    int32_t *frame_idx;
+    uint32_t *bits_ws;     // workspace: [B][nch][xrows] (fast, spilled) or [B][32*nch][xw] (general)
+    int B, T_x, T_y;
+    int path_esize;
+    unsigned long long one;
+    FastLayout lay;
+};
+
+int element_size(int dtype);
+unsigned long long one_pattern(int dtype);
+Plan choose_plan(int T_x, int T_y, int flags, FastLayout *lay, size_t extra_smem = 0,
+                 int max_stages = 3);
+
+cudaError_t launch_lengths_from_mask(const void *mask, int mask_dtype, int B, int T_x, int T_y,
+                                     int64_t sb, int64_t sx, int64_t sy, int32_t *t_x, int32_t *t_y,
+                                     cudaStream_t st);
+cudaError_t launch_fast(const MasArgs &a, int value_dtype, cudaStream_t st);
+cudaError_t launch_general(const MasArgs &a, int value_dtype, cudaStream_t st);
+cudaError_t launch_generate_path(const void *dur, int dur_dtype, const int32_t *t_x,
+                                 const int32_t *t_y, void *path, int esize, unsigned long long one,
+                                 int B, int T_x, int T_y, cudaStream_t st);
+
+struct PriorArgs {
+    const float *mu_x;
+    const float *y;
+    const int32_t *t_x;
+    const int32_t *t_y;
+    void *path;
+    int32_t *durations;
+    int32_t *frame_idx;
+    float *score;
+    uint32_t *bits_ws;
+    int B, F, T_x, T_y;
+    int path_esize;
+    unsigned long long one;
+    FastLayout lay;
+};
+cudaError_t launch_from_prior(const PriorArgs &a, cudaStream_t st);
+size_t prior_extra_smem(int F, int T_x);
+cudaError_t launch_log_prior(const float *mu_x, const float *y, float *lp, int B, int F, int T_x,
+                             int T_y, cudaStream_t st);
+
+void count_launch(int n = 1);
+
+}  // namespace mas

@@ -1,0 +1,460 @@
+// mas_kernels.cu -- drop-in maximum_path kernels for sm_100a.
+//
+// Replaces maximum_path_c (src/model/monotonic_align/core.pyx:38-45) and the host glue of
+// maximum_path (src/model/monotonic_align/__init__.py:13-23) of antoinelii/art-tts.
+//
+// mas_fast_kernel   one CTA per utterance: warp 0 runs the frame-sequential recurrence on
+//                   32-frame tiles that four staging warps stream from HBM into a swizzled
+//                   shared-memory ring (coalesced along frames, band-limited), while the
+//                   same staging warps zero-fill the dense output path.  Direction bits
+//                   stay in shared memory (or spill to the workspace for long utterances);
+//                   the backtrack runs on them and the whole CTA then writes the 1-cells.
+//                   The fp32 score matrix is read exactly once and never written.
+// mas_general_kernel  size-agnostic fallback (T_x > 512): block-wide row sweep, one
+//                   __syncthreads per frame, direction bits in the workspace.
+#include "mas_dp.cuh"
+#include "mas_internal.h"
+
+namespace mas {
+
+// ------------------------------------------------------------------------------------
+// lengths from the mask (monotonic_align/__init__.py:18-21)
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ double mask_elem(const void *m, int dtype, int64_t i)
+{
+    switch (dtype) {
+    case MAS_F32: return static_cast<const float *>(m)[i];
+    case MAS_F16: return __half2float(static_cast<const __half *>(m)[i]);
+    case MAS_BF16: return __bfloat162float(static_cast<const __nv_bfloat16 *>(m)[i]);
+    case MAS_F64: return static_cast<const double *>(m)[i];
+    case MAS_I32: return static_cast<const int32_t *>(m)[i];
+    case MAS_U8: return static_cast<const uint8_t *>(m)[i];
+    default: return static_cast<double>(static_cast<const int64_t *>(m)[i]);
+    }
+}
+
+__global__ void __launch_bounds__(128) lengths_kernel(const void *mask, int dtype, int T_x, int T_y,
+                                                      int64_t sb, int64_t sx, int64_t sy,
+                                                      int32_t *t_x, int32_t *t_y)
+{
+    const int b = blockIdx.x;
+    double ax = 0.0, ay = 0.0;
+    for (int x = threadIdx.x; x < T_x; x += blockDim.x) ax += mask_elem(mask, dtype, b * sb + x * sx);
+    for (int y = threadIdx.x; y < T_y; y += blockDim.x) ay += mask_elem(mask, dtype, b * sb + y * sy);
+    __shared__ double red[2][4];
+    for (int o = 16; o > 0; o >>= 1) {
+        ax += __shfl_xor_sync(kFull, ax, o);
+        ay += __shfl_xor_sync(kFull, ay, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        red[0][threadIdx.x >> 5] = ax;
+        red[1][threadIdx.x >> 5] = ay;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        t_x[b] = static_cast<int32_t>(red[0][0] + red[0][1] + red[0][2] + red[0][3]);
+        t_y[b] = static_cast<int32_t>(red[1][0] + red[1][1] + red[1][2] + red[1][3]);
+    }
+}
+
+cudaError_t launch_lengths_from_mask(const void *mask, int mask_dtype, int B, int T_x, int T_y,
+                                     int64_t sb, int64_t sx, int64_t sy, int32_t *t_x, int32_t *t_y,
+                                     cudaStream_t st)
+{
+    lengths_kernel<<<B, 128, 0, st>>>(mask, mask_dtype, T_x, T_y, sb, sx, sy, t_x, t_y);
+    count_launch();
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------
+// fast kernel
+// ------------------------------------------------------------------------------------
+// Stage the band of tile t (frames 32t..32t+31, tokens lo..hi) into shared memory.
+// One warp per token row, lanes along frames: every global request is one contiguous
+// 128-byte segment, every shared store is conflict-free under the XOR swizzle.
+template <typename InT>
+__device__ __forceinline__ void stage_value_tile(const InT *__restrict__ vb,
+                                                 const float *__restrict__ mb, float *stage, int t,
+                                                 int tx, int ty, int64_t T_y, int hw, int nhw,
+                                                 int lane)
+{
+    const int y = t * kTileY + lane;
+    const bool in = y < ty;
+    const int lo = max(0, tx + t * kTileY - ty);
+    const int hi = min(tx - 1, t * kTileY + kTileY - 1);
+    constexpr int U = 4;
+    for (int x0 = lo + hw; x0 <= hi; x0 += U * nhw) {
+        float v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int x = x0 + u * nhw;
+            v[u] = 0.0f;
+            if (x <= hi && in) {
+                const int64_t e = (int64_t)x * T_y + y;
+                v[u] = load_as_f32(vb + e);
+                if (mb) v[u] *= __ldg(mb + e);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int x = x0 + u * nhw;
+            if (x <= hi) stage[tile_index(x, lane)] = v[u];
+        }
+    }
+}
+
+template <int XPL>
+__device__ __forceinline__ float run_forward(const TileRing &ring, uint32_t *bits, int xrows, int tx,
+                                             int ty, int lane)
+{
+    return dp_forward<XPL>(ring, bits, xrows, tx, ty, lane);
+}
+
+// dispatch on tokens-per-lane of THIS utterance (warp-uniform), bounded by the launch bucket
+template <int XPLMAX>
+__device__ __forceinline__ float forward_dispatch(const TileRing &ring, uint32_t *bits, int xrows,
+                                                  int tx, int ty, int lane)
+{
+    const int xpl = (tx + 31) >> 5;
+#define MAS_CASE(N)                                                               \
+    case N:                                                                       \
+        if constexpr (N <= XPLMAX) return run_forward<N>(ring, bits, xrows, tx, ty, lane); \
+        break;
+    switch (xpl) {
+        MAS_CASE(1) MAS_CASE(2) MAS_CASE(3) MAS_CASE(4) MAS_CASE(5) MAS_CASE(6) MAS_CASE(7)
+        MAS_CASE(8) MAS_CASE(9) MAS_CASE(10) MAS_CASE(11) MAS_CASE(12) MAS_CASE(13) MAS_CASE(14)
+        MAS_CASE(15) MAS_CASE(16)
+    default: break;
+    }
+#undef MAS_CASE
+    return 0.0f;
+}
+
+template <typename InT, int XPLMAX>
+__global__ void __launch_bounds__(kFastThreads) mas_fast_kernel(const MasArgs a)
+{
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const FastLayout &L = a.lay;
+    float *stages = reinterpret_cast<float *>(smem + L.off_stages);
+    int *first = reinterpret_cast<int *>(smem + L.off_first);
+    int *dur = reinterpret_cast<int *>(smem + L.off_dur);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + L.off_bars);
+
+    const int b = blockIdx.x;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int T_x = a.T_x;
+    const int64_t T_y = a.T_y;
+    const int tx = min(max(a.t_x[b], 0), T_x);
+    const int ty = min(max(a.t_y[b], 0), a.T_y);
+    const bool degenerate = tx > ty && ty >= 1;
+    const bool active = tx >= 1 && ty >= 1 && !degenerate;
+    const int ntiles = active ? (ty + kTileY - 1) / kTileY : 0;
+    constexpr int kHelperWarps = kFastThreads / 32 - 1;
+
+    uint32_t *bits = L.bits_in_smem
+                         ? reinterpret_cast<uint32_t *>(smem + L.off_bits)
+                         : a.bits_ws + (size_t)b * L.nch * L.xrows;
+    TileRing ring;
+    ring.stages = stages;
+    ring.full = bars;
+    ring.empty = bars + L.nstages;
+    ring.nstages = L.nstages;
+    ring.stage_floats = L.xrows * kTileY;
+
+    if (tid == 0) {
+        for (int s = 0; s < L.nstages; ++s) {
+            mbar_init(&ring.full[s], kHelperWarps);
+            mbar_init(&ring.empty[s], 1);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    const InT *vb = static_cast<const InT *>(a.value) + (int64_t)b * T_x * T_y;
+    const float *mb = a.cell_mask ? a.cell_mask + (int64_t)b * T_x * T_y : nullptr;
+
+    if (warp == 0) {
+        // ---------------- DP warp: forward recurrence + backtrack ----------------
+        for (int x = lane; x < T_x; x += 32) dur[x] = 0;
+        __syncwarp();
+        float score = 0.0f;
+        if (active) {
+            score = forward_dispatch<XPLMAX>(ring, bits, L.xrows, tx, ty, lane);
+            __syncwarp();
+            if (lane == 0) backtrack_bits(bits, L.xrows, tx, ty, first, dur);
+        } else if (degenerate) {
+            if (lane == 0) {
+                auto val = [&](int x, int y) {
+                    const int64_t e = (int64_t)x * T_y + y;
+                    float v = load_as_f32(vb + e);
+                    if (mb) v *= mb[e];
+                    return v;
+                };
+                backtrack_degenerate(val, tx, ty, first, dur);
+                score = val(tx - 1, ty - 1);  // the reference leaves value[t_x-1,t_y-1] untouched
+            }
+            score = __shfl_sync(kFull, score, 0);
+        }
+        if (lane == 0 && a.score) a.score[b] = score;
+    } else {
+        // ---------------- staging warps: HBM -> ring, and zero-fill of the output ----------------
+        const int hw = warp - 1;
+        const int htid = tid - 32;
+        constexpr int nht = kHelperWarps * 32;
+        char *pb = a.path ? static_cast<char *>(a.path) + (int64_t)b * T_x * T_y * a.path_esize
+                          : nullptr;
+        const int64_t pbytes = a.path ? (int64_t)T_x * T_y * a.path_esize : 0;
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int t = 0; t < ntiles; ++t) {
+            if (t >= L.nstages) mbar_wait(&ring.empty[stage], phase ^ 1u);
+            stage_value_tile<InT>(vb, mb, stages + stage * ring.stage_floats, t, tx, ty, T_y, hw,
+                                  kHelperWarps, lane);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ring.full[stage]);
+            if (++stage == L.nstages) {
+                stage = 0;
+                phase ^= 1u;
+            }
+            zero_fill_part(pb, pbytes, t, ntiles, htid, nht);
+        }
+        if (ntiles == 0) zero_fill_part(pb, pbytes, 0, 1, htid, nht);
+    }
+    __syncthreads();
+    write_path_ones(a.path ? static_cast<char *>(a.path) + (int64_t)b * T_x * T_y * a.path_esize
+                           : nullptr,
+                    a.durations ? a.durations + (int64_t)b * T_x : nullptr, first, dur, T_x, T_y,
+                    a.path_esize, a.one, tid, kFastThreads);
+    write_frame_idx(a.frame_idx ? a.frame_idx + (int64_t)b * T_y : nullptr, first, dur, T_x, ty,
+                    a.T_y, tid, kFastThreads);
+}
+
+template <typename InT>
+static cudaError_t launch_fast_typed(const MasArgs &a, cudaStream_t st)
+{
+    const int xplmax = (a.T_x + 31) / 32;
+    void (*k)(const MasArgs) = nullptr;
+    if constexpr (sizeof(InT) == 4) {  // fp32: register budget sized to the batch's T_x bucket
+        if (xplmax <= 2) k = mas_fast_kernel<InT, 2>;
+        else if (xplmax <= 4) k = mas_fast_kernel<InT, 4>;
+        else if (xplmax <= 6) k = mas_fast_kernel<InT, 6>;
+        else if (xplmax <= 8) k = mas_fast_kernel<InT, 8>;
+        else if (xplmax <= 12) k = mas_fast_kernel<InT, 12>;
+        else k = mas_fast_kernel<InT, 16>;
+    } else {  // fp16 / bf16 / fp64 inputs: two buckets keep the library small
+        if (xplmax <= 8) k = mas_fast_kernel<InT, 8>;
+        else k = mas_fast_kernel<InT, 16>;
+    }
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)a.lay.total);
+    if (e != cudaSuccess) return e;
+    k<<<a.B, kFastThreads, a.lay.total, st>>>(a);
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fast(const MasArgs &a, int value_dtype, cudaStream_t st)
+{
+    switch (value_dtype) {
+    case MAS_F32: return launch_fast_typed<float>(a, st);
+    case MAS_F16: return launch_fast_typed<__half>(a, st);
+    case MAS_BF16: return launch_fast_typed<__nv_bfloat16>(a, st);
+    case MAS_F64: return launch_fast_typed<double>(a, st);
+    default: return cudaErrorInvalidValue;
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// general kernel (any T_x): block-wide sweep, bits [frame][token word] in the workspace
+// ------------------------------------------------------------------------------------
+template <typename InT>
+__global__ void __launch_bounds__(kGeneralThreads) mas_general_kernel(const MasArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int T_x = a.T_x;
+    const int64_t T_y = a.T_y;
+    float *Va = reinterpret_cast<float *>(smem);
+    float *Vb = Va + T_x;
+    int *first = reinterpret_cast<int *>(Vb + T_x);
+    int *dur = first + T_x;
+
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+    const int tx = min(max(a.t_x[b], 0), T_x);
+    const int ty = min(max(a.t_y[b], 0), a.T_y);
+    const bool degenerate = tx > ty && ty >= 1;
+    const bool active = tx >= 1 && ty >= 1 && !degenerate;
+    const int xw = (T_x + 31) >> 5;
+    uint32_t *bits = a.bits_ws + (size_t)b * (size_t)a.lay.nch * 32 * xw;
+    const InT *vb = static_cast<const InT *>(a.value) + (int64_t)b * T_x * T_y;
+    const float *mb = a.cell_mask ? a.cell_mask + (int64_t)b * T_x * T_y : nullptr;
+    char *pb = a.path ? static_cast<char *>(a.path) + (int64_t)b * T_x * T_y * a.path_esize : nullptr;
+
+    for (int x = tid; x < T_x; x += kGeneralThreads) {
+        Va[x] = kNeg;
+        Vb[x] = kNeg;
+        dur[x] = 0;
+    }
+    zero_fill_part(pb, a.path ? (int64_t)T_x * T_y * a.path_esize : 0, 0, 1, tid, kGeneralThreads);
+    __syncthreads();
+
+    float *Vp = Va, *Vc = Vb;
+    if (active) {
+        for (int y = 0; y < ty; ++y) {
+            const int lo = max(0, tx + y - ty), hi = min(tx - 1, y);
+            const int xb0 = (lo >> 5) << 5;
+            for (int xb = xb0 + (tid & ~31); xb <= hi; xb += kGeneralThreads) {
+                const int x = xb + lane;
+                bool bit = false;
+                if (x >= lo && x <= hi) {
+                    const float vc = (x == y) ? kNeg : Vp[x];
+                    const float vp = (x == 0) ? ((y == 0) ? 0.0f : kNeg) : Vp[x - 1];
+                    const bool take_prev = vp > vc;
+                    const int64_t e = (int64_t)x * T_y + y;
+                    float v = load_as_f32(vb + e);
+                    if (mb) v *= mb[e];
+                    Vc[x] = __fadd_rn(take_prev ? vp : vc, v);
+                    bit = (x != 0) && (x == y || take_prev);
+                }
+                const uint32_t w = __ballot_sync(kFull, bit);
+                if (lane == 0) bits[(size_t)y * xw + (xb >> 5)] = w;
+            }
+            __syncthreads();
+            float *tmp = Vp;
+            Vp = Vc;
+            Vc = tmp;
+        }
+        if (tid == 0) {
+            if (a.score) a.score[b] = Vp[tx - 1];
+            int idx = tx - 1, top = ty - 1;
+            for (int y = ty - 1; y >= 0; --y) {
+                const uint32_t w = bits[(size_t)y * xw + (idx >> 5)];
+                if ((w >> (idx & 31)) & 1u) {
+                    first[idx] = y;
+                    dur[idx] = top - y + 1;
+                    --idx;
+                    top = y - 1;
+                }
+            }
+            if (top >= 0) {
+                first[idx] = 0;
+                dur[idx] = top + 1;
+            }
+        }
+    } else if (tid == 0) {
+        float s = 0.0f;
+        if (degenerate) {
+            auto val = [&](int x, int y) {
+                const int64_t e = (int64_t)x * T_y + y;
+                float v = load_as_f32(vb + e);
+                if (mb) v *= mb[e];
+                return v;
+            };
+            backtrack_degenerate(val, tx, ty, first, dur);
+            s = val(tx - 1, ty - 1);
+        }
+        if (a.score) a.score[b] = s;
+    }
+    __syncthreads();
+    write_path_ones(pb, a.durations ? a.durations + (int64_t)b * T_x : nullptr, first, dur, T_x, T_y,
+                    a.path_esize, a.one, tid, kGeneralThreads);
+    write_frame_idx(a.frame_idx ? a.frame_idx + (int64_t)b * T_y : nullptr, first, dur, T_x, ty,
+                    a.T_y, tid, kGeneralThreads);
+}
+
+cudaError_t launch_general(const MasArgs &a, int value_dtype, cudaStream_t st)
+{
+    const size_t smem = (size_t)a.T_x * 16;
+    void (*k)(const MasArgs) = nullptr;
+    switch (value_dtype) {
+    case MAS_F32: k = mas_general_kernel<float>; break;
+    case MAS_F16: k = mas_general_kernel<__half>; break;
+    case MAS_BF16: k = mas_general_kernel<__nv_bfloat16>; break;
+    case MAS_F64: k = mas_general_kernel<double>; break;
+    default: return cudaErrorInvalidValue;
+    }
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    k<<<a.B, kGeneralThreads, smem, st>>>(a);
+    count_launch();
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------
+// generate_path (src/model/utils.py:26-43): durations -> dense path
+// ------------------------------------------------------------------------------------
+// grid (B, nsplit): every CTA recomputes the (tiny) cumulative sum, then owns a contiguous
+// slab of token rows: zero-fills it with 16-byte stores and writes the runs of ones.
+__global__ void __launch_bounds__(256) generate_path_kernel(const void *dur_in, int dur_dtype,
+                                                            const int32_t *t_x, const int32_t *t_y,
+                                                            void *path, int esize,
+                                                            unsigned long long one, int T_x, int T_y)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    int *start = reinterpret_cast<int *>(smem);  // [T_x + 1] first frame of every token
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const int tx = t_x ? min(max(t_x[b], 0), T_x) : T_x;
+    const int ty = t_y ? min(max(t_y[b], 0), T_y) : T_y;
+    if (tid < 32) {
+        // cumsum by one warp, sequential over 32-token groups; fp32 durations are summed in
+        // fp32 left to right (== torch.cumsum on CPU), then y < cum  <=>  y < ceil(cum)
+        const int lane = tid;
+        if (dur_dtype == MAS_I32) {
+            const int32_t *d = static_cast<const int32_t *>(dur_in) + (int64_t)b * T_x;
+            int carry = 0;
+            for (int x0 = 0; x0 < T_x; x0 += 32) {
+                const int x = x0 + lane;
+                int v = (x < T_x) ? d[x] : 0;
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int n = __shfl_up_sync(kFull, v, o);
+                    if (lane >= o) v += n;
+                }
+                if (x < T_x) start[x + 1] = min(max(carry + v, 0), T_y);
+                carry += __shfl_sync(kFull, v, 31);
+            }
+        } else if (lane == 0) {
+            const float *d = static_cast<const float *>(dur_in) + (int64_t)b * T_x;
+            float cum = 0.0f;
+            for (int x = 0; x < T_x; ++x) {
+                cum += d[x];
+                const float c = ceilf(cum);
+                start[x + 1] = (c <= 0.0f) ? 0 : (c >= (float)T_y ? T_y : (int)c);
+            }
+        }
+        if (lane == 0) start[0] = 0;
+    }
+    __syncthreads();
+    const int nsplit = gridDim.y;
+    const int rows_per = (T_x + nsplit - 1) / nsplit;
+    const int x0 = blockIdx.y * rows_per, x1 = min(T_x, x0 + rows_per);
+    if (x0 >= x1) return;
+    char *pb = static_cast<char *>(path) + ((int64_t)b * T_x + x0) * (int64_t)T_y * esize;
+    zero_fill_part(pb, (int64_t)(x1 - x0) * T_y * esize, 0, 1, tid, 256);
+    __syncthreads();
+    for (int x = x0 + tid; x < x1; x += 256) {
+        if (x >= tx) continue;
+        const int f = start[x], l = min(start[x + 1], ty);
+        for (int y = f; y < l; ++y) st_one(pb, (int64_t)(x - x0) * T_y + y, esize, one);
+    }
+}
+
+cudaError_t launch_generate_path(const void *dur, int dur_dtype, const int32_t *t_x,
+                                 const int32_t *t_y, void *path, int esize, unsigned long long one,
+                                 int B, int T_x, int T_y, cudaStream_t st)
+{
+    int nsplit = 1;
+    while (B * nsplit < 296 && nsplit * 8 <= T_x) nsplit *= 2;
+    const size_t smem = (size_t)(T_x + 1) * sizeof(int);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(generate_path_kernel,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    generate_path_kernel<<<dim3(B, nsplit), 256, smem, st>>>(dur, dur_dtype, t_x, t_y, path, esize,
+                                                             one, T_x, T_y);
+    count_launch();
+    return cudaGetLastError();
+}
+
+}  // namespace mas

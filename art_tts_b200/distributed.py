@@ -1,0 +1,80 @@
+"""Batch-sharded MAS over the GPUs of one box.
+
+MAS is embarrassingly parallel over utterances (core.pyx:44-45; the reference's own DDP
+script runs one independent call per rank, train_v1_1_dist.py:249), so the data path has NO
+collective.  The only exchange is the re-assembly of results: one all-gather of the int32
+durations [B/g, T_x] (and optionally scores) over NCCL/NVLink; dense paths are rebuilt
+locally from durations with the generate_path kernel (exact, utils.py:26-43) instead of
+moving 4 B/cell across the links.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous shard [lo, hi) of n utterances for `rank` (cf. balance_batch.py:148-150);
+    the first n % world ranks get one extra utterance."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def length_bucket_order(t_x: torch.Tensor, t_y: torch.Tensor, world: int = 1) -> torch.Tensor:
+    """Permutation that sorts utterances by work (t_x*t_y, longest first) and deals them
+    round-robin to ranks, so that every contiguous shard holds the same length mix and each
+    GPU starts its longest utterances first (LPT).  Returns int64 indices [B]."""
+    work = t_x.to(torch.int64) * t_y.to(torch.int64)
+    order = torch.argsort(work, descending=True, stable=True)
+    if world <= 1:
+        return order
+    n = order.numel()
+    parts = [order[r::world] for r in range(world)]
+    # shard_bounds gives the first n%world ranks one more element: same as the strided deal
+    assert sum(p.numel() for p in parts) == n
+    return torch.cat(parts)
+
+
+def all_gather_rows(local: torch.Tensor, n_total: int, group: Optional[dist.ProcessGroup] = None
+                    ) -> torch.Tensor:
+    """All-gather row-shards of unequal size (differing by at most one row) into [n_total, ...].
+    Uses one all_gather_into_tensor on padded shards (NCCL all-gather over NVLink on GPUs)."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    per = (n_total + world - 1) // world
+    lo, hi = shard_bounds(n_total, rank, world)
+    assert local.shape[0] == hi - lo, (local.shape, lo, hi)
+    pad = local
+    if local.shape[0] != per:
+        pad = local.new_zeros((per,) + tuple(local.shape[1:]))
+        pad[: local.shape[0]] = local
+    out = local.new_empty((world * per,) + tuple(local.shape[1:]))
+    dist.all_gather_into_tensor(out, pad.contiguous(), group=group)
+    if n_total == world * per:
+        return out
+    pieces = []
+    for r in range(world):
+        rlo, rhi = shard_bounds(n_total, r, world)
+        pieces.append(out[r * per: r * per + (rhi - rlo)])
+    return torch.cat(pieces)
+
+
+def maximum_path_from_prior_sharded(mu_x, y, t_x, t_y, *, group=None, rebuild_path=False):
+    """Every rank holds the FULL batch description (or just its shard, see below), computes MAS
+    for its contiguous shard and all-gathers durations.  Returns (durations [B,T_x] int32 for
+    the whole batch, local path for the shard, optional rebuilt global path)."""
+    from . import monotonic_align, utils
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    B = mu_x.shape[0]
+    lo, hi = shard_bounds(B, rank, world)
+    path, dur = monotonic_align.maximum_path_from_prior(mu_x[lo:hi], None, y[lo:hi], t_x[lo:hi],
+                                                        t_y[lo:hi])
+    dur_all = all_gather_rows(dur, B, group)
+    full = None
+    if rebuild_path:
+        full = utils.generate_path_lengths(dur_all, t_x, t_y, y.shape[2], out_dtype=mu_x.dtype)
+    return dur_all, path, full

@@ -1,0 +1,192 @@
+"""B200-native drop-in for art-tts's `model.monotonic_align`.
+
+Mirrors the reference module's surface (src/model/monotonic_align/__init__.py:8-23):
+
+    maximum_path(value, mask) -> path            same shape, dtype and device semantics
+
+and adds the fused entry point that replaces the log-prior block of
+GradTTS/ArtTTS.compute_loss (src/model/tts.py:483-505):
+
+    maximum_path_from_prior(mu_x, logs, y, x_mask, y_mask) -> (path, durations)
+
+Everything runs in hand-written sm_100a kernels behind the C ABI of include/mas_b200.h;
+PyTorch only provides device memory and the current stream.  No host synchronisation, no
+D2H/H2D copies, no CPU fallback.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from .. import _lib
+
+__all__ = [
+    "maximum_path",
+    "maximum_path_lengths",
+    "maximum_path_from_prior",
+    "lengths_from_mask",
+]
+
+_FLOAT_VALUE = (torch.float32, torch.float16, torch.bfloat16, torch.float64)
+
+
+def lengths_from_mask(mask: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """t_x = mask.sum(1)[:, 0], t_y = mask.sum(2)[:, 0] as int32 (reference __init__.py:18-21).
+
+    Reads one column and one row of each utterance's mask through its strides (no copy)."""
+    if mask.dim() != 3:
+        raise ValueError(f"mask must be [B, T_x, T_y], got {tuple(mask.shape)}")
+    _lib.require_cuda(mask, "mask")
+    B, T_x, T_y = mask.shape
+    t_x = torch.empty(B, dtype=torch.int32, device=mask.device)
+    t_y = torch.empty(B, dtype=torch.int32, device=mask.device)
+    if B == 0:
+        return t_x, t_y
+    lib = _lib.load()
+    with torch.cuda.device(mask.device):
+        sb, sx, sy = mask.stride()
+        code = lib.mas_lengths_from_mask(_lib.ptr(mask), _lib.dtype_code(mask.dtype), B, T_x, T_y,
+                                         sb, sx, sy, _lib.ptr(t_x), _lib.ptr(t_y),
+                                         _lib.stream_ptr(mask.device))
+    _lib.check(code, "mas_lengths_from_mask")
+    return t_x, t_y
+
+
+def maximum_path_lengths(value: torch.Tensor, t_x: torch.Tensor, t_y: torch.Tensor, *,
+                         out_dtype: Optional[torch.dtype] = None,
+                         cell_mask: Optional[torch.Tensor] = None,
+                         return_durations: bool = False, return_score: bool = False,
+                         want_path: bool = True, flags: int = 0):
+    """MAS on `value [B,T_x,T_y]` with explicit int32 lengths (core.pyx:38-45 semantics).
+
+    Returns path (dtype `out_dtype`, default value.dtype), then optionally durations
+    (int32 [B,T_x]) and score (fp32 [B]) in that order."""
+    if value.dim() != 3:
+        raise ValueError(f"value must be [B, T_x, T_y], got {tuple(value.shape)}")
+    _lib.require_cuda(value, "value")
+    if value.dtype not in _FLOAT_VALUE:
+        raise TypeError(f"value must be a floating tensor, got {value.dtype}")
+    B, T_x, T_y = value.shape
+    dev = value.device
+    out_dtype = out_dtype or value.dtype
+    value = value.contiguous()
+    t_x = t_x.to(device=dev, dtype=torch.int32).contiguous()
+    t_y = t_y.to(device=dev, dtype=torch.int32).contiguous()
+    if t_x.numel() != B or t_y.numel() != B:
+        raise ValueError("t_x and t_y must have one entry per utterance")
+    if cell_mask is not None:
+        if cell_mask.shape != value.shape:
+            raise ValueError("cell_mask must have value's shape")
+        cell_mask = cell_mask.to(device=dev, dtype=torch.float32).contiguous()
+    path = torch.empty((B, T_x, T_y), dtype=out_dtype, device=dev) if want_path else None
+    dur = torch.empty((B, T_x), dtype=torch.int32, device=dev) if return_durations else None
+    score = torch.empty((B,), dtype=torch.float32, device=dev) if return_score else None
+    if B > 0 and T_x > 0 and T_y > 0:
+        lib = _lib.load()
+        with torch.cuda.device(dev):
+            nws = int(lib.mas_workspace_bytes(B, T_x, T_y))
+            ws = _lib.workspace(dev, nws) if lib.mas_plan(B, T_x, T_y, flags) != 0 else None
+            code = lib.mas_maximum_path(
+                _lib.ptr(value), _lib.dtype_code(value.dtype), _lib.ptr(cell_mask), _lib.ptr(t_x),
+                _lib.ptr(t_y), _lib.ptr(path), _lib.dtype_code(out_dtype), _lib.ptr(dur),
+                _lib.ptr(score), B, T_x, T_y, _lib.ptr(ws), ws.numel() if ws is not None else 0,
+                flags, _lib.stream_ptr(dev))
+        _lib.check(code, "mas_maximum_path")
+    out = [path] if want_path else []
+    if return_durations:
+        out.append(dur)
+    if return_score:
+        out.append(score)
+    return out[0] if len(out) == 1 else tuple(out)
+
+
+def maximum_path(value: torch.Tensor, mask: torch.Tensor, *, strict_mask: bool = False):
+    """Drop-in for the reference's `maximum_path(value, mask)` (__init__.py:8-23).
+
+    value: [b, t_x, t_y] float tensor on a CUDA device;  mask: [b, t_x, t_y] 0/1.
+    Returns the hard monotonic alignment [b, t_x, t_y] with entries {0,1}, in the dtype of
+    `value * mask` and on value's device -- bit-exact with the reference's Cython kernel.
+
+    The reference multiplies every cell by the mask and reads the lengths from the mask's
+    first column/row.  For the rectangular sequence masks its callers build
+    (tts.py:477-480: x_mask[..., None] * y_mask[:, :, None]) the multiplication is the
+    identity on every cell the algorithm touches, so by default only that column and row of
+    the mask are read (8 B/cell of HBM traffic instead of 12).  Pass strict_mask=True to
+    apply the mask per cell as well (needed only for masks with holes)."""
+    if value.shape != mask.shape:
+        raise ValueError(f"value {tuple(value.shape)} and mask {tuple(mask.shape)} differ")
+    _lib.require_cuda(value, "value")
+    mask = mask.to(value.device)
+    out_dtype = torch.result_type(value, mask)  # dtype of `value * mask`
+    if out_dtype not in _FLOAT_VALUE:
+        raise TypeError(f"value * mask has dtype {out_dtype}; a floating dtype is required")
+    t_x, t_y = lengths_from_mask(mask)
+    cell_mask = None
+    if strict_mask:
+        if value.dtype == torch.float32 and mask.dtype == torch.float32:
+            cell_mask = mask
+        else:  # exact promotion semantics of `value * mask` for mixed dtypes
+            value = value * mask
+    if value.dtype not in _FLOAT_VALUE:
+        value = value.to(out_dtype)
+    return maximum_path_lengths(value, t_x, t_y, out_dtype=out_dtype, cell_mask=cell_mask)
+
+
+def maximum_path_from_prior(mu_x: torch.Tensor, logs: Optional[torch.Tensor], y: torch.Tensor,
+                            x_mask: torch.Tensor, y_mask: torch.Tensor, *,
+                            return_score: bool = False, return_frame_idx: bool = False,
+                            return_log_prior: bool = False, want_path: bool = True,
+                            flags: int = 0):
+    """Fused Gaussian log-prior + MAS + durations (replaces tts.py:483-505).
+
+    mu_x [B,F,T_x], y [B,F,T_y] fp32;  x_mask [B,1,T_x], y_mask [B,1,T_y] 0/1 sequence masks
+    (or int lengths [B]).  `logs` must be None: the reference's prior has unit variance.
+    Returns (path [B,T_x,T_y] in mu_x.dtype, durations [B,T_x] int32), followed by the
+    optional extras in the order score [B] fp32, frame_idx [B,T_y] int32, log_prior."""
+    if logs is not None:
+        raise NotImplementedError("the reference has a unit-variance prior only (logs=None)")
+    if mu_x.dim() != 3 or y.dim() != 3 or mu_x.shape[:2] != y.shape[:2]:
+        raise ValueError("mu_x must be [B,F,T_x] and y [B,F,T_y]")
+    _lib.require_cuda(mu_x, "mu_x")
+    _lib.require_cuda(y, "y")
+    dev = mu_x.device
+    B, F, T_x = mu_x.shape
+    T_y = y.shape[2]
+    out_dtype = mu_x.dtype
+    mu32 = mu_x.detach().to(torch.float32).contiguous()
+    y32 = y.detach().to(torch.float32).contiguous()
+
+    def lengths(m, T):
+        if m.dim() == 1:
+            return m.to(device=dev, dtype=torch.int32).contiguous()
+        m2 = m.reshape(B, -1)
+        if m2.shape[1] != T:
+            raise ValueError("mask length does not match the tensor it masks")
+        return m2.to(device=dev).sum(1).to(torch.int32)
+
+    t_x = lengths(x_mask, T_x)
+    t_y = lengths(y_mask, T_y)
+    path = torch.empty((B, T_x, T_y), dtype=out_dtype, device=dev) if want_path else None
+    dur = torch.empty((B, T_x), dtype=torch.int32, device=dev)
+    score = torch.empty((B,), dtype=torch.float32, device=dev) if return_score else None
+    fidx = torch.empty((B, T_y), dtype=torch.int32, device=dev) if return_frame_idx else None
+    lp = None
+    if B > 0 and T_x > 0 and T_y > 0:
+        lib = _lib.load()
+        unfused = lib.mas_from_prior_plan(B, F, T_x, T_y, flags) != 0
+        if return_log_prior or unfused:
+            lp = torch.empty((B, T_x, T_y), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            nws = int(lib.mas_workspace_bytes(B, T_x, T_y))
+            ws = _lib.workspace(dev, nws)
+            code = lib.mas_from_prior_f32(
+                _lib.ptr(mu32), None, _lib.ptr(y32), _lib.ptr(t_x), _lib.ptr(t_y), _lib.ptr(path),
+                _lib.dtype_code(out_dtype), _lib.ptr(dur), _lib.ptr(fidx), _lib.ptr(score),
+                _lib.ptr(lp), B, F, T_x, T_y, _lib.ptr(ws), ws.numel(), flags, _lib.stream_ptr(dev))
+        _lib.check(code, "mas_from_prior_f32")
+    out = [path, dur] if want_path else [dur]
+    for flag, t in ((return_score, score), (return_frame_idx, fidx), (return_log_prior, lp)):
+        if flag:
+            out.append(t)
+    return tuple(out) if len(out) > 1 else out[0]

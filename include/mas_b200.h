@@ -1,0 +1,162 @@
+/*
+ * mas_b200.h -- C ABI of libmas_sm100.so: Monotonic Alignment Search for B200 (sm_100a).
+ *
+ * This is the drop-in boundary for ONE path of antoinelii/art-tts (paths relative to the
+ * reference tree):
+ *
+ *   log_prior(mu_x, y) -> monotonic_align.maximum_path(value, mask) -> path -> durations
+ *
+ * Every entry point below names the reference interface it replaces.  Conventions:
+ *   - all pointers are DEVICE pointers unless the name says `host`; the library never
+ *     allocates, frees or keeps them; inputs are never modified (the reference clobbers
+ *     its private host copy of `value`, core.pyx:30);
+ *   - tensors are dense, C-contiguous, innermost axis = frames (T_y), exactly the
+ *     memoryview layout of core.pyx:40 (`float[:,:,::1]`);
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued asynchronously on
+ *     it, nothing synchronises the host, every call is CUDA-graph capturable;
+ *   - return value: 0 = ok, <0 = MAS_ERR_* (argument errors, detected on the host before
+ *     any launch), >0 = cudaError_t of the failed launch.  Nothing throws across the ABI.
+ */
+#ifndef MAS_B200_H
+#define MAS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MAS_ABI_VERSION 1
+
+/* element types accepted for value / mask / path tensors */
+enum {
+    MAS_F32 = 0,
+    MAS_F16 = 1,
+    MAS_BF16 = 2,
+    MAS_F64 = 3,
+    MAS_I32 = 4,
+    MAS_U8 = 5, /* also torch.bool */
+    MAS_I64 = 6
+};
+
+enum {
+    MAS_OK = 0,
+    MAS_ERR_NULL = -1,      /* a required pointer is NULL                          */
+    MAS_ERR_SHAPE = -2,     /* B, T_x, T_y or F out of range                       */
+    MAS_ERR_DTYPE = -3,     /* unsupported element type for this argument          */
+    MAS_ERR_WORKSPACE = -4, /* workspace missing or smaller than *_workspace_bytes */
+    MAS_ERR_ALIGN = -5,     /* pointer not aligned to its element size             */
+    MAS_ERR_NO_DEVICE = -6  /* no sm_100 device / driver available                 */
+};
+
+/* flags for mas_maximum_path / mas_from_prior_f32 */
+enum {
+    MAS_FLAG_NONE = 0,
+    MAS_FLAG_FORCE_GENERAL = 1, /* use the size-agnostic kernel even when the fast one fits */
+    MAS_FLAG_NO_TMA = 2         /* fast kernel: stage tiles with LDG/STS instead of TMA      */
+};
+
+int mas_abi_version(void);
+const char *mas_strerror(int code);
+
+/*
+ * Lengths from a mask -- replaces monotonic_align/__init__.py:18-21
+ *     t_x_max = mask.sum(1)[:, 0];  t_y_max = mask.sum(2)[:, 0]
+ * Reads only column 0 and row 0 of each utterance's mask (element strides given in
+ * elements, so views such as attn_mask.squeeze(1) need no copy).  Sums are truncated to
+ * int32 like `.astype(np.int32)`.
+ */
+int mas_lengths_from_mask(const void *mask, int mask_dtype, int B, int T_x, int T_y,
+                          int64_t stride_b, int64_t stride_x, int64_t stride_y,
+                          int32_t *t_x_out, int32_t *t_y_out, void *stream);
+
+/*
+ * Bytes of scratch mas_maximum_path / mas_from_prior_f32 need for this shape (packed
+ * 1-bit-per-cell direction mask when it does not fit in shared memory, plus scheduling
+ * state).  Never 0, so one allocation can be reused for every call of the same shape.
+ */
+size_t mas_workspace_bytes(int B, int T_x, int T_y);
+
+/*
+ * The drop-in kernel -- replaces maximum_path_c (core.pyx:38-45) together with the host
+ * glue of maximum_path (monotonic_align/__init__.py:13-23).
+ *
+ *   value      [B,T_x,T_y]  value_dtype in {F32,F16,BF16,F64}; converted to fp32 on load
+ *                           (== `.astype(np.float32)`, __init__.py:16)
+ *   cell_mask  NULL, or [B,T_x,T_y] fp32 0/1: each value is multiplied by it on load
+ *              (`value * mask`, __init__.py:13) -- only needed for masks that are not
+ *              rectangular; for the sequence masks the reference builds (tts.py:477-480)
+ *              the product is the identity on every cell the algorithm reads.
+ *   t_x, t_y   [B] int32 lengths (from mas_lengths_from_mask).  t_x<=0 or t_y<=0: the
+ *              utterance's path is all zeros.  t_x>t_y (the reference's degenerate case:
+ *              empty band, backtrack over raw values) is reproduced exactly.
+ *   path       [B,T_x,T_y]  path_dtype in {F32,F16,BF16,F64,I32,U8}; receives 0/1, padding
+ *              included (== the zero-initialised int32 path cast to value.dtype, :17,:23)
+ *   durations  NULL or [B,T_x] int32: sum_y path (tts.py:503-505), free by-product
+ *   score      NULL or [B] fp32: V[t_x-1,t_y-1], the total alignment log-likelihood
+ *
+ * Arithmetic is the reference's: fp32 compare-select + one fp32 add per cell,
+ * max_neg_val = -1e9f, strict `<` in the backtrack (ties stay on the current token).
+ */
+int mas_maximum_path(const void *value, int value_dtype, const float *cell_mask,
+                     const int32_t *t_x, const int32_t *t_y, void *path, int path_dtype,
+                     int32_t *durations, float *score, int B, int T_x, int T_y,
+                     void *workspace, size_t workspace_bytes, int flags, void *stream);
+
+/*
+ * Fused Gaussian log-prior + MAS -- replaces the block GradTTS.compute_loss runs under
+ * torch.no_grad() (tts.py:483-500; identical copies at :200-214, :776-790, :1067-1081)
+ * plus the duration sum of tts.py:503-505.  The [T_x,T_y] fp32 score matrix never
+ * exists in HBM.
+ *
+ *   mu_x  [B,F,T_x] fp32, y [B,F,T_y] fp32 (layouts of text_encoder.py:432 / the collate)
+ *   logs  must be NULL: the reference has a unit-variance prior only
+ *   lp[x,j] = -0.5*sum_f y^2 + sum_f mu*y - 0.5*sum_f mu^2 - 0.5*F*log(2*pi)   (fp32)
+ *   path       NULL or [B,T_x,T_y] in path_dtype
+ *   durations  NULL or [B,T_x] int32
+ *   frame_idx  NULL or [B,T_y] int32: token index of every frame, -1 on padding
+ *   score      NULL or [B] fp32
+ *   log_prior_out  NULL or [B,T_x,T_y] fp32: parity tap -- the prior written by a separate
+ *              kernel with the same operation order as the fused producers (bit-identical)
+ */
+int mas_from_prior_f32(const float *mu_x, const float *logs, const float *y,
+                       const int32_t *t_x, const int32_t *t_y, void *path, int path_dtype,
+                       int32_t *durations, int32_t *frame_idx, float *score,
+                       float *log_prior_out, int B, int F, int T_x, int T_y,
+                       void *workspace, size_t workspace_bytes, int flags, void *stream);
+
+/*
+ * 0 when mas_from_prior_f32 runs fused for this shape; 1 when mu_x (F*T_x floats) does not
+ * fit in shared memory next to the tile ring, in which case the prior is written once to
+ * `log_prior_out` (then REQUIRED, used as scratch) and the drop-in kernel consumes it.
+ */
+int mas_from_prior_plan(int B, int F, int T_x, int T_y, int flags);
+
+/*
+ * Durations -> path -- replaces generate_path (src/model/utils.py:26-43 and
+ * src/model_ms/utils.py:20-37) for rectangular masks:
+ *   path[b,x,y] = (cum[x-1] <= y < cum[x]) && x < t_x[b] && y < t_y[b],  cum = cumsum(dur)
+ * durations: [B,T_x], dur_dtype MAS_I32 or MAS_F32 (the reference passes the fp32 tensor
+ * ceil(w)*length_scale, tts.py:132,146; fp32 sums run left to right like torch.cumsum on
+ * the CPU and `y < cum` is evaluated as y < ceil(cum)).  t_x / t_y may be NULL (= full).
+ * Also used to rebuild dense paths from all-gathered durations.
+ */
+int mas_generate_path(const void *durations, int dur_dtype, const int32_t *t_x,
+                      const int32_t *t_y, void *path, int path_dtype, int B, int T_x, int T_y,
+                      void *stream);
+
+/*
+ * Which kernel a shape dispatches to (for tests, bench and DESIGN.md):
+ * 0 = fast single-warp-DP kernel with bits in shared memory, 1 = fast kernel with the
+ * direction mask spilled to the workspace, 2 = general kernel.
+ */
+int mas_plan(int B, int T_x, int T_y, int flags);
+
+/* Kernel launches enqueued by this library in this process (bench.py's gpu_launches). */
+uint64_t mas_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MAS_B200_H */

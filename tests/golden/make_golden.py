@@ -1,0 +1,244 @@
+"""Generate tests/golden/*.npz by RUNNING THE REFERENCE ITSELF (build container only).
+
+Needs /root/reference (read-only) and oracle/_ref (built by oracle/build_ref.py from the
+reference's own core.pyx).  The reference's Python files are never copied into the repo: a
+throw-away shim package under a temp dir symlinks them next to the compiled kernel so that
+`from model import monotonic_align, GradTTS, ArtTTS` works exactly as in the reference.
+
+Outputs (committed):
+  mas_small.npz      explicit value/mask inputs + reference paths for edge cases
+                     (ragged, ties, t_x=1, t_x=t_y, degenerate t_x>t_y, fp16/fp64 dtypes)
+  mas_seeded.npz     larger seeded cases: seed recipe + sha256 of the inputs + reference
+                     durations/score (the path is rebuilt from durations in the tests)
+  prior_gradtts.npz  GradTTS(params_v2) random-init compute_loss: captured mu_x, y, log_prior,
+                     attn durations, dur_loss, prior_loss        (F=80, tts.py:450-563)
+  prior_arttts.npz   ArtTTS(params_v1) same capture              (F=16, tts.py:160-290)
+
+Run:  python tests/golden/make_golden.py
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+import shutil
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+REF_SRC = "/root/reference/src"
+
+
+def make_shim() -> str:
+    from oracle import build_ref
+
+    assert build_ref.build(), "oracle/_ref could not be built"
+    tmp = tempfile.mkdtemp(prefix="ref_shim_")
+    model = os.path.join(tmp, "model")
+    os.makedirs(os.path.join(model, "monotonic_align"))
+    for name in os.listdir(os.path.join(REF_SRC, "model")):
+        src = os.path.join(REF_SRC, "model", name)
+        if name == "monotonic_align" or name.startswith("__pycache__"):
+            continue
+        os.symlink(src, os.path.join(model, name))
+    os.symlink(os.path.join(REF_SRC, "model", "monotonic_align", "__init__.py"),
+               os.path.join(model, "monotonic_align", "__init__.py"))
+    shutil.copy(build_ref.ref_so("serial"), os.path.join(model, "monotonic_align"))
+    os.symlink(os.path.join(REF_SRC, "configs"), os.path.join(tmp, "configs"))
+    return tmp
+
+
+def seeded_case(seed, B, T_x, T_y, kind):
+    """Input recipe shared with tests/conftest.py::seeded_case (keep in sync)."""
+    rng = np.random.default_rng(seed)
+    if kind == "ljs":
+        value = -(rng.random((B, T_x, T_y), dtype=np.float32) * 100 + 50)
+        t_x = rng.integers(min(60, T_x), T_x + 1, B).astype(np.int32)
+        t_y = np.minimum(T_y, 4 * t_x + rng.integers(0, 100, B)).astype(np.int32)
+        t_x[0], t_y[0] = T_x, T_y
+    elif kind == "full":  # config 4 style, all full length
+        value = rng.standard_normal((B, T_x, T_y), dtype=np.float32) * 5 - 100
+        t_x = np.full(B, T_x, np.int32)
+        t_y = np.full(B, T_y, np.int32)
+    elif kind == "ties":  # integer-valued scores: many exact ties
+        value = rng.integers(-3, 1, (B, T_x, T_y)).astype(np.float32)
+        t_x = rng.integers(1, T_x + 1, B).astype(np.int32)
+        t_y = np.maximum(t_x, rng.integers(1, T_y + 1, B)).astype(np.int32)
+        t_y = np.minimum(t_y, T_y).astype(np.int32)
+        t_x = np.minimum(t_x, t_y).astype(np.int32)
+    else:
+        raise ValueError(kind)
+    return value, t_x, t_y
+
+
+def rect_mask(t_x, t_y, T_x, T_y, dtype=np.float32):
+    m = (np.arange(T_x)[None, :, None] < t_x[:, None, None]) & \
+        (np.arange(T_y)[None, None, :] < t_y[:, None, None])
+    return m.astype(dtype)
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def main():
+    shim = make_shim()
+    sys.path.insert(0, shim)
+    import torch
+    from model import monotonic_align  # the reference's own wrapper + compiled kernel
+
+    def ref_path(value, mask):
+        return monotonic_align.maximum_path(torch.from_numpy(value), torch.from_numpy(mask)).numpy()
+
+    # ---------------------------------------------------------------- mas_small
+    out = {}
+    rng = np.random.default_rng(1234)
+    cases = []
+    # (name, B, T_x, T_y, t_x list or None, t_y list or None, value kind)
+    v = rng.standard_normal((6, 12, 40)).astype(np.float32) * 3 - 5
+    cases.append(("ragged", v, np.array([12, 7, 1, 12, 5, 9], np.int32),
+                  np.array([40, 23, 9, 12, 5, 33], np.int32)))
+    cases.append(("all_ties", np.zeros((1, 3, 6), np.float32), np.array([3], np.int32),
+                  np.array([6], np.int32)))
+    v = rng.integers(-2, 1, (5, 37, 70)).astype(np.float32)
+    cases.append(("int_ties", v, np.array([37, 33, 32, 31, 2], np.int32),
+                  np.array([70, 64, 33, 31, 65], np.int32)))
+    v = rng.standard_normal((4, 9, 5)).astype(np.float32)
+    cases.append(("degenerate_tx_gt_ty", v, np.array([9, 6, 5, 2], np.int32),
+                  np.array([5, 3, 5, 1], np.int32)))
+    v = rng.standard_normal((3, 70, 131)).astype(np.float32) * 10
+    cases.append(("wide_unaligned", v, np.array([70, 65, 33], np.int32),
+                  np.array([131, 97, 129], np.int32)))
+    v = (rng.standard_normal((2, 20, 48)) * 4).astype(np.float16)
+    cases.append(("fp16", v, np.array([20, 11], np.int32), np.array([48, 30], np.int32)))
+    v = (rng.standard_normal((2, 20, 48)) * 4).astype(np.float64)
+    cases.append(("fp64", v, np.array([20, 11], np.int32), np.array([48, 30], np.int32)))
+    v = rng.standard_normal((2, 8, 16)).astype(np.float32)
+    cases.append(("zero_len_frames", v, np.array([8, 3], np.int32), np.array([16, 0], np.int32)))
+    names = []
+    for name, value, t_x, t_y in cases:
+        B, T_x, T_y = value.shape
+        mask = rect_mask(t_x, t_y, T_x, T_y, value.dtype)
+        # NB "zero_len_frames": an empty utterance has an all-zero mask, so the reference
+        # derives t_x = t_y = 0 from it and writes nothing.
+        path = ref_path(value, mask)
+        assert path.dtype == value.dtype
+        out[f"{name}.value"] = value
+        out[f"{name}.mask"] = mask
+        out[f"{name}.path"] = path
+        names.append(name)
+    # a non-rectangular mask (holes inside the rectangle): per-cell multiply matters
+    v = rng.standard_normal((2, 10, 30)).astype(np.float32) - 1
+    m = rect_mask(np.array([10, 6], np.int32), np.array([30, 17], np.int32), 10, 30)
+    holes = rng.random(m.shape) < 0.15
+    holes[:, :, 0] = False
+    holes[:, 0, :] = False
+    m = (m * ~holes).astype(np.float32)
+    out["holes.value"], out["holes.mask"], out["holes.path"] = v, m, ref_path(v, m)
+    names.append("holes")
+    out["names"] = np.array(names)
+    np.savez_compressed(os.path.join(HERE, "mas_small.npz"), **out)
+
+    # ---------------------------------------------------------------- mas_seeded
+    out = {}
+    recipes = [("cfg1_ljs", 0, 16, 190, 870, "ljs"),
+               ("cfg1_ljs_872", 10, 8, 190, 872, "ljs"),
+               ("cfg4_long", 4, 2, 512, 4096, "full"),
+               ("ties_mid", 7, 12, 100, 300, "ties"),
+               ("xpl_edges", 8, 10, 257, 600, "ljs"),
+               ("tx_1024", 9, 2, 1024, 1500, "full")]
+    for name, seed, B, T_x, T_y, kind in recipes:
+        value, t_x, t_y = seeded_case(seed, B, T_x, T_y, kind)
+        mask = rect_mask(t_x, t_y, T_x, T_y)
+        # the reference clobbers its private copy of value; recover the score from a re-run
+        from oracle import ref as oref
+        vv = np.ascontiguousarray(value * mask)
+        pp = np.zeros(vv.shape, np.int32)
+        oref.maximum_path_c(pp, vv, t_x, t_y)
+        path = ref_path(value, mask)
+        assert np.array_equal(pp, path.astype(np.int32))
+        score = np.array([vv[b, t_x[b] - 1, t_y[b] - 1] for b in range(B)], np.float32)
+        out[f"{name}.recipe"] = np.array([seed, B, T_x, T_y], np.int64)
+        out[f"{name}.kind"] = np.array(kind)
+        out[f"{name}.value_sha256"] = np.array(sha(value))
+        out[f"{name}.t_x"], out[f"{name}.t_y"] = t_x, t_y
+        out[f"{name}.durations"] = path.sum(-1).astype(np.int32)
+        out[f"{name}.score"] = score
+        out[f"{name}.path_sha256"] = np.array(sha(path.astype(np.uint8)))
+    out["names"] = np.array([r[0] for r in recipes])
+    np.savez_compressed(os.path.join(HERE, "mas_seeded.npz"), **out)
+
+    # ---------------------------------------------------------------- prior (full models)
+    import importlib
+    from model import ArtTTS, GradTTS
+
+    captured = {}
+    real_mp = monotonic_align.maximum_path
+
+    def spy(value, mask):
+        captured["log_prior"] = value.detach().clone()
+        captured["mask"] = mask.detach().clone()
+        path = real_mp(value, mask)
+        captured["attn"] = path.detach().clone()
+        return path
+
+    def capture(model, x, x_lengths, y, y_lengths, fname, extra):
+        enc_out = {}
+        h = model.encoder.register_forward_hook(lambda m, i, o: enc_out.update(mu_x=o[0], logw=o[1],
+                                                                                x_mask=o[2]))
+        monotonic_align.maximum_path = spy
+        model.eval()  # dropout off: mu_x must be reproducible from the hook only
+        torch.manual_seed(99)
+        with torch.no_grad():
+            dur_loss, prior_loss, diff_loss = model.compute_loss(x, x_lengths, y, y_lengths,
+                                                                 out_size=None)
+        monotonic_align.maximum_path = real_mp
+        h.remove()
+        attn = captured["attn"].numpy()
+        np.savez_compressed(
+            os.path.join(HERE, fname),
+            mu_x=enc_out["mu_x"].detach().numpy(), logw=enc_out["logw"].detach().numpy(),
+            x_mask=enc_out["x_mask"].detach().numpy(), y=y.numpy(),
+            x_lengths=x_lengths.numpy().astype(np.int32), y_lengths=y_lengths.numpy().astype(np.int32),
+            log_prior=captured["log_prior"].numpy(), durations=attn.sum(-1).astype(np.int32),
+            attn_packed=np.packbits(attn.astype(np.uint8), axis=-1),
+            dur_loss=np.float32(dur_loss.item()), prior_loss=np.float32(prior_loss.item()), **extra)
+
+    p2 = importlib.import_module("configs.params_v2")
+    torch.manual_seed(p2.random_seed)
+    n_vocab = 149
+    g = GradTTS(n_vocab, p2.n_spks, p2.spk_emb_dim, p2.n_enc_channels, p2.filter_channels,
+                p2.filter_channels_dp, p2.n_heads, p2.n_enc_layers, p2.enc_kernel, p2.enc_dropout,
+                p2.window_size, p2.n_feats, p2.dec_dim, p2.beta_min, p2.beta_max, p2.pe_scale)
+    B, T_x, T_y = 4, 40, 160
+    x_lengths = torch.tensor([40, 31, 17, 36])
+    y_lengths = torch.tensor([160, 130, 80, 151])
+    x = torch.randint(0, n_vocab, (B, T_x))
+    y = torch.randn(B, p2.n_feats, T_y) * (torch.arange(T_y)[None, None, :] < y_lengths[:, None, None])
+    capture(g, x, x_lengths, y, y_lengths, "prior_gradtts.npz", {"x_tokens": x.numpy()})
+
+    p1 = importlib.import_module("configs.params_v1")
+    torch.manual_seed(p1.random_seed)
+    a = ArtTTS(p1.n_ipa_feats, p1.n_spks, p1.spk_emb_dim, p1.n_enc_channels, p1.filter_channels,
+               p1.filter_channels_dp, p1.n_heads, p1.n_enc_layers, p1.enc_kernel, p1.enc_dropout,
+               p1.window_size, p1.n_feats, p1.dec_dim, p1.beta_min, p1.beta_max, p1.pe_scale)
+    B, T_x, T_y = 4, 48, 152
+    x_lengths = torch.tensor([48, 20, 35, 41])
+    y_lengths = torch.tensor([152, 70, 121, 100])
+    x = torch.randint(-1, 2, (B, p1.n_ipa_feats, T_x)).float()  # ternary IPA traits
+    y = torch.randn(B, p1.n_feats, T_y)
+    y[:, [12, 14]] = 0.0  # the two padded SPARC channels (data_phnm.py:136-140)
+    y = y * (torch.arange(T_y)[None, None, :] < y_lengths[:, None, None])
+    capture(a, x, x_lengths, y, y_lengths, "prior_arttts.npz", {"x_traits": x.numpy()})
+
+    shutil.rmtree(shim, ignore_errors=True)
+    for f in sorted(os.listdir(HERE)):
+        if f.endswith(".npz"):
+            print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,335 @@
+"""GPU parity: the sm_100a kernels (through the C ABI) against the CPU oracle and the golden
+vectors recorded from the reference.  Bars (BASELINE.json north_star):
+  maximum_path on the reference's own value tensor .... bit-exact path and durations
+  fused prior+MAS ..... prior <= 1e-5 relative, >= 99.9 % of cells equal, score <= 1e-4 rel."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from conftest import GOLDEN, path_from_durations, rect_mask, seeded_case
+
+pytestmark = pytest.mark.gpu
+
+
+def run_mas(value, mask, cuda, **kw):
+    from art_tts_b200 import monotonic_align
+    v = torch.from_numpy(np.ascontiguousarray(value)).to(cuda)
+    m = torch.from_numpy(np.ascontiguousarray(mask)).to(cuda)
+    out = monotonic_align.maximum_path(v, m, **kw)
+    torch.cuda.synchronize()
+    return out
+
+
+def run_lengths(value, t_x, t_y, cuda, **kw):
+    from art_tts_b200 import monotonic_align
+    v = torch.from_numpy(np.ascontiguousarray(value)).to(cuda)
+    out = monotonic_align.maximum_path_lengths(v, torch.from_numpy(t_x), torch.from_numpy(t_y), **kw)
+    torch.cuda.synchronize()
+    return out
+
+
+# ------------------------------------------------------------------ golden vectors
+def test_small_goldens_bit_exact(cuda, golden_small):
+    g = golden_small
+    for name in g["names"]:
+        value, mask, want = g[f"{name}.value"], g[f"{name}.mask"], g[f"{name}.path"]
+        strict = name == "holes"
+        got = run_mas(value, mask, cuda, strict_mask=strict)
+        assert got.dtype == torch.from_numpy(want).dtype, name
+        assert got.shape == want.shape
+        assert np.array_equal(got.cpu().numpy(), want), name
+
+
+@pytest.mark.parametrize("flags", [0, 1], ids=["fast", "general"])
+def test_seeded_goldens_bit_exact(cuda, golden_seeded, flags):
+    g = golden_seeded
+    for name in g["names"]:
+        seed, B, T_x, T_y = (int(v) for v in g[f"{name}.recipe"])
+        if flags == 1 and B * T_x * T_y > 5_000_000:
+            continue  # the general kernel is the slow fallback: keep its cases small
+        value, t_x, t_y = seeded_case(seed, B, T_x, T_y, str(g[f"{name}.kind"]))
+        path, dur, score = run_lengths(value, t_x, t_y, cuda, return_durations=True,
+                                       return_score=True, flags=flags)
+        assert np.array_equal(dur.cpu().numpy(), g[f"{name}.durations"]), name
+        assert np.array_equal(score.cpu().numpy(), g[f"{name}.score"]), name
+        p8 = path.to(torch.uint8).cpu().numpy()
+        assert hashlib.sha256(p8.tobytes()).hexdigest() == str(g[f"{name}.path_sha256"]), name
+
+
+# ------------------------------------------------------------------ oracle on random inputs
+@pytest.mark.parametrize("flags", [0, 1], ids=["fast", "general"])
+def test_random_ragged_vs_oracle(cuda, flags):
+    rng = np.random.default_rng(2024 + flags)
+    for it in range(30):
+        B = int(rng.integers(1, 7))
+        T_x = int(rng.integers(1, 200))
+        T_y = int(rng.integers(1, 420))
+        t_x = rng.integers(0, T_x + 1, B).astype(np.int32)
+        t_y = rng.integers(0, T_y + 1, B).astype(np.int32)     # degenerate + empty included
+        value = (rng.integers(-3, 2, (B, T_x, T_y)) if it % 3 == 0 else
+                 rng.standard_normal((B, T_x, T_y)) * 7).astype(np.float32)
+        mask = rect_mask(t_x, t_y, T_x, T_y)
+        tx_eff = mask.sum(1)[:, 0].astype(np.int32)   # what the reference derives from the mask
+        ty_eff = mask.sum(2)[:, 0].astype(np.int32)
+        want = oracle.maximum_path(value, mask)
+        got = run_mas(value, mask, cuda)
+        assert np.array_equal(got.cpu().numpy(), want), (it, B, T_x, T_y)
+        path, dur = run_lengths(value, tx_eff, ty_eff, cuda, return_durations=True, flags=flags)
+        assert np.array_equal(path.cpu().numpy(), want), (it, B, T_x, T_y, flags)
+        assert np.array_equal(dur.cpu().numpy(), want.sum(-1).astype(np.int32))
+
+
+@pytest.mark.parametrize("T_x", [1, 31, 32, 33, 64, 65, 190, 256, 257, 511, 512])
+def test_token_axis_edges_vs_oracle(cuda, T_x):
+    rng = np.random.default_rng(T_x)
+    T_y = T_x + int(rng.integers(0, 300))
+    B = 3
+    t_x = np.array([T_x, max(1, T_x - 1), max(1, T_x // 2)], np.int32)
+    t_y = np.array([T_y, max(t_x[1], T_y - 17), t_x[2]], np.int32)   # last one: t_x == t_y
+    value = (rng.standard_normal((B, T_x, T_y)) * 3 - 20).astype(np.float32)
+    mask = rect_mask(t_x, t_y, T_x, T_y)
+    want, wsc = oracle.maximum_path(value, mask, return_scores=True)
+    path, dur, score = run_lengths(value, t_x, t_y, cuda, return_durations=True, return_score=True)
+    assert np.array_equal(path.cpu().numpy(), want)
+    assert np.array_equal(score.cpu().numpy(), wsc)
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16, torch.float64])
+def test_value_dtypes_follow_reference_casts(cuda, dtype):
+    rng = np.random.default_rng(11)
+    B, T_x, T_y = 3, 45, 150
+    t_x = np.array([45, 20, 33], np.int32)
+    t_y = np.array([150, 100, 33], np.int32)
+    v = torch.from_numpy(rng.standard_normal((B, T_x, T_y)) * 4).to(dtype)
+    mask = torch.from_numpy(rect_mask(t_x, t_y, T_x, T_y)).to(dtype)
+    # reference: (value*mask) in `dtype`, then astype(float32); path returned in `dtype`
+    v32 = (v * mask).to(torch.float32).numpy()
+    want = oracle.maximum_path(v32, mask.to(torch.float32).numpy())
+    from art_tts_b200 import monotonic_align
+    got = monotonic_align.maximum_path(v.to(cuda), mask.to(cuda))
+    assert got.dtype == dtype
+    assert np.array_equal(got.to(torch.float32).cpu().numpy(), want)
+
+
+def test_mask_dtype_promotion_and_views(cuda):
+    """mask may be bool / a broadcast view (x_mask[...,None] * y_mask[:,:,None] unmaterialised)."""
+    from art_tts_b200 import monotonic_align
+    rng = np.random.default_rng(3)
+    B, T_x, T_y = 4, 50, 170
+    t_x = torch.tensor([50, 10, 25, 49])
+    t_y = torch.tensor([170, 60, 25, 169])
+    value = torch.from_numpy(rng.standard_normal((B, T_x, T_y)).astype(np.float32)).to(cuda)
+    xm = (torch.arange(T_x)[None, :] < t_x[:, None]).to(cuda)
+    ym = (torch.arange(T_y)[None, :] < t_y[:, None]).to(cuda)
+    view = xm[:, :, None] & ym[:, None, :]                      # bool
+    want = oracle.maximum_path(value.cpu().numpy(), view.cpu().numpy().astype(np.float32))
+    got = monotonic_align.maximum_path(value, view)
+    assert got.dtype == torch.float32
+    assert np.array_equal(got.cpu().numpy(), want)
+    exp = xm[:, :, None].float().expand(B, T_x, T_y) * ym[:, None, :].float()
+    got2 = monotonic_align.maximum_path(value, exp.transpose(1, 2).contiguous().transpose(1, 2))
+    assert np.array_equal(got2.cpu().numpy(), want)
+
+
+def test_out_dtypes_and_no_input_clobber(cuda):
+    value, t_x, t_y = seeded_case(21, 4, 70, 260, "ljs")
+    mask = rect_mask(t_x, t_y, 70, 260)
+    want = oracle.maximum_path(value, mask)
+    from art_tts_b200 import monotonic_align
+    v = torch.from_numpy(value).to(cuda)
+    keep = v.clone()
+    for dt in (torch.float32, torch.float16, torch.bfloat16, torch.float64, torch.int32, torch.uint8):
+        got = monotonic_align.maximum_path_lengths(v, torch.from_numpy(t_x), torch.from_numpy(t_y),
+                                                   out_dtype=dt)
+        assert got.dtype == dt
+        assert np.array_equal(got.to(torch.float32).cpu().numpy(), want), dt
+    assert torch.equal(v, keep)   # unlike the reference, the input is never modified
+
+
+# ------------------------------------------------------------------ full-size properties
+def check_path_invariants(path, dur, t_x, t_y):
+    """SURVEY.md App. A.4 for 1 <= t_x <= t_y, on device."""
+    B, T_x, T_y = path.shape
+    tx = torch.as_tensor(t_x, device=path.device).long()
+    ty = torch.as_tensor(t_y, device=path.device).long()
+    col = path.sum(1)                                   # ones per frame
+    frames = torch.arange(T_y, device=path.device)[None, :]
+    assert torch.equal(col, (frames < ty[:, None]).to(col.dtype))
+    assert torch.equal(path.sum(2).to(torch.int32), dur)
+    tokens = torch.arange(T_x, device=path.device)[None, :]
+    valid = tokens < tx[:, None]
+    assert bool(((dur >= 1) == valid).all())            # every valid token >= 1 frame, padding 0
+    assert torch.equal(dur.sum(1).long(), ty)
+    # monotone: token index per frame is non-decreasing and moves by at most 1
+    idx = path.argmax(1)
+    step = idx[:, 1:] - idx[:, :-1]
+    inside = frames[:, 1:] < ty[:, None]
+    assert bool(((step == 0) | (step == 1))[inside].all())
+
+
+def test_config1_ljspeech_batch_bit_exact_and_invariants(cuda):
+    value, t_x, t_y = seeded_case(0, 16, 190, 870, "ljs")
+    mask = rect_mask(t_x, t_y, 190, 870)
+    want = oracle.maximum_path(value, mask, n_threads=8)
+    path, dur = run_lengths(value, t_x, t_y, cuda, return_durations=True)
+    assert np.array_equal(path.cpu().numpy(), want)
+    check_path_invariants(path, dur, t_x, t_y)
+
+
+def test_config4_long_utterances_spilled_bits(cuda):
+    """T_x=512, T_y=4096: direction bits (262 KB/utterance) spill to the workspace."""
+    value, t_x, t_y = seeded_case(4, 4, 512, 4096, "full")
+    want = oracle.maximum_path(value, rect_mask(t_x, t_y, 512, 4096), n_threads=4)
+    path, dur = run_lengths(value, t_x, t_y, cuda, return_durations=True)
+    assert np.array_equal(path.cpu().numpy(), want)
+    check_path_invariants(path, dur, t_x, t_y)
+
+
+def test_config5_b1024_properties_and_generate_path_roundtrip(cuda):
+    """BASELINE config 5 size: checked through size-independent properties + a sampled oracle."""
+    from art_tts_b200 import monotonic_align, utils
+    B, T_x, T_y = 1024, 190, 870
+    g = torch.Generator(device="cpu").manual_seed(5)
+    t_x = torch.randint(60, T_x + 1, (B,), generator=g, dtype=torch.int32)
+    t_y = torch.minimum(torch.tensor(T_y), 4 * t_x + torch.randint(0, 100, (B,), generator=g,
+                                                                    dtype=torch.int32)).int()
+    torch.manual_seed(5)
+    value = -(torch.rand(B, T_x, T_y, device=cuda) * 100 + 50)
+    path, dur, score = monotonic_align.maximum_path_lengths(value, t_x, t_y, return_durations=True,
+                                                            return_score=True)
+    check_path_invariants(path, dur, t_x.numpy(), t_y.numpy())
+    # score == sum of value over the path (linearity of the objective along the chosen path)
+    s2 = (value.double() * path.double()).sum((1, 2))
+    assert torch.allclose(score.double(), s2, rtol=1e-5)
+    # generate_path is the exact inverse (utils.py:26-43)
+    again = utils.generate_path_lengths(dur, t_x, t_y, T_y, out_dtype=torch.float32)
+    assert torch.equal(again, path)
+    # idempotent / deterministic
+    path2 = monotonic_align.maximum_path_lengths(value, t_x, t_y)
+    assert torch.equal(path2, path)
+    # sampled utterances against the oracle, bit-exact
+    pick = [0, 1, 17, 500, 1023]
+    sub = value[pick].cpu().numpy()
+    want = oracle.maximum_path(sub, rect_mask(t_x[pick].numpy(), t_y[pick].numpy(), T_x, T_y))
+    assert np.array_equal(path[pick].cpu().numpy(), want)
+
+
+# ------------------------------------------------------------------ lengths / generate_path
+def test_lengths_from_mask_dtypes(cuda):
+    from art_tts_b200 import monotonic_align
+    t_x = np.array([7, 1, 0, 5], np.int32)
+    t_y = np.array([13, 2, 0, 9], np.int32)
+    m = rect_mask(t_x, t_y, 9, 13)
+    for dt in (torch.float32, torch.float16, torch.bfloat16, torch.float64, torch.int32,
+               torch.int64, torch.uint8, torch.bool):
+        lx, ly = monotonic_align.lengths_from_mask(torch.from_numpy(m).to(dt).to(cuda))
+        assert lx.cpu().tolist() == (m.sum(1)[:, 0]).astype(int).tolist(), dt
+        assert ly.cpu().tolist() == (m.sum(2)[:, 0]).astype(int).tolist(), dt
+
+
+def test_generate_path_matches_reference_formula(cuda):
+    from art_tts_b200 import utils
+    rng = np.random.default_rng(9)
+    B, T_x, T_y = 5, 37, 211
+    t_x = np.array([37, 20, 1, 36, 9], np.int32)
+    t_y = np.array([211, 90, 5, 210, 64], np.int32)
+    mask = rect_mask(t_x, t_y, T_x, T_y)
+    dur = rng.integers(0, 9, (B, T_x)).astype(np.float32)         # fp32 like ceil(w) (tts.py:132)
+    want = oracle.generate_path(dur, mask)
+    got = utils.generate_path(torch.from_numpy(dur).to(cuda), torch.from_numpy(mask).to(cuda))
+    assert got.dtype == torch.float32
+    assert np.array_equal(got.cpu().numpy(), want)
+    frac = (dur * 1.3).astype(np.float32)                          # length_scale != 1
+    want = oracle.generate_path(frac, mask)
+    got = utils.generate_path(torch.from_numpy(frac).to(cuda), torch.from_numpy(mask).to(cuda))
+    assert np.array_equal(got.cpu().numpy(), want)
+    got = utils.generate_path(torch.from_numpy(dur.astype(np.int32)).to(cuda),
+                              torch.from_numpy(mask).to(cuda))
+    assert np.array_equal(got.cpu().numpy(), oracle.generate_path(dur.astype(np.int32), mask))
+
+
+# ------------------------------------------------------------------ fused prior + MAS
+def fused(mu_x, y, x_len, y_len, cuda, **kw):
+    from art_tts_b200 import monotonic_align
+    out = monotonic_align.maximum_path_from_prior(
+        torch.from_numpy(mu_x).to(cuda), None, torch.from_numpy(y).to(cuda),
+        torch.from_numpy(np.asarray(x_len, np.int32)), torch.from_numpy(np.asarray(y_len, np.int32)),
+        **kw)
+    torch.cuda.synchronize()
+    return out
+
+
+def prior_bars(lp_gpu, path_gpu, score_gpu, lp_ref, path_ref, mask):
+    m = mask.astype(bool)
+    rel = np.abs(lp_gpu - lp_ref)[m] / np.maximum(np.abs(lp_ref[m]), 1e-6)
+    assert rel.max() <= 1e-5, rel.max()                       # prior within 1e-5 relative
+    agree = (path_gpu == path_ref).mean()
+    assert agree >= 0.999, agree                              # >= 99.9 % of cells
+    ll_ref = (lp_ref.astype(np.float64) * path_ref).sum((1, 2))
+    assert np.allclose(score_gpu, ll_ref, rtol=1e-4)          # total log-likelihood 1e-4 relative
+
+
+@pytest.mark.parametrize("fname", ["prior_gradtts.npz", "prior_arttts.npz"])
+def test_fused_matches_reference_model_capture(cuda, fname):
+    """mu_x / y captured inside the reference's compute_loss (tts.py:472-499)."""
+    g = np.load(os.path.join(GOLDEN, fname))
+    mu_x, y = g["mu_x"], g["y"]
+    x_len, y_len = g["x_lengths"], g["y_lengths"]
+    T_x, T_y = mu_x.shape[2], y.shape[2]
+    mask = rect_mask(x_len, y_len, T_x, T_y)
+    path, dur, score, fidx, lp = fused(mu_x, y, x_len, y_len, cuda, return_score=True,
+                                       return_frame_idx=True, return_log_prior=True)
+    want_path = np.unpackbits(g["attn_packed"], axis=-1)[:, :, :T_y].astype(np.float32)
+    prior_bars(lp.cpu().numpy(), path.cpu().numpy(), score.cpu().numpy(), g["log_prior"], want_path,
+               mask)
+    # the kernel's own prior -> oracle MAS must reproduce the kernel's path bit-exactly
+    self_path = oracle.maximum_path(lp.cpu().numpy(), mask)
+    assert np.array_equal(path.cpu().numpy(), self_path)
+    assert np.array_equal(dur.cpu().numpy(), self_path.sum(-1).astype(np.int32))
+    fi = fidx.cpu().numpy()
+    for b in range(mu_x.shape[0]):
+        assert np.array_equal(fi[b, :y_len[b]], self_path[b].argmax(0)[:y_len[b]])
+        assert (fi[b, y_len[b]:] == -1).all()
+
+
+@pytest.mark.parametrize("F,B,T_x,T_y,seed", [(16, 32, 160, 512, 1), (80, 16, 190, 870, 2),
+                                              (80, 3, 33, 95, 3), (7, 2, 5, 40, 4)])
+def test_fused_vs_oracle_configs(cuda, F, B, T_x, T_y, seed):
+    """BASELINE config 2 (articulatory, F=16, ragged) and the LJSpeech shape (F=80)."""
+    rng = np.random.default_rng(seed)
+    x_len = rng.integers(max(1, T_x // 8), T_x + 1, B).astype(np.int32)
+    y_len = np.minimum(T_y, 3 * x_len + rng.integers(0, 61, B)).astype(np.int32)
+    x_len[0], y_len[0] = T_x, T_y
+    mu_x = rng.standard_normal((B, F, T_x)).astype(np.float32)
+    y = rng.standard_normal((B, F, T_y)).astype(np.float32)
+    if F == 16:
+        y[:, [12, 14]] = 0.0
+    mu_x *= (np.arange(T_x)[None, None, :] < x_len[:, None, None])
+    y *= (np.arange(T_y)[None, None, :] < y_len[:, None, None])
+    mask = rect_mask(x_len, y_len, T_x, T_y)
+    lp_ref = oracle.log_prior(mu_x, y)
+    path_ref = oracle.maximum_path(lp_ref, mask, n_threads=8)
+    path, dur, score, lp = fused(mu_x, y, x_len, y_len, cuda, return_score=True,
+                                 return_log_prior=True)
+    prior_bars(lp.cpu().numpy(), path.cpu().numpy(), score.cpu().numpy(), lp_ref, path_ref, mask)
+    self_path = oracle.maximum_path(lp.cpu().numpy(), mask, n_threads=8)
+    assert np.array_equal(path.cpu().numpy(), self_path)
+    assert np.array_equal(dur.cpu().numpy(), self_path.sum(-1).astype(np.int32))
+
+
+def test_fused_unfused_plan_for_long_text(cuda):
+    """T_x=512 at F=80: mu_x does not fit beside the ring -> prior to HBM once, then drop-in."""
+    rng = np.random.default_rng(6)
+    B, F, T_x, T_y = 2, 80, 512, 1200
+    mu_x = rng.standard_normal((B, F, T_x)).astype(np.float32)
+    y = rng.standard_normal((B, F, T_y)).astype(np.float32)
+    x_len = np.array([512, 300], np.int32)
+    y_len = np.array([1200, 1000], np.int32)
+    mask = rect_mask(x_len, y_len, T_x, T_y)
+    path, dur, lp = fused(mu_x, y, x_len, y_len, cuda, return_log_prior=True)
+    self_path = oracle.maximum_path(lp.cpu().numpy(), mask, n_threads=2)
+    assert np.array_equal(path.cpu().numpy(), self_path)

@@ -1,0 +1,109 @@
+"""CPU: pin the oracle (oracle/) to the reference's own outputs (tests/golden/, made by
+running /root/reference in the build container) and to oracle/_ref when it is present."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from oracle import ref as oref
+from conftest import GOLDEN, path_from_durations, rect_mask, seeded_case
+
+
+def test_oracle_matches_reference_small_goldens(golden_small):
+    g = golden_small
+    for name in g["names"]:
+        value, mask, want = g[f"{name}.value"], g[f"{name}.mask"], g[f"{name}.path"]
+        got = oracle.maximum_path(value, mask)
+        assert got.dtype == want.dtype, name
+        assert np.array_equal(got, want), name
+
+
+def test_oracle_matches_reference_seeded_goldens(golden_seeded):
+    g = golden_seeded
+    for name in g["names"]:
+        seed, B, T_x, T_y = (int(v) for v in g[f"{name}.recipe"])
+        value, t_x, t_y = seeded_case(seed, B, T_x, T_y, str(g[f"{name}.kind"]))
+        assert hashlib.sha256(value.tobytes()).hexdigest() == str(g[f"{name}.value_sha256"]), name
+        assert np.array_equal(t_x, g[f"{name}.t_x"]) and np.array_equal(t_y, g[f"{name}.t_y"])
+        path, score = oracle.maximum_path(value, rect_mask(t_x, t_y, T_x, T_y), return_scores=True)
+        assert np.array_equal(path.sum(-1).astype(np.int32), g[f"{name}.durations"]), name
+        assert np.array_equal(score, g[f"{name}.score"]), name
+        assert hashlib.sha256(path.astype(np.uint8).tobytes()).hexdigest() == \
+            str(g[f"{name}.path_sha256"]), name
+        # durations determine the path (generate_path is the inverse, utils.py:26-43)
+        assert np.array_equal(path_from_durations(g[f"{name}.durations"], t_y, T_y),
+                              path.astype(np.uint8)), name
+
+
+@pytest.mark.skipif(not oref.available("serial"), reason="oracle/_ref not built on this box")
+@pytest.mark.parametrize("kind", ["serial", "omp"])
+def test_oracle_matches_live_reference_kernel(kind):
+    rng = np.random.default_rng(42)
+    for it in range(40):
+        B = int(rng.integers(1, 5))
+        T_x = int(rng.integers(1, 70))
+        T_y = int(rng.integers(1, 150))
+        t_x = rng.integers(1, T_x + 1, B).astype(np.int32)
+        t_y = rng.integers(1, T_y + 1, B).astype(np.int32)   # includes degenerate t_x > t_y
+        value = (rng.integers(-3, 2, (B, T_x, T_y)) if it % 2 else
+                 rng.standard_normal((B, T_x, T_y)) * 4).astype(np.float32)
+        mask = rect_mask(t_x, t_y, T_x, T_y)
+        assert np.array_equal(oracle.maximum_path(value, mask), oref.maximum_path(value, mask, kind))
+
+
+def test_oracle_threads_give_identical_paths():
+    value, t_x, t_y = seeded_case(3, 12, 64, 200, "ljs")
+    mask = rect_mask(t_x, t_y, 64, 200)
+    assert np.array_equal(oracle.maximum_path(value, mask, n_threads=1),
+                          oracle.maximum_path(value, mask, n_threads=4))
+
+
+def test_rowsweep_bit_formulation_matches_oracle():
+    """The 1-bit direction form the CUDA kernels use is exact."""
+    rng = np.random.default_rng(7)
+    for it in range(60):
+        T_x = int(rng.integers(1, 50))
+        T_y = int(rng.integers(T_x, 120))
+        t_x = int(rng.integers(1, T_x + 1))
+        t_y = int(rng.integers(t_x, T_y + 1))
+        value = (rng.integers(-2, 1, (T_x, T_y)) if it % 3 == 0 else
+                 rng.standard_normal((T_x, T_y))).astype(np.float32)
+        mask = rect_mask([t_x], [t_y], T_x, T_y)
+        want, wsc = oracle.maximum_path(value[None], mask, return_scores=True)
+        got, dur, sc = oracle.maximum_path_rowsweep(value, t_x, t_y)
+        assert np.array_equal(got, want[0].astype(np.int32))
+        assert sc == wsc[0]
+        assert dur[:t_x].min() >= 1 and dur.sum() == t_y
+
+
+def test_all_ties_pile_on_last_token():
+    path = oracle.maximum_path(np.zeros((1, 3, 6), np.float32), np.ones((1, 3, 6), np.float32))
+    assert path.sum(-1).tolist() == [[1, 1, 4]]
+
+
+def test_generate_path_is_inverse_of_mas():
+    value, t_x, t_y = seeded_case(5, 6, 40, 130, "ljs")
+    mask = rect_mask(t_x, t_y, 40, 130)
+    path = oracle.maximum_path(value, mask)
+    assert np.array_equal(oracle.generate_path(path.sum(-1), mask), path)
+
+
+@pytest.mark.parametrize("fname,F", [("prior_gradtts.npz", 80), ("prior_arttts.npz", 16)])
+def test_prior_restatement_matches_reference_model(fname, F):
+    """tts.py:483-495 as captured from the reference's own compute_loss."""
+    g = np.load(os.path.join(GOLDEN, fname))
+    mu_x, y, want = g["mu_x"], g["y"], g["log_prior"]
+    assert mu_x.shape[1] == F
+    for method in ("numpy", "c"):
+        got = oracle.log_prior(mu_x, y, method=method)
+        assert np.allclose(got, want, rtol=1e-5, atol=1e-4), method
+    direct = oracle.log_prior_f64(mu_x, y)
+    assert np.allclose(direct, want, rtol=1e-5, atol=1e-4)
+    # and MAS on the captured prior reproduces the captured alignment
+    x_len, y_len = g["x_lengths"], g["y_lengths"]
+    mask = rect_mask(x_len, y_len, mu_x.shape[2], y.shape[2])
+    path = oracle.maximum_path(want, mask)
+    assert np.array_equal(path.sum(-1).astype(np.int32), g["durations"])
+    assert np.array_equal(np.packbits(path.astype(np.uint8), axis=-1), g["attn_packed"])
