@@ -67,7 +67,9 @@ Plan choose_plan(int T_x, int T_y, int flags, FastLayout *lay, size_t extra_smem
         auto occ = [&](int s) { return (int)((size_t)(kSmemBudget + 1024) / (total(s, fits) + 1024)); };
         for (int s = 3; s <= max_stages; ++s)
             if (total(s, fits) <= (size_t)kSmemBudget && (occ(s) >= occ(2) || occ(s) >= 3)) S = s;
-        if (forced >= 2 && forced <= 8 && total(forced, fits) <= (size_t)kSmemBudget) S = forced;
+        if (forced >= 2 && forced <= (extra_smem ? max_stages : 6) &&
+            total(forced, fits) <= (size_t)kSmemBudget)
+            S = forced;
         L.nstages = S;
     }
     if (plan == kPlanGeneral) {
@@ -188,6 +190,9 @@ int mas_maximum_path(const void *value, int value_dtype, const float *cell_mask,
     a.T_y = T_y;
     a.path_esize = path ? esize : 4;
     a.one = one_pattern(path_dtype);
+    a.load_mode = 0;
+    if (value_dtype == MAS_F32 && !cell_mask && !(flags & MAS_FLAG_NO_ASYNC))
+        a.load_mode = (T_y % 4 == 0 && (uintptr_t)value % 16 == 0) ? 2 : 1;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const cudaError_t e = (plan == kPlanGeneral) ? launch_general(a, value_dtype, st)
                                                  : launch_fast(a, value_dtype, st);
@@ -249,6 +254,7 @@ int mas_from_prior_f32(const float *mu_x, const float *logs, const float *y, con
         m.T_y = T_y;
         m.path_esize = path ? esize : 4;
         m.one = one_pattern(path_dtype);
+        m.load_mode = (T_y % 4 == 0 && (uintptr_t)log_prior_out % 16 == 0) ? 2 : 1;
         return (int)((p2 == kPlanGeneral) ? launch_general(m, MAS_F32, st) : launch_fast(m, MAS_F32, st));
     }
     a.mu_x = mu_x;

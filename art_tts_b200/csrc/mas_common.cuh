@@ -55,6 +55,29 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
     }
 }
 
+// ---------------------------------------------------------------- cp.async (LDGSTS)
+// Asynchronous global->shared copies: no register staging, any number in flight per thread.
+// `bytes` < size zero-fills the remainder (bytes == 0 reads nothing).
+__device__ __forceinline__ void cp_async4(void *dst_smem, const void *src, uint32_t bytes)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(dst_smem)), "l"(src),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async16(void *dst_smem, const void *src, uint32_t bytes)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst_smem)), "l"(src),
+                 "r"(bytes)
+                 : "memory");
+}
+// The mbarrier receives one arrival once all cp.async issued so far by this thread have
+// landed (.noinc: that arrival is part of the barrier's initial expected count).
+__device__ __forceinline__ void cp_async_arrive(uint64_t *bar)
+{
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+
 // ---------------------------------------------------------------- streaming global access
 template <typename T>
 __device__ __forceinline__ float load_as_f32(const T *p);

@@ -36,6 +36,8 @@ struct MasArgs {
     uint32_t *bits_ws;     // workspace: [B][nch][xrows] (fast, spilled) or [B][32*nch][xw] (general)
     int B, T_x, T_y;
     int path_esize;
+    int load_mode;         // fast kernel staging: 0 = LDG/STS (any dtype, cell mask), 1 = cp.async 4 B,
+                           // 2 = cp.async 16 B (fp32, rows 16-byte aligned)
     unsigned long long one;
     FastLayout lay;
 };

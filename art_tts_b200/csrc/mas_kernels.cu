@@ -82,7 +82,7 @@ __device__ __forceinline__ void stage_value_tile(const InT *__restrict__ vb,
     const bool in = y < ty;
     const int lo = max(0, tx + t * kTileY - ty);
     const int hi = min(tx - 1, t * kTileY + kTileY - 1);
-    constexpr int U = 4;
+    constexpr int U = 8;
     for (int x0 = lo + hw; x0 <= hi; x0 += U * nhw) {
         float v[U];
 #pragma unroll
@@ -100,6 +100,33 @@ __device__ __forceinline__ void stage_value_tile(const InT *__restrict__ vb,
             const int x = x0 + u * nhw;
             if (x <= hi) stage[tile_index(x, lane)] = v[u];
         }
+    }
+}
+
+// fp32, unmasked: the same band through cp.async -- nothing waits on a register, so a staging
+// thread can have every row of several tiles in flight (HBM latency is hidden by depth, not
+// by occupancy).  VEC16: rows are 16-byte aligned (T_y % 4 == 0), one request moves 4 frames.
+template <bool VEC16>
+__device__ __forceinline__ void stage_value_tile_async(const float *__restrict__ vb, float *stage,
+                                                       int t, int tx, int ty, int64_t T_y, int hw,
+                                                       int nhw, int lane)
+{
+    const int y0 = t * kTileY;
+    const int lo = max(0, tx + y0 - ty);
+    const int hi = min(tx - 1, y0 + kTileY - 1);
+    if constexpr (VEC16) {
+        const int c = lane & 7, r = lane >> 3;   // 16-byte chunk of the row, row within a group of 4
+        const int left = ty - (y0 + 4 * c);      // valid frames from this chunk on
+        const uint32_t bytes = left >= 4 ? 16u : (left > 0 ? 4u * left : 0u);
+        const int yo = bytes ? y0 + 4 * c : 0;   // nothing is read when bytes == 0
+        for (int x = lo + 4 * hw + r; x <= hi; x += 4 * nhw)
+            cp_async16(stage + (x << 5) + ((c ^ (x & 7)) << 2), vb + (int64_t)x * T_y + yo, bytes);
+    } else {
+        const int y = y0 + lane;
+        const uint32_t bytes = y < ty ? 4u : 0u;
+        const float *src = vb + (y < ty ? y : 0);
+        for (int x = lo + hw; x <= hi; x += nhw)
+            cp_async4(stage + tile_index(x, lane), src + (int64_t)x * T_y, bytes);
     }
 }
 
@@ -163,7 +190,7 @@ __global__ void __launch_bounds__(kFastThreads) mas_fast_kernel(const MasArgs a)
 
     if (tid == 0) {
         for (int s = 0; s < L.nstages; ++s) {
-            mbar_init(&ring.full[s], kHelperWarps);
+            mbar_init(&ring.full[s], kHelperWarps * 32);  // every staging thread arrives once
             mbar_init(&ring.empty[s], 1);
         }
         mbar_fence_init();
@@ -208,10 +235,25 @@ __global__ void __launch_bounds__(kFastThreads) mas_fast_kernel(const MasArgs a)
         uint32_t phase = 0;
         for (int t = 0; t < ntiles; ++t) {
             if (t >= L.nstages) mbar_wait(&ring.empty[stage], phase ^ 1u);
-            stage_value_tile<InT>(vb, mb, stages + stage * ring.stage_floats, t, tx, ty, T_y, hw,
-                                  kHelperWarps, lane);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&ring.full[stage]);
+            float *dst = stages + stage * ring.stage_floats;
+            bool async_done = false;
+            if constexpr (sizeof(InT) == 4) {
+                if (a.load_mode == 2) {
+                    stage_value_tile_async<true>(reinterpret_cast<const float *>(vb), dst, t, tx, ty,
+                                                 T_y, hw, kHelperWarps, lane);
+                    async_done = true;
+                } else if (a.load_mode == 1) {
+                    stage_value_tile_async<false>(reinterpret_cast<const float *>(vb), dst, t, tx, ty,
+                                                  T_y, hw, kHelperWarps, lane);
+                    async_done = true;
+                }
+            }
+            if (async_done) {
+                cp_async_arrive(&ring.full[stage]);
+            } else {
+                stage_value_tile<InT>(vb, mb, dst, t, tx, ty, T_y, hw, kHelperWarps, lane);
+                mbar_arrive(&ring.full[stage]);
+            }
             if (++stage == L.nstages) {
                 stage = 0;
                 phase ^= 1u;

@@ -23,40 +23,34 @@
 
 namespace mas {
 
-constexpr int kPriorThreads = 288;                     // 1 DP warp + 8 producer warps
-constexpr int kProducerWarps = kPriorThreads / 32 - 1;
+constexpr int kComputeWarps = 8;
+constexpr int kPriorThreads = 32 * (2 + kComputeWarps);  // DP warp + slab loader warp + 8 FMA warps
 
-__host__ __device__ inline int mu_pitch(int F)
-{
-    int p = (F + 3) & ~3;          // float4 reads along f
-    if (((p >> 2) & 1) == 0) p += 4;  // odd number of 16-byte chunks per row: spreads banks
-    return p;
-}
-
+// extra shared memory of the fused kernel (after the ring / bits / bars of FastLayout):
+//   mu_s  [F][xrows]        mu_x of the utterance, token axis contiguous (global layout kept)
+//   musq  [xrows]           -0.5 * |mu_x|^2 per token
+//   yslab [nstages][F][32]  the 32-frame slab of y behind each ring stage
+//   ysq   [nstages][32]     -0.5 * |y_j|^2 per frame of the slab
+//   ybar  [nstages]         slab-ready mbarriers
 struct PriorSmem {
-    size_t off_mu, off_musq, off_ytile, total_extra;
+    size_t off_mu, off_musq, off_yslab, off_ysq, off_ybar, total_extra;
 };
 
-__host__ __device__ inline PriorSmem prior_smem(int F, int xrows)
+__host__ __device__ inline PriorSmem prior_smem(int F, int xrows, int nstages)
 {
     PriorSmem s;
-    const int P = mu_pitch(F);
     s.off_mu = 0;
-    s.off_musq = s.off_mu + (size_t)xrows * P * 4;
-    s.off_ytile = s.off_musq + (size_t)xrows * 4;
-    s.total_extra = s.off_ytile + 2 * (size_t)P * kTileY * 4;
-    s.total_extra = (s.total_extra + 15) & ~(size_t)15;
+    s.off_musq = s.off_mu + (size_t)F * xrows * 4;
+    s.off_yslab = s.off_musq + (size_t)xrows * 4;
+    s.off_ysq = s.off_yslab + (size_t)nstages * F * kTileY * 4;
+    s.off_ybar = s.off_ysq + (size_t)nstages * kTileY * 4;
+    s.total_extra = (s.off_ybar + (size_t)nstages * 8 + 15) & ~(size_t)15;
     return s;
 }
 
 size_t prior_extra_smem(int F, int T_x)
 {
-    return prior_smem(F, ((T_x + 31) / 32) * 32).total_extra;
-}
-
-__device__ __forceinline__ void producer_bar()
-{
-    asm volatile("bar.sync 1, %0;" ::"n"(kProducerWarps * 32) : "memory");
+    return prior_smem(F, ((T_x + 31) / 32) * 32, 3).total_extra;  // sized for the deepest ring
 }
 
 // one cell of the prior, same operation order as the producers / log_prior_kernel
@@ -93,23 +87,71 @@ __device__ __forceinline__ float prior_forward_dispatch(const TileRing &ring, ui
     return 0.0f;
 }
 
+// 32 tokens x 32 frames of the prior by one warp: thread (xg, yg) owns 4 tokens x 8 frames,
+// i.e. 32 independent fp32 FMA chains fed by 3 LDS.128 per feature (one conflict-free read of
+// mu, two of y).  Accumulation runs over f in ascending order with one FMA per term, exactly
+// like log_prior_kernel / lp_cell, so all three produce bit-identical values.
+__device__ __forceinline__ void prior_pass(const float *__restrict__ mu_s, const float *__restrict__ musq,
+                                           const float *__restrict__ ys, const float *__restrict__ ysq,
+                                           float *__restrict__ tile, int F, int xrows, int p, int lane,
+                                           float cst)
+{
+    const int xg = lane >> 2, yg = lane & 3;
+    const int x0 = 32 * p + 4 * xg;
+    const float *mp = mu_s + x0;
+    const float *yp = ys + 8 * yg;
+    float acc[4][8];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[r][k] = 0.0f;
+#pragma unroll 2
+    for (int f = 0; f < F; ++f) {
+        const float4 m = *reinterpret_cast<const float4 *>(mp + (size_t)f * xrows);
+        const float4 ya = *reinterpret_cast<const float4 *>(yp + f * kTileY);
+        const float4 yb = *reinterpret_cast<const float4 *>(yp + f * kTileY + 4);
+        const float mr[4] = {m.x, m.y, m.z, m.w};
+        const float yk[8] = {ya.x, ya.y, ya.z, ya.w, yb.x, yb.y, yb.z, yb.w};
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[r][k] = __fmaf_rn(mr[r], yk[k], acc[r][k]);
+    }
+    const float4 qa = *reinterpret_cast<const float4 *>(ysq + 8 * yg);
+    const float4 qb = *reinterpret_cast<const float4 *>(ysq + 8 * yg + 4);
+    const float q[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int x = x0 + r;
+        const float msq = musq[x];
+        float o[8];
+        // tts.py:495: y_square - y_mu_double + mu_square + const  (y_mu_double == -cross)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] = ((q[k] + acc[r][k]) + msq) + cst;
+        float *row = tile + (x << 5);
+        *reinterpret_cast<float4 *>(row + (((2 * yg) ^ (x & 7)) << 2)) = make_float4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<float4 *>(row + (((2 * yg + 1) ^ (x & 7)) << 2)) = make_float4(o[4], o[5], o[6], o[7]);
+    }
+}
+
 template <int XPLMAX>
 __global__ void __launch_bounds__(kPriorThreads) mas_prior_kernel(const PriorArgs a)
 {
     extern __shared__ __align__(1024) unsigned char smem[];
     const FastLayout &L = a.lay;
-    const int F = a.F, T_x = a.T_x;
+    const int F = a.F, T_x = a.T_x, NS = L.nstages;
     const int64_t T_y = a.T_y;
-    const int P = mu_pitch(F);
-    const PriorSmem ps = prior_smem(F, L.xrows);
+    const PriorSmem ps = prior_smem(F, L.xrows, NS);
     float *stages = reinterpret_cast<float *>(smem + L.off_stages);
     int *first = reinterpret_cast<int *>(smem + L.off_first);
     int *dur = reinterpret_cast<int *>(smem + L.off_dur);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + L.off_bars);
     unsigned char *extra = smem + L.off_bars + 128;
-    float *mu_s = reinterpret_cast<float *>(extra + ps.off_mu);      // [xrows][P]
-    float *musq = reinterpret_cast<float *>(extra + ps.off_musq);    // [xrows]
-    float *ytile = reinterpret_cast<float *>(extra + ps.off_ytile);  // [2][32 frames][P]
+    float *mu_s = reinterpret_cast<float *>(extra + ps.off_mu);
+    float *musq = reinterpret_cast<float *>(extra + ps.off_musq);
+    float *yslab = reinterpret_cast<float *>(extra + ps.off_yslab);
+    float *ysq = reinterpret_cast<float *>(extra + ps.off_ysq);
+    uint64_t *ybar = reinterpret_cast<uint64_t *>(extra + ps.off_ybar);
 
     const int b = blockIdx.x;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -118,43 +160,40 @@ __global__ void __launch_bounds__(kPriorThreads) mas_prior_kernel(const PriorArg
     const bool degenerate = tx > ty && ty >= 1;
     const bool active = tx >= 1 && ty >= 1 && !degenerate;
     const int ntiles = active ? (ty + kTileY - 1) / kTileY : 0;
+    const int npass = (tx + 31) >> 5;  // 32-token passes per tile
 
     uint32_t *bits = L.bits_in_smem ? reinterpret_cast<uint32_t *>(smem + L.off_bits)
                                     : a.bits_ws + (size_t)b * L.nch * L.xrows;
     TileRing ring;
     ring.stages = stages;
     ring.full = bars;
-    ring.empty = bars + L.nstages;
-    ring.nstages = L.nstages;
+    ring.empty = bars + NS;
+    ring.nstages = NS;
     ring.stage_floats = L.xrows * kTileY;
     if (tid == 0) {
-        for (int s = 0; s < L.nstages; ++s) {
-            mbar_init(&ring.full[s], kProducerWarps);
+        for (int s = 0; s < NS; ++s) {
+            mbar_init(&ring.full[s], kComputeWarps);  // every FMA warp arrives once per tile
             mbar_init(&ring.empty[s], 1);
+            mbar_init(&ybar[s], 1);
         }
         mbar_fence_init();
     }
 
-    // mu_x[b] -> shared, transposed to [token][feature] so that a producer reads four
-    // features of one token with a single broadcast LDS.128.
     const float *mub = a.mu_x + (int64_t)b * F * T_x;
     const float *yb = a.y + (int64_t)b * F * T_y;
+    const int xr = npass * 32;  // token rows any pass may touch
     if (active) {
-        for (int i = tid; i < F * tx; i += kPriorThreads) {
-            const int f = i / tx, x = i - f * tx;
-            mu_s[x * P + f] = __ldg(mub + (int64_t)f * T_x + x);
-        }
-        for (int i = tid; i < (P - F) * tx; i += kPriorThreads) {  // zero the pad features
-            const int x = i / (P - F), f = F + i - x * (P - F);
-            mu_s[x * P + f] = 0.0f;
+        for (int i = tid; i < F * xr; i += kPriorThreads) {
+            const int f = i / xr, x = i - f * xr;
+            mu_s[f * L.xrows + x] = (x < tx) ? __ldg(mub + (int64_t)f * T_x + x) : 0.0f;
         }
     }
     __syncthreads();
     if (active) {
-        for (int x = tid; x < tx; x += kPriorThreads) {
+        for (int x = tid; x < xr; x += kPriorThreads) {
             float s = 0.0f;
             for (int f = 0; f < F; ++f) {
-                const float m = mu_s[x * P + f];
+                const float m = mu_s[f * L.xrows + x];
                 s = __fmaf_rn(m, m, s);
             }
             musq[x] = -0.5f * s;  // tts.py:494  mu_square = sum(factor * mu^2)
@@ -167,6 +206,7 @@ __global__ void __launch_bounds__(kPriorThreads) mas_prior_kernel(const PriorArg
     const int64_t pbytes = a.path ? (int64_t)T_x * T_y * a.path_esize : 0;
 
     if (warp == 0) {
+        // ---------------- DP warp ----------------
         for (int x = lane; x < T_x; x += 32) dur[x] = 0;
         __syncwarp();
         float score = 0.0f;
@@ -183,79 +223,83 @@ __global__ void __launch_bounds__(kPriorThreads) mas_prior_kernel(const PriorArg
             score = __shfl_sync(kFull, score, 0);
         }
         if (lane == 0 && a.score) a.score[b] = score;
-    } else {
-        const int pw = warp - 1;
-        const int ptid = tid - 32;
-        constexpr int npt = kProducerWarps * 32;
-        int stage = 0;
-        uint32_t phase = 0;
-        // prologue: y slab of tile 0
-        auto load_y = [&](int t, float *dst) {
-            // dst[frame][f]; global reads coalesced along frames, one feature row at a time
+    } else if (warp == 1) {
+        // ---------------- slab loader: y[:, 32t..32t+31] -> shared (cp.async), -0.5|y|^2, and the
+        // zero-fill of the dense output path (it is the only warp with idle issue slots)
+        const bool vec16 = (T_y % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.y) & 15) == 0);
+        auto issue = [&](int t) {
+            const int s = t % NS;
+            if (t >= NS) mbar_wait(&ring.empty[s], ((t / NS) - 1) & 1);  // tile t-NS consumed
+            float *dst = yslab + (size_t)s * F * kTileY;
             const int y0 = t * kTileY;
-            for (int i = ptid; i < F * kTileY; i += npt) {
-                const int f = i >> 5, s = i & 31;
-                const int y = y0 + s;
-                dst[s * P + f] = (y < ty) ? __ldg(yb + (int64_t)f * T_y + y) : 0.0f;
+            if (vec16) {
+                const int c = lane & 7, r = lane >> 3;
+                const int left = ty - (y0 + 4 * c);
+                const uint32_t bytes = left >= 4 ? 16u : (left > 0 ? 4u * left : 0u);
+                const int yo = bytes ? y0 + 4 * c : 0;
+                for (int f = r; f < F; f += 4)
+                    cp_async16(dst + f * kTileY + 4 * c, yb + (int64_t)f * T_y + yo, bytes);
+            } else {
+                const int y = y0 + lane;
+                const uint32_t bytes = y < ty ? 4u : 0u;
+                const float *src = yb + (y < ty ? y : 0);
+                for (int f = 0; f < F; ++f) cp_async4(dst + f * kTileY + lane, src + (int64_t)f * T_y, bytes);
             }
-            for (int i = ptid; i < (P - F) * kTileY; i += npt) {
-                const int s = i / (P - F), f = F + i - s * (P - F);
-                dst[s * P + f] = 0.0f;
-            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
         };
-        if (ntiles > 0) load_y(0, ytile);
-        for (int t = 0; t < ntiles; ++t) {
-            producer_bar();  // slab t visible to all producers; slab t-1 no longer read
-            if (t + 1 < ntiles) load_y(t + 1, ytile + ((t + 1) & 1) * P * kTileY);
-            if (t >= L.nstages) mbar_wait(&ring.empty[stage], phase ^ 1u);
-            float *tile = stages + stage * ring.stage_floats;
-            const float *ys = ytile + (t & 1) * P * kTileY + lane * P;  // this lane's frame
-            // -0.5 * |y_j|^2 for this lane's frame (tts.py:488-490)
-            float ysq = 0.0f;
-            for (int f = 0; f < P; f += 4) {
-                const float4 v = *reinterpret_cast<const float4 *>(ys + f);
-                ysq = __fmaf_rn(v.x, v.x, ysq);
-                ysq = __fmaf_rn(v.y, v.y, ysq);
-                ysq = __fmaf_rn(v.z, v.z, ysq);
-                ysq = __fmaf_rn(v.w, v.w, ysq);
+        auto finish = [&](int t) {
+            const int s = t % NS;
+            const float *src = yslab + (size_t)s * F * kTileY + lane;
+            float q = 0.0f;
+            for (int f = 0; f < F; ++f) {
+                const float v = src[f * kTileY];
+                q = __fmaf_rn(v, v, q);
             }
-            ysq *= -0.5f;
+            ysq[s * kTileY + lane] = -0.5f * q;  // tts.py:488-490  y_square
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ybar[s]);
+        };
+        // software pipeline: slabs t+1 .. t+NS-1 are in flight while slab t is finished; slab t is
+        // finished BEFORE the (possibly blocking) issue of slab t+NS-1 so the FMA warps never wait
+        // on the DP warp through this loader.
+        const int depth = NS - 1;
+        for (int t = 0; t < min(depth, ntiles); ++t) issue(t);
+        for (int t = 0; t < ntiles; ++t) {
+            const int allowed = min(depth - 1, ntiles - 1 - t);  // groups that may still be pending
+            if (allowed <= 0) asm volatile("cp.async.wait_group 0;" ::: "memory");
+            else if (allowed == 1) asm volatile("cp.async.wait_group 1;" ::: "memory");
+            else asm volatile("cp.async.wait_group 2;" ::: "memory");
+            __syncwarp();
+            finish(t);
+            if (t + depth < ntiles) issue(t + depth);
+            zero_fill_part(pb, pbytes, t, ntiles, lane, 32);
+        }
+        if (ntiles == 0) zero_fill_part(pb, pbytes, 0, 1, lane, 32);
+    } else {
+        // ---------------- FMA warps: work items (tile t, pass p), dealt round-robin ----------------
+        // Every FMA warp waits for every slab and arrives on every tile's `full` barrier (with or
+        // without work in it): parity waits are only sound if no waiter can fall two phases behind
+        // or run a phase ahead of a barrier, and this makes both impossible by construction.
+        const int cw = warp - 2;
+        int s = 0;
+        uint32_t phase = 0;
+        for (int t = 0; t < ntiles; ++t) {
             const int lo = max(0, tx + t * kTileY - ty);
             const int hi = min(tx - 1, t * kTileY + kTileY - 1);
-            // two token rows per pass: every y value read from shared memory feeds two FMAs
-            for (int x = lo + 2 * pw; x <= hi; x += 2 * kProducerWarps) {
-                const int x1 = min(x + 1, hi);
-                const float *m0 = mu_s + x * P, *m1 = mu_s + x1 * P;
-                float c0 = 0.0f, c1 = 0.0f;
-#pragma unroll 4
-                for (int f = 0; f < P; f += 4) {
-                    const float4 yv = *reinterpret_cast<const float4 *>(ys + f);
-                    const float4 a0 = *reinterpret_cast<const float4 *>(m0 + f);
-                    const float4 a1 = *reinterpret_cast<const float4 *>(m1 + f);
-                    c0 = __fmaf_rn(a0.x, yv.x, c0);
-                    c1 = __fmaf_rn(a1.x, yv.x, c1);
-                    c0 = __fmaf_rn(a0.y, yv.y, c0);
-                    c1 = __fmaf_rn(a1.y, yv.y, c1);
-                    c0 = __fmaf_rn(a0.z, yv.z, c0);
-                    c1 = __fmaf_rn(a1.z, yv.z, c1);
-                    c0 = __fmaf_rn(a0.w, yv.w, c0);
-                    c1 = __fmaf_rn(a1.w, yv.w, c1);
-                }
-                // tts.py:495: y_square - y_mu_double + mu_square + const, y_mu_double = -cross
-                const float lp0 = ((ysq + c0) + musq[x]) + cst;
-                const float lp1 = ((ysq + c1) + musq[x1]) + cst;
-                tile[tile_index(x, lane)] = lp0;
-                if (x1 != x) tile[tile_index(x1, lane)] = lp1;
-            }
+            mbar_wait(&ybar[s], phase);  // slab t is in shared memory => ring stage s is free too
+            int p = (cw - t * npass) % kComputeWarps;
+            if (p < 0) p += kComputeWarps;
+            for (; p < npass; p += kComputeWarps)
+                if (32 * p <= hi && 32 * p + 31 >= lo)
+                    prior_pass(mu_s, musq, yslab + (size_t)s * F * kTileY, ysq + s * kTileY,
+                               stages + (size_t)s * ring.stage_floats, F, L.xrows, p, lane, cst);
             __syncwarp();
-            if (lane == 0) mbar_arrive(&ring.full[stage]);
-            if (++stage == L.nstages) {
-                stage = 0;
+            if (lane == 0) mbar_arrive(&ring.full[s]);
+            if (++s == NS) {
+                s = 0;
                 phase ^= 1u;
             }
-            zero_fill_part(pb, pbytes, t, ntiles, ptid, npt);
         }
-        if (ntiles == 0) zero_fill_part(pb, pbytes, 0, 1, ptid, npt);
     }
     __syncthreads();
     write_path_ones(pb, a.durations ? a.durations + (int64_t)b * T_x : nullptr, first, dur, T_x, T_y,

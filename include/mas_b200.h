@@ -54,7 +54,7 @@ enum {
 enum {
     MAS_FLAG_NONE = 0,
     MAS_FLAG_FORCE_GENERAL = 1, /* use the size-agnostic kernel even when the fast one fits */
-    MAS_FLAG_NO_TMA = 2         /* fast kernel: stage tiles with LDG/STS instead of TMA      */
+    MAS_FLAG_NO_ASYNC = 2       /* fast kernel: stage tiles with LDG/STS instead of cp.async */
 };
 
 int mas_abi_version(void);
