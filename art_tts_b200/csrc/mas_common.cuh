@@ -55,6 +55,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
     }
 }
 
+__device__ __forceinline__ float4 lds128(uint32_t addr)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "r"(addr));
+    return v;
+}
+
 // ---------------------------------------------------------------- cp.async (LDGSTS)
 // Asynchronous global->shared copies: no register staging, any number in flight per thread.
 // `bytes` < size zero-fills the remainder (bytes == 0 reads nothing).

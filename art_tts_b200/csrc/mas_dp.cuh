@@ -58,7 +58,9 @@ __device__ __forceinline__ void dp_tile(float (&V)[XPL], uint32_t (&acc)[XPL],
                                         const float *__restrict__ stage, int lane, int y0,
                                         int nsteps)
 {
-    const float *rowbase = stage + (lane << 5);
+    // explicit shared-space address: `stage` arrives through a struct, and a generic LD would
+    // otherwise be emitted for the hottest load of the kernel
+    const uint32_t rowbase = smem_u32(stage + (lane << 5));
     const int sw = lane & 7;
 #pragma unroll 1
     for (int g = 0; g < 8; ++g) {
@@ -67,7 +69,7 @@ __device__ __forceinline__ void dp_tile(float (&V)[XPL], uint32_t (&acc)[XPL],
         float4 vv[XPL];
 #pragma unroll
         for (int j = 0; j < XPL; ++j)
-            vv[j] = *reinterpret_cast<const float4 *>(rowbase + (j << 10) + ((g ^ sw) << 2));
+            vv[j] = lds128(rowbase + (j << 12) + ((g ^ sw) << 4));
         float v[XPL];
 #pragma unroll
         for (int j = 0; j < XPL; ++j) v[j] = f4_get<0>(vv[j]);

@@ -4,7 +4,7 @@
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--op fused|dropin]
 
 A "step" is one pass of the hot path over one synthetic batch of BASELINE config 5:
-B=1024 LJSpeech-shape utterances per GPU (T_text<=190, T_mel<=870, n_feats=80, ragged,
+B=1024 LJSpeech-shape utterances per GPU (T_text<=190, T_mel<=870 padded to 872, n_feats=80, ragged,
 length-bucketed), i.e.  (mu_x, y, lengths) -> log-prior -> MAS -> (path, durations), followed
 at N>1 by the NCCL all-gather of the int32 durations.  cells = B*T_text*T_mel (padded).
 
@@ -39,7 +39,9 @@ import torch  # noqa: E402
 
 METRIC = "mas_alignment_cells_per_s"
 UNIT = "cells/s"
-B_PER_GPU, T_X, T_Y, N_FEATS = 1024, 190, 870, 80
+# T_mel: 870 frames padded to 872 by fix_len_compatibility (src/model/utils.py:13-17), which is
+# what the reference's collate hands to compute_loss (data_textmel.py:132-153); lengths stay <= 870
+B_PER_GPU, T_X, T_Y, T_Y_MAXLEN, N_FEATS = 1024, 190, 872, 870, 80
 
 
 def parse():
@@ -62,8 +64,8 @@ def make_lengths(B, seed):
     then length-bucketed (sorted by work, longest first)."""
     rng = np.random.default_rng(seed)
     t_x = rng.integers(60, T_X + 1, B).astype(np.int32)
-    t_y = np.minimum(T_Y, 4 * t_x + rng.integers(0, 100, B)).astype(np.int32)
-    t_x[0], t_y[0] = T_X, T_Y
+    t_y = np.minimum(T_Y_MAXLEN, 4 * t_x + rng.integers(0, 100, B)).astype(np.int32)
+    t_x[0], t_y[0] = T_X, T_Y_MAXLEN
     order = np.argsort(-(t_x.astype(np.int64) * t_y), kind="stable")
     return t_x[order], t_y[order]
 
