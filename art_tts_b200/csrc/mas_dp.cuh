@@ -10,14 +10,39 @@
 //     V[x] <- ((V[x-1] > V[x]) ? V[x-1] : V[x]) + value[x,y],     V[x] == -1e9 while x > y,
 // and the only thing that outlives a frame is the backtrack predicate
 //     d[x,y] = (x != 0) && (x == y || V[x,y-1] < V[x-1,y-1]).
-// A lane owns tokens x = lane + 32*j (j < XPL), so the x-1 neighbour is always one
-// shuffle away and a 32-frame tile of d packs into one 32-bit word per token without any
-// cross-lane traffic (bit s of word [chunk][x] is frame 32*chunk+s).
+//
+// Token ownership: lane l owns the XPL CONSECUTIVE tokens x = l*XPL + j (XPL = ceil(t_x/32),
+// per utterance).  The x-1 neighbour is then a register for all but the lane's first token,
+// and that one needs the left lane's LAST token of the previous frame -- a value produced
+// a whole frame earlier, so its shuffle is issued right after it is computed and lands
+// while the lane's other tokens are being updated: the recurrence is issue-bound, not
+// shuffle-latency-bound (measured 120 + 28*XPL cycles/frame with the strided ownership
+// this replaced).  Staged tiles keep token x in physical row (x % XPL)*32 + x / XPL so that
+// lane l still reads rows l, 32+l, 64+l, ... : conflict-free LDS.128 under the 128-byte
+// XOR swizzle.  A 32-frame tile of d packs into one 32-bit word per token without any
+// cross-lane traffic (bit s of word [chunk][row] is frame 32*chunk+s).
 #pragma once
 
 #include "mas_common.cuh"
 
 namespace mas {
+
+// Per-utterance token -> physical row mapping (see above).  `inv` = ceil(65536 / XPL) makes
+// x / XPL an exact multiply-shift for x < 512, XPL <= 16.
+struct RowMap {
+    int xpl;
+    uint32_t inv;
+    __device__ __forceinline__ explicit RowMap(int tx)
+    {
+        xpl = max(1, (tx + 31) >> 5);
+        inv = (65536u + xpl - 1) / xpl;
+    }
+    __device__ __forceinline__ int row(int x) const
+    {
+        const int q = (int)((uint32_t)x * inv >> 16);
+        return ((x - q * xpl) << 5) + q;
+    }
+};
 
 template <int K>
 __device__ __forceinline__ float f4_get(const float4 &v)
@@ -28,34 +53,35 @@ __device__ __forceinline__ float f4_get(const float4 &v)
     return v.w;
 }
 
-// One frame.  `v[j]` is value[x_j, y]; `bit` = 1 << (y & 31).
+// One frame.  `v[j]` is value[x_j, y]; `bit` = 1 << (y & 31); `left` is the left lane's last
+// token at frame y-1 (lane 0: the x == 0 boundary of core.pyx:23-27) and is replaced by the
+// value for frame y.  Tokens are updated from the lane's last to its first so that V[j-1]
+// is still the previous frame's value when token j reads it.
 template <int XPL, bool DIAG>
 __device__ __forceinline__ void dp_step(float (&V)[XPL], uint32_t (&acc)[XPL],
-                                        const float (&v)[XPL], int lane, int y, uint32_t bit)
+                                        const float (&v)[XPL], float &left, int lane, int x0,
+                                        int y, uint32_t bit)
 {
-    float r[XPL];
+    float nxt = 0.0f;
 #pragma unroll
-    for (int j = 0; j < XPL; ++j) r[j] = __shfl_sync(kFull, V[j], (lane + 31) & 31);
-    // token 0 has no predecessor: v_prev = 0 at the first frame, -1e9 after (core.pyx:23-27)
-    const float bnd = (y == 0) ? 0.0f : kNeg;
-#pragma unroll
-    for (int j = 0; j < XPL; ++j) {
-        const float wrap = (j == 0) ? bnd : r[j > 0 ? j - 1 : 0];  // lane 31's previous group
-        const float up = (lane == 0) ? wrap : r[j];                 // V[x-1, y-1]
-        const bool take_prev = up > V[j];                           // core.pyx:30 max()
+    for (int j = XPL - 1; j >= 0; --j) {
+        const float up = (j == 0) ? left : V[j > 0 ? j - 1 : 0];   // V[x-1, y-1]
+        const bool take_prev = up > V[j];                          // core.pyx:30 max()
         const float m = take_prev ? up : V[j];
         float nv = __fadd_rn(m, v[j]);
-        if (DIAG) nv = (lane + 32 * j <= y) ? nv : kNeg;            // x > y: not reachable yet
+        if (DIAG) nv = (x0 + j <= y) ? nv : kNeg;                  // x > y: not reachable yet
         if (take_prev) acc[j] |= bit;
         V[j] = nv;
+        if (j == XPL - 1) nxt = __shfl_up_sync(kFull, nv, 1);      // in flight during the rest
     }
+    left = (lane == 0) ? kNeg : nxt;  // token 0: v_prev = -1e9 after the first frame
 }
 
 // One staged tile of up to 32 frames (frames y0 .. y0+nsteps-1, y0 % 32 == 0).
-// `stage` is the swizzled [token][32 frames] tile in shared memory (see tile_index()).
-template <int XPL, bool DIAG>
-__device__ __forceinline__ void dp_tile(float (&V)[XPL], uint32_t (&acc)[XPL],
-                                        const float *__restrict__ stage, int lane, int y0,
+// `stage` is the swizzled [row][32 frames] tile in shared memory (see tile_index()).
+template <int XPL, bool DIAG, bool FULL>
+__device__ __forceinline__ void dp_tile(float (&V)[XPL], uint32_t (&acc)[XPL], float &left,
+                                        const float *__restrict__ stage, int lane, int x0, int y0,
                                         int nsteps)
 {
     // explicit shared-space address: `stage` arrives through a struct, and a generic LD would
@@ -65,29 +91,28 @@ __device__ __forceinline__ void dp_tile(float (&V)[XPL], uint32_t (&acc)[XPL],
 #pragma unroll 1
     for (int g = 0; g < 8; ++g) {
         const int s0 = g << 2;
-        if (s0 >= nsteps) break;
+        if (!FULL && s0 >= nsteps) break;
         float4 vv[XPL];
 #pragma unroll
-        for (int j = 0; j < XPL; ++j)
-            vv[j] = lds128(rowbase + (j << 12) + ((g ^ sw) << 4));
+        for (int j = 0; j < XPL; ++j) vv[j] = lds128(rowbase + (j << 12) + ((g ^ sw) << 4));
         float v[XPL];
 #pragma unroll
         for (int j = 0; j < XPL; ++j) v[j] = f4_get<0>(vv[j]);
-        dp_step<XPL, DIAG>(V, acc, v, lane, y0 + s0, 1u << s0);
-        if (s0 + 1 < nsteps) {
+        dp_step<XPL, DIAG>(V, acc, v, left, lane, x0, y0 + s0, 1u << s0);
+        if (FULL || s0 + 1 < nsteps) {
 #pragma unroll
             for (int j = 0; j < XPL; ++j) v[j] = f4_get<1>(vv[j]);
-            dp_step<XPL, DIAG>(V, acc, v, lane, y0 + s0 + 1, 2u << s0);
+            dp_step<XPL, DIAG>(V, acc, v, left, lane, x0, y0 + s0 + 1, 2u << s0);
         }
-        if (s0 + 2 < nsteps) {
+        if (FULL || s0 + 2 < nsteps) {
 #pragma unroll
             for (int j = 0; j < XPL; ++j) v[j] = f4_get<2>(vv[j]);
-            dp_step<XPL, DIAG>(V, acc, v, lane, y0 + s0 + 2, 4u << s0);
+            dp_step<XPL, DIAG>(V, acc, v, left, lane, x0, y0 + s0 + 2, 4u << s0);
         }
-        if (s0 + 3 < nsteps) {
+        if (FULL || s0 + 3 < nsteps) {
 #pragma unroll
             for (int j = 0; j < XPL; ++j) v[j] = f4_get<3>(vv[j]);
-            dp_step<XPL, DIAG>(V, acc, v, lane, y0 + s0 + 3, 8u << s0);
+            dp_step<XPL, DIAG>(V, acc, v, left, lane, x0, y0 + s0 + 3, 8u << s0);
         }
     }
 }
@@ -103,8 +128,8 @@ struct TileRing {
 };
 
 // Forward pass of one utterance by ONE warp.  Consumes ceil(t_y/32) tiles from the ring,
-// writes the direction words to bits[chunk*xrows + x] (shared or global memory) and
-// returns V[t_x-1, t_y-1].  Requires 1 <= t_x <= t_y and t_x <= 32*XPL.
+// writes the direction words to bits[chunk*xrows + row] (shared or global memory) and
+// returns V[t_x-1, t_y-1].  Requires 1 <= t_x <= t_y and XPL == ceil(t_x/32).
 template <int XPL>
 __device__ __noinline__ float dp_forward(const TileRing ring, uint32_t *bits, int xrows, int tx,
                                          int ty, int lane)
@@ -116,6 +141,8 @@ __device__ __noinline__ float dp_forward(const TileRing ring, uint32_t *bits, in
         V[j] = kNeg;
         acc[j] = 0u;
     }
+    const int x0 = lane * XPL;                  // this lane's first token
+    float left = (lane == 0) ? 0.0f : kNeg;     // frame 0: v_prev(x=0) = 0, everything else -1e9
     const int ntiles = (ty + kTileY - 1) / kTileY;
     int stage = 0;
     uint32_t phase = 0;
@@ -125,10 +152,12 @@ __device__ __noinline__ float dp_forward(const TileRing ring, uint32_t *bits, in
         const int y0 = t * kTileY;
         const int nsteps = min(kTileY, ty - y0);
         const bool diag = y0 < tx;  // some token x > y still exists in this tile
-        if (diag)
-            dp_tile<XPL, true>(V, acc, tile, lane, y0, nsteps);
-        else
-            dp_tile<XPL, false>(V, acc, tile, lane, y0, nsteps);
+        if (nsteps == kTileY) {
+            if (diag) dp_tile<XPL, true, true>(V, acc, left, tile, lane, x0, y0, nsteps);
+            else dp_tile<XPL, false, true>(V, acc, left, tile, lane, x0, y0, nsteps);
+        } else {
+            dp_tile<XPL, true, false>(V, acc, left, tile, lane, x0, y0, nsteps);
+        }
         __syncwarp();
         if (lane == 0) mbar_arrive(&ring.empty[stage]);
         if (++stage == ring.nstages) {
@@ -139,7 +168,7 @@ __device__ __noinline__ float dp_forward(const TileRing ring, uint32_t *bits, in
         if (diag) {
 #pragma unroll
             for (int j = 0; j < XPL; ++j)
-                if (j == t) acc[j] |= (1u << lane);
+                if (((x0 + j) >> 5) == t) acc[j] |= 1u << ((x0 + j) & 31);
         }
         if (lane == 0) acc[0] = 0u;
         uint32_t *dst = bits + (size_t)t * xrows + lane;
@@ -149,12 +178,13 @@ __device__ __noinline__ float dp_forward(const TileRing ring, uint32_t *bits, in
             acc[j] = 0u;
         }
     }
-    // total alignment score sits in lane (tx-1)%32, group (tx-1)/32
+    // total alignment score: token tx-1 = lane (tx-1)/XPL, slot (tx-1)%XPL
+    const int ql = (tx - 1) / XPL, qj = (tx - 1) - ql * XPL;
     float s = 0.0f;
 #pragma unroll
     for (int j = 0; j < XPL; ++j)
-        if (j == ((tx - 1) >> 5)) s = V[j];
-    return __shfl_sync(kFull, s, (tx - 1) & 31);
+        if (j == qj) s = V[j];
+    return __shfl_sync(kFull, s, ql);
 }
 
 // Backtrack over the packed direction words (core.pyx:32-35), executed by one lane.
@@ -164,10 +194,11 @@ __device__ __noinline__ float dp_forward(const TileRing ring, uint32_t *bits, in
 __device__ __forceinline__ void backtrack_bits(const uint32_t *bits, int xrows, int tx, int ty,
                                                int *first, int *dur)
 {
+    const RowMap rm(tx);
     int idx = tx - 1, y = ty - 1, top = ty - 1;
     while (y >= 0) {
         const int c = y >> 5, s = y & 31;
-        const uint32_t w = (idx != 0) ? bits[(size_t)c * xrows + idx] : 0u;
+        const uint32_t w = (idx != 0) ? bits[(size_t)c * xrows + rm.row(idx)] : 0u;
         const uint32_t m = w & (0xffffffffu >> (31 - s));
         if (m == 0u) {
             y = (c << 5) - 1;  // stays on this token down to the chunk start

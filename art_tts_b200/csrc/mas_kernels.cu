@@ -78,6 +78,7 @@ __device__ __forceinline__ void stage_value_tile(const InT *__restrict__ vb,
                                                  int tx, int ty, int64_t T_y, int hw, int nhw,
                                                  int lane)
 {
+    const RowMap rm(tx);
     const int y = t * kTileY + lane;
     const bool in = y < ty;
     const int lo = max(0, tx + t * kTileY - ty);
@@ -98,7 +99,7 @@ __device__ __forceinline__ void stage_value_tile(const InT *__restrict__ vb,
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int x = x0 + u * nhw;
-            if (x <= hi) stage[tile_index(x, lane)] = v[u];
+            if (x <= hi) stage[tile_index(rm.row(x), lane)] = v[u];
         }
     }
 }
@@ -111,6 +112,7 @@ __device__ __forceinline__ void stage_value_tile_async(const float *__restrict__
                                                        int t, int tx, int ty, int64_t T_y, int hw,
                                                        int nhw, int lane)
 {
+    const RowMap rm(tx);
     const int y0 = t * kTileY;
     const int lo = max(0, tx + y0 - ty);
     const int hi = min(tx - 1, y0 + kTileY - 1);
@@ -119,14 +121,16 @@ __device__ __forceinline__ void stage_value_tile_async(const float *__restrict__
         const int left = ty - (y0 + 4 * c);      // valid frames from this chunk on
         const uint32_t bytes = left >= 4 ? 16u : (left > 0 ? 4u * left : 0u);
         const int yo = bytes ? y0 + 4 * c : 0;   // nothing is read when bytes == 0
-        for (int x = lo + 4 * hw + r; x <= hi; x += 4 * nhw)
-            cp_async16(stage + (x << 5) + ((c ^ (x & 7)) << 2), vb + (int64_t)x * T_y + yo, bytes);
+        for (int x = lo + 4 * hw + r; x <= hi; x += 4 * nhw) {
+            const int row = rm.row(x);
+            cp_async16(stage + (row << 5) + ((c ^ (row & 7)) << 2), vb + (int64_t)x * T_y + yo, bytes);
+        }
     } else {
         const int y = y0 + lane;
         const uint32_t bytes = y < ty ? 4u : 0u;
         const float *src = vb + (y < ty ? y : 0);
         for (int x = lo + hw; x <= hi; x += nhw)
-            cp_async4(stage + tile_index(x, lane), src + (int64_t)x * T_y, bytes);
+            cp_async4(stage + tile_index(rm.row(x), lane), src + (int64_t)x * T_y, bytes);
     }
 }
 

@@ -103,7 +103,7 @@ __device__ __forceinline__ float prior_forward_dispatch(const TileRing &ring, ui
 __device__ __forceinline__ void prior_pass(const float *__restrict__ mu_s, const float *__restrict__ musq,
                                            const float *__restrict__ ys, const float *__restrict__ ysq,
                                            float *__restrict__ tile, int F, int xrows, int p, int lane,
-                                           float cst)
+                                           float cst, const RowMap rm)
 {
     const int xg = lane >> 2, yg = lane & 3;
     const int x0 = 32 * p + 4 * xg;
@@ -137,9 +137,10 @@ __device__ __forceinline__ void prior_pass(const float *__restrict__ mu_s, const
         // tts.py:495: y_square - y_mu_double + mu_square + const  (y_mu_double == -cross)
 #pragma unroll
         for (int k = 0; k < 8; ++k) o[k] = ((q[k] + acc[r][k]) + msq) + cst;
-        float *row = tile + (x << 5);
-        *reinterpret_cast<float4 *>(row + (((2 * yg) ^ (x & 7)) << 2)) = make_float4(o[0], o[1], o[2], o[3]);
-        *reinterpret_cast<float4 *>(row + (((2 * yg + 1) ^ (x & 7)) << 2)) = make_float4(o[4], o[5], o[6], o[7]);
+        const int pr = rm.row(x);  // physical row of token x in the staged tile (mas_dp.cuh)
+        float *row = tile + (pr << 5);
+        *reinterpret_cast<float4 *>(row + (((2 * yg) ^ (pr & 7)) << 2)) = make_float4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<float4 *>(row + (((2 * yg + 1) ^ (pr & 7)) << 2)) = make_float4(o[4], o[5], o[6], o[7]);
     }
 }
 
@@ -303,6 +304,7 @@ __global__ void __launch_bounds__(kPriorThreads) mas_prior_kernel(const PriorArg
         // without work in it): parity waits are only sound if no waiter can fall two phases behind
         // or run a phase ahead of a barrier, and this makes both impossible by construction.
         const int cw = warp;
+        const RowMap rm(tx);
         int s = 0;
         uint32_t phase = 0;
         for (int t = 0; t < ntiles; ++t) {
@@ -316,7 +318,7 @@ __global__ void __launch_bounds__(kPriorThreads) mas_prior_kernel(const PriorArg
             for (; p < npass; p += kComputeWarps)
                 if (32 * p <= hi && 32 * p + 31 >= lo)
                     prior_pass(mu_s, musq, yslab + (size_t)ys * F * kTileY, ysq + ys * kTileY,
-                               stages + (size_t)s * ring.stage_floats, F, L.xrows, p, lane, cst);
+                               stages + (size_t)s * ring.stage_floats, F, L.xrows, p, lane, cst, rm);
             __syncwarp();
             if (lane == 0) mbar_arrive(&ring.full[s]);
             if (++s == NS) {
