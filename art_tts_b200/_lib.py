@@ -41,7 +41,8 @@ class MasError(RuntimeError):
 
 
 def lib_path() -> str:
-    return _build.LIB
+    # MAS_LIB_PATH: load an instrumented build (profiles/prior_timeline.py); never a fallback
+    return os.environ.get("MAS_LIB_PATH") or _build.LIB
 
 
 def load() -> ctypes.CDLL:

@@ -71,11 +71,20 @@ def _compile_one(args):
     return subprocess.run(cmd, capture_output=True, text=True)
 
 
-def build(force: bool = False, verbose: bool = False, extra=()) -> str:
+def build(force: bool = False, verbose: bool = False, extra=(), out: str | None = None) -> str:
+    """`out`: build a variant (e.g. extra=["-DMAS_TIMING"]) next to the production library."""
+    global LIB, STAMP
+    if out is not None:
+        saved = (LIB, STAMP)
+        LIB, STAMP = out, out + ".srchash"
+        try:
+            return build(force=True, verbose=verbose, extra=extra)
+        finally:
+            LIB, STAMP = saved
     if not force and not stale():
         return LIB
     os.makedirs(LIBDIR, exist_ok=True)
-    objdir = os.path.join(LIBDIR, "obj")
+    objdir = os.path.join(LIBDIR, "obj" + ("_var" if extra else ""))
     os.makedirs(objdir, exist_ok=True)
     nvcc = nvcc_path()
     jobs = [(nvcc, s, os.path.join(objdir, os.path.basename(s) + ".o"), tuple(extra), verbose)

@@ -190,31 +190,82 @@ __device__ __noinline__ float dp_forward(const TileRing ring, uint32_t *bits, in
 // Backtrack over the packed direction words (core.pyx:32-35), executed by one lane.
 // Instead of one step per frame it jumps from token boundary to token boundary: inside a
 // 32-frame word the next decrement is the highest set bit at or below the current frame.
+// The word of the NEXT token (same chunk) is prefetched every iteration, so the common
+// transition (next token, same chunk) costs a handful of dependent ALU ops, not a load.
 // Records, per visited token, its first frame and its duration.
-__device__ __forceinline__ void backtrack_bits(const uint32_t *bits, int xrows, int tx, int ty,
-                                               int *first, int *dur)
+template <bool SMEM>
+__device__ __forceinline__ uint32_t bt_word(const uint32_t *bits, uint32_t sbits, int xrows, int c,
+                                            int row)
+{
+    if constexpr (SMEM) {
+        uint32_t w;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(sbits + 4u * (uint32_t)(c * xrows + row)));
+        return w;
+    } else {
+        return bits[(size_t)c * xrows + row];
+    }
+}
+
+template <bool SMEM>
+__device__ __forceinline__ void backtrack_bits_impl(const uint32_t *bits, int xrows, int tx, int ty,
+                                                    int *first, int *dur)
 {
     const RowMap rm(tx);
+    const int xpl = rm.xpl;
+    const uint32_t sbits = SMEM ? smem_u32(bits) : 0u;
     int idx = tx - 1, y = ty - 1, top = ty - 1;
+    int q = idx / xpl, j = idx - q * xpl;          // token idx = lane q, slot j -> row (j<<5)+q
+    int row = (j << 5) + q;
+    // row of token idx-1
+    auto step_row = [&](int &jj, int &qq) {
+        if (jj > 0) --jj;
+        else { jj = xpl - 1; --qq; }
+        return (jj << 5) + qq;
+    };
+    int jn = j, qn = q;
+    int rown = idx > 0 ? step_row(jn, qn) : 0;
+    int c = y >> 5;
+    uint32_t w = bt_word<SMEM>(bits, sbits, xrows, c, row);
+    uint32_t wn = idx > 0 ? bt_word<SMEM>(bits, sbits, xrows, c, rown) : 0u;
     while (y >= 0) {
-        const int c = y >> 5, s = y & 31;
-        const uint32_t w = (idx != 0) ? bits[(size_t)c * xrows + rm.row(idx)] : 0u;
-        const uint32_t m = w & (0xffffffffu >> (31 - s));
-        if (m == 0u) {
-            y = (c << 5) - 1;  // stays on this token down to the chunk start
+        const int s = y & 31;
+        const uint32_t m = (idx != 0 ? w : 0u) & (0xffffffffu >> (31 - s));
+        if (m == 0u) {  // stays on this token down to the chunk start
+            y = (c << 5) - 1;
+            if (y < 0) break;
+            --c;
+            w = bt_word<SMEM>(bits, sbits, xrows, c, row);
+            wn = idx > 0 ? bt_word<SMEM>(bits, sbits, xrows, c, rown) : 0u;
         } else {
-            const int ys = (c << 5) + (31 - __clz(m));
+            const int p = 31 - __clz(m);
+            const int ys = (c << 5) + p;
             first[idx] = ys;
             dur[idx] = top - ys + 1;
             --idx;
             y = ys - 1;
             top = y;
+            row = rown;
+            w = wn;
+            if (idx > 0) rown = step_row(jn, qn);
+            if (p == 0) {  // crossed into the previous chunk
+                if (y < 0) break;
+                --c;
+                w = bt_word<SMEM>(bits, sbits, xrows, c, row);
+            }
+            wn = idx > 0 ? bt_word<SMEM>(bits, sbits, xrows, c, rown) : 0u;
         }
     }
     if (top >= 0) {
         first[idx] = 0;
         dur[idx] = top + 1;
     }
+}
+
+__device__ __forceinline__ void backtrack_bits(const uint32_t *bits, int xrows, int tx, int ty,
+                                               int *first, int *dur, bool bits_in_smem)
+{
+    if (bits_in_smem) backtrack_bits_impl<true>(bits, xrows, tx, ty, first, dur);
+    else backtrack_bits_impl<false>(bits, xrows, tx, ty, first, dur);
 }
 
 // The reference's degenerate case t_x > t_y: the band of core.pyx:18 is empty, the

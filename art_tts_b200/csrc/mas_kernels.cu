@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(kFastThreads) mas_fast_kernel(const MasArgs a)
         if (active) {
             score = forward_dispatch<XPLMAX>(ring, bits, L.xrows, tx, ty, lane);
             __syncwarp();
-            if (lane == 0) backtrack_bits(bits, L.xrows, tx, ty, first, dur);
+            if (lane == 0) backtrack_bits(bits, L.xrows, tx, ty, first, dur, L.bits_in_smem != 0);
         } else if (degenerate) {
             if (lane == 0) {
                 auto val = [&](int x, int y) {
