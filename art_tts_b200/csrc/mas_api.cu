@@ -266,17 +266,8 @@ int mas_from_prior_f32(const float *mu_x, const float *logs, const float *y, con
     a.frame_idx = frame_idx;
     a.score = score;
     a.bits_ws = static_cast<uint32_t *>(workspace);
-#ifdef MAS_TIMING
-    {   // timing builds: stamps go to the end of an over-allocated workspace
-        const size_t need = mas_workspace_bytes(B, T_x, T_y), tbytes = (size_t)B * 32 * 8;
-        a.timing = (workspace_bytes >= need + tbytes + 16)
-                       ? reinterpret_cast<long long *>(static_cast<char *>(workspace) +
-                                                       ((workspace_bytes - tbytes) & ~(size_t)15))
-                       : nullptr;
-    }
-#endif
-    a.extra_fma = env_int("MAS_PRIOR_EXTRA_FMA", 0);
-    if (a.extra_fma < 0 || a.extra_fma > 2) a.extra_fma = 0;
+    a.extra_fma = env_int("MAS_PRIOR_EXTRA_FMA", 2);
+    if (a.extra_fma < 0 || a.extra_fma > 2) a.extra_fma = 2;
     a.B = B;
     a.F = F;
     a.T_x = T_x;

@@ -130,9 +130,11 @@ struct TileRing {
 // Forward pass of one utterance by ONE warp.  Consumes ceil(t_y/32) tiles from the ring,
 // writes the direction words to bits[chunk*xrows + row] (shared or global memory) and
 // returns V[t_x-1, t_y-1].  Requires 1 <= t_x <= t_y and XPL == ceil(t_x/32).
+// `g0` = index (in the ring's lifetime) of this utterance's first tile: a persistent CTA keeps
+// one ring and its barrier phases running across utterances.
 template <int XPL>
 __device__ __noinline__ float dp_forward(const TileRing ring, uint32_t *bits, int xrows, int tx,
-                                         int ty, int lane)
+                                         int ty, int lane, int g0 = 0)
 {
     float V[XPL];
     uint32_t acc[XPL];
@@ -144,8 +146,8 @@ __device__ __noinline__ float dp_forward(const TileRing ring, uint32_t *bits, in
     const int x0 = lane * XPL;                  // this lane's first token
     float left = (lane == 0) ? 0.0f : kNeg;     // frame 0: v_prev(x=0) = 0, everything else -1e9
     const int ntiles = (ty + kTileY - 1) / kTileY;
-    int stage = 0;
-    uint32_t phase = 0;
+    int stage = g0 % ring.nstages;
+    uint32_t phase = (uint32_t)(g0 / ring.nstages) & 1u;
     for (int t = 0; t < ntiles; ++t) {
         mbar_wait(&ring.full[stage], phase);
         const float *tile = ring.stages + stage * ring.stage_floats;

@@ -67,7 +67,6 @@ struct PriorArgs {
     float *score;
     uint32_t *bits_ws;
     int extra_fma;         // FMA warps sharing the DP warp's scheduler (0..2), see mas_prior.cu
-    long long *timing;     // MAS_TIMING builds only: [B][32] clock64 stamps (taken from the workspace tail)
     int B, F, T_x, T_y;
     int path_esize;
     unsigned long long one;
