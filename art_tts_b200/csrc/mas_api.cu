@@ -204,7 +204,7 @@ int mas_from_prior_plan(int B, int F, int T_x, int T_y, int flags)
     (void)B;
     if (T_x < 1 || T_y < 1 || F < 1) return MAS_ERR_SHAPE;
     FastLayout lay;
-    const Plan plan = choose_plan(T_x, T_y, flags, &lay, prior_extra_smem(F, T_x), 3);
+    const Plan plan = choose_plan(T_x, T_y, flags, &lay, prior_extra_smem(F, T_x, T_y, false), 3);
     return plan == kPlanGeneral ? 1 : 0;
 }
 
@@ -227,7 +227,14 @@ int mas_from_prior_f32(const float *mu_x, const float *logs, const float *y, con
     cudaStream_t st = static_cast<cudaStream_t>(stream);
 
     PriorArgs a{};
-    const Plan plan = choose_plan(T_x, T_y, flags, &a.lay, prior_extra_smem(F, T_x), 3);
+    // prefer two direction-bit buffers in shared memory (backtrack of utterance k overlaps the
+    // forward pass of k+1); else one; else the bits spill to the workspace
+    Plan plan = choose_plan(T_x, T_y, flags, &a.lay, prior_extra_smem(F, T_x, T_y, true), 3);
+    a.bits_slots = 2;
+    if (plan != kPlanFastSmemBits) {
+        plan = choose_plan(T_x, T_y, flags, &a.lay, prior_extra_smem(F, T_x, T_y, false), 3);
+        a.bits_slots = (plan == kPlanFastSmemBits) ? 1 : 0;
+    }
     const bool fused = plan != kPlanGeneral;
     if (!workspace || workspace_bytes < mas_workspace_bytes(B, T_x, T_y)) return MAS_ERR_WORKSPACE;
     if ((uintptr_t)workspace % 16) return MAS_ERR_ALIGN;
@@ -266,8 +273,15 @@ int mas_from_prior_f32(const float *mu_x, const float *logs, const float *y, con
     a.frame_idx = frame_idx;
     a.score = score;
     a.bits_ws = static_cast<uint32_t *>(workspace);
-    a.extra_fma = env_int("MAS_PRIOR_EXTRA_FMA", 2);
-    if (a.extra_fma < 0 || a.extra_fma > 2) a.extra_fma = 2;
+    a.stats = nullptr;
+    if (env_int("MAS_PRIOR_STATS", 0)) {  // profiling aid: counters at the tail of an over-sized workspace
+        const size_t need = mas_workspace_bytes(B, T_x, T_y), sbytes = (size_t)1024 * 16 * 8;
+        if (workspace_bytes >= need + sbytes + 16)
+            a.stats = reinterpret_cast<long long *>(static_cast<char *>(workspace) +
+                                                    ((workspace_bytes - sbytes) & ~(size_t)15));
+    }
+    a.extra_fma = env_int("MAS_PRIOR_EXTRA_FMA", 1);
+    if (a.extra_fma < 0 || a.extra_fma > 1) a.extra_fma = 1;
     a.B = B;
     a.F = F;
     a.T_x = T_x;

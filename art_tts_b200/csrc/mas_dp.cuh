@@ -134,7 +134,7 @@ struct TileRing {
 // one ring and its barrier phases running across utterances.
 template <int XPL>
 __device__ __noinline__ float dp_forward(const TileRing ring, uint32_t *bits, int xrows, int tx,
-                                         int ty, int lane, int g0 = 0)
+                                         int ty, int lane, int g0 = 0, long long *wait_acc = nullptr)
 {
     float V[XPL];
     uint32_t acc[XPL];
@@ -149,7 +149,13 @@ __device__ __noinline__ float dp_forward(const TileRing ring, uint32_t *bits, in
     int stage = g0 % ring.nstages;
     uint32_t phase = (uint32_t)(g0 / ring.nstages) & 1u;
     for (int t = 0; t < ntiles; ++t) {
-        mbar_wait(&ring.full[stage], phase);
+        if (wait_acc) {  // profiling aid: cycles this warp spends starved of tiles
+            const long long t0 = clock64();
+            mbar_wait(&ring.full[stage], phase);
+            *wait_acc += clock64() - t0;
+        } else {
+            mbar_wait(&ring.full[stage], phase);
+        }
         const float *tile = ring.stages + stage * ring.stage_floats;
         const int y0 = t * kTileY;
         const int nsteps = min(kTileY, ty - y0);

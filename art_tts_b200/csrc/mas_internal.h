@@ -66,14 +66,16 @@ struct PriorArgs {
     int32_t *frame_idx;
     float *score;
     uint32_t *bits_ws;
+    int bits_slots;        // direction-bit buffers in shared memory: 2, 1, or 0 (spilled to the workspace)
     int extra_fma;         // FMA warps sharing the DP warp's scheduler (0..2), see mas_prior.cu
+    long long *stats;      // optional [grid][16] cycle counters (MAS_PRIOR_STATS=1), else NULL
     int B, F, T_x, T_y;
     int path_esize;
     unsigned long long one;
     FastLayout lay;
 };
 cudaError_t launch_from_prior(const PriorArgs &a, cudaStream_t st);
-size_t prior_extra_smem(int F, int T_x);
+size_t prior_extra_smem(int F, int T_x, int T_y, bool second_bits);
 cudaError_t launch_log_prior(const float *mu_x, const float *y, float *lp, int B, int F, int T_x,
                              int T_y, cudaStream_t st);
 

@@ -36,13 +36,14 @@ namespace mas {
 // most of one scheduler's issue slots to run at its natural ~85 cycles/frame, and it cannot be
 // given priority over the FMA warps' long independent streams (measured: sharing a scheduler
 // with 4 FMA warps serialised the two).  So scheduler 3 is reserved for the latency-bound
-// agents -- DP warp (warp 3) and slab loader (warp 7) -- plus an optional, tunable number of
-// FMA warps (warps 11, 15); schedulers 0-2 run 4 FMA warps each.
+// agents -- DP warp (warp 3), slab loader (warp 7), backtrack warp (warp 11) -- plus an optional
+// FMA warp (warp 15); schedulers 0-2 run 4 FMA warps each.
 constexpr int kFmaPerSmsp = 4;
 constexpr int kPriorWarps = 16;
 constexpr int kPriorThreads = 32 * kPriorWarps;
 constexpr int kDpWarp = 3;
 constexpr int kLoaderWarp = 7;
+constexpr int kBacktrackWarp = 11;
 constexpr int kZeroBytes = 4096;  // zeroed shared buffer behind the bulk stores
 constexpr int kSlabs = 4;         // y slabs in flight (own ring, see below)
 
@@ -51,7 +52,7 @@ __device__ __forceinline__ int fma_warp_index(int warp, int extra)
 {
     const int sm = warp & 3, slot = warp >> 2;
     if (sm != 3) return slot * 3 + sm;
-    return (slot >= 2 && slot - 2 < extra) ? 3 * kFmaPerSmsp + (slot - 2) : -1;
+    return (slot >= 3 && slot - 3 < extra) ? 3 * kFmaPerSmsp + (slot - 3) : -1;
 }
 
 // extra shared memory of the fused kernel (after the ring / bits / bars of FastLayout):
@@ -60,31 +61,40 @@ __device__ __forceinline__ int fma_warp_index(int warp, int extra)
 //   yslab [kSlabs][F][32]   ring of 32-frame slabs of y (own ring: a slab is free as soon as
 //                           the FMA warps are done with it, not when the DP warp has consumed
 //                           the tile made from it)
-//   ybar  [kSlabs]          slab-ready mbarriers (loader -> FMA warps)
+//   ysq   [kSlabs][32]      -0.5 * |y_j|^2 per frame of the slab (computed by the loader warp)
+//   ybar  [kSlabs]          slab-landed mbarriers (cp.async completion -> FMA warps)
+//   qbar  [kSlabs]          ysq-ready mbarriers (loader -> FMA warps; only needed by a pass's
+//                           epilogue, so the loader's arithmetic is off the critical path)
 //   yfree [kSlabs]          slab-consumed mbarriers (FMA warps -> loader); a dedicated pair per
 //                           slot keeps every parity wait at most one phase away by construction
-//   ctrl  [4] int           zero-fill progress counter (loader -> DP warp)
+//   ctrl  [4] int           progress counters between loader / DP warp / backtrack warp
+//   bits2 [nch][xrows]      optional second direction-bit buffer
 //   zero  [kZeroBytes]      zeros, source of the bulk stores that clear the output path
 struct PriorSmem {
-    size_t off_mu, off_musq, off_yslab, off_ybar, off_ctrl, off_zero, total_extra;
+    size_t off_mu, off_musq, off_yslab, off_ysq, off_ybar, off_ctrl, off_zero, off_bits2, total_extra;
 };
 
-__host__ __device__ inline PriorSmem prior_smem(int F, int xrows)
+__host__ __device__ inline PriorSmem prior_smem(int F, int xrows, size_t bits2_bytes = 0)
 {
     PriorSmem s;
     s.off_mu = 0;
     s.off_musq = s.off_mu + (size_t)F * xrows * 4;
     s.off_yslab = s.off_musq + (size_t)xrows * 4;
-    s.off_ybar = s.off_yslab + (size_t)kSlabs * F * kTileY * 4;
-    s.off_ctrl = s.off_ybar + (size_t)kSlabs * 16;
+    s.off_ysq = s.off_yslab + (size_t)kSlabs * F * kTileY * 4;
+    s.off_ybar = s.off_ysq + (size_t)kSlabs * kTileY * 4;
+    s.off_ctrl = s.off_ybar + (size_t)kSlabs * 24;
     s.off_zero = (s.off_ctrl + 16 + 15) & ~(size_t)15;
-    s.total_extra = s.off_zero + kZeroBytes;
+    s.off_bits2 = s.off_zero + kZeroBytes;
+    s.total_extra = s.off_bits2 + bits2_bytes;
     return s;
 }
 
-size_t prior_extra_smem(int F, int T_x)
+// `second_bits`: room for a second direction-bit buffer (the backtrack warp works on one while the
+// DP warp fills the other)
+size_t prior_extra_smem(int F, int T_x, int T_y, bool second_bits)
 {
-    return prior_smem(F, ((T_x + 31) / 32) * 32).total_extra;
+    const size_t xrows = (size_t)((T_x + 31) / 32) * 32, nch = (size_t)(T_y + 31) / 32;
+    return prior_smem(F, (int)xrows, second_bits ? nch * xrows * 4 : 0).total_extra;
 }
 
 // one cell of the prior, same operation order as the producers / log_prior_kernel
@@ -104,12 +114,13 @@ __device__ __forceinline__ float lp_cell(const float *mub, const float *yb, int 
 
 template <int XPLMAX>
 __device__ __forceinline__ float prior_forward_dispatch(const TileRing &ring, uint32_t *bits,
-                                                        int xrows, int tx, int ty, int lane, int g0)
+                                                        int xrows, int tx, int ty, int lane, int g0,
+                                                        long long *wacc)
 {
     const int xpl = (tx + 31) >> 5;
 #define MAS_CASE(N)                                                                           \
     case N:                                                                                   \
-        if constexpr (N <= XPLMAX) return dp_forward<N>(ring, bits, xrows, tx, ty, lane, g0); \
+        if constexpr (N <= XPLMAX) return dp_forward<N>(ring, bits, xrows, tx, ty, lane, g0, wacc); \
         break;
     switch (xpl) {
         MAS_CASE(1) MAS_CASE(2) MAS_CASE(3) MAS_CASE(4) MAS_CASE(5) MAS_CASE(6) MAS_CASE(7)
@@ -121,59 +132,67 @@ __device__ __forceinline__ float prior_forward_dispatch(const TileRing &ring, ui
     return 0.0f;
 }
 
-// One work item = 32 tokens x 16 frames of the prior by one warp: thread (xg, yg) owns 4 tokens
-// x 4 frames, i.e. 16 independent fp32 FMA chains fed by 2 LDS.128 per feature (both
-// conflict-free).  Items are half the size of a full 32x32 pass so that a tile splits into
-// enough pieces to keep every FMA warp busy.  Accumulation runs over f in ascending order with
+// One work item = 32 tokens x 32 frames of the prior by one warp: thread (xg, yg) owns 4 tokens
+// x 8 frames, i.e. 32 independent fp32 FMA chains fed by 3 conflict-free LDS.128 per feature
+// (88% of the issued instructions are FFMA).  Accumulation runs over f in ascending order with
 // one FMA per term, exactly like log_prior_kernel / lp_cell: all three are bit-identical.
-__device__ __forceinline__ void prior_item(const float *__restrict__ mu_s, const float *__restrict__ musq,
-                                           const float *__restrict__ ys, float *__restrict__ tile, int F,
-                                           int xrows, int p, int h, int lane, float cst, const RowMap rm)
+__device__ __forceinline__ void prior_pass(const float *__restrict__ mu_s, const float *__restrict__ musq,
+                                           const float *__restrict__ ys, const float *__restrict__ ysq,
+                                           float *__restrict__ tile, int F, int xrows, int p, int lane,
+                                           float cst, const RowMap rm, uint64_t *qbar, uint32_t qparity)
 {
     const int xg = lane >> 2, yg = lane & 3;
     const int x0 = 32 * p + 4 * xg;
-    const int s0 = 16 * h + 4 * yg;             // first of this thread's 4 frames
-    const float *mp = mu_s + x0;
-    const float *yp = ys + s0;
-    // -0.5*|y_j|^2 (tts.py:488-490): of the 8 lanes that share these 4 frames (same yg), lanes
-    // xg = 0..3 each accumulate ONE of them alongside the main loop; shuffles distribute them.
-    const float *yq = ys + s0 + (xg & 3);
-    float qsum = 0.0f;
-    float acc[4][4];
+    uint32_t ma = smem_u32(mu_s + x0);            // walks down the feature axis of mu_s
+    const uint32_t mstep = 4u * (uint32_t)xrows;
+    uint32_t ya = smem_u32(ys + 8 * yg);          // slab row stride is a constant 128 B
+    float acc[4][8];
 #pragma unroll
     for (int r = 0; r < 4; ++r)
 #pragma unroll
-        for (int k = 0; k < 4; ++k) acc[r][k] = 0.0f;
+        for (int k = 0; k < 8; ++k) acc[r][k] = 0.0f;
 #pragma unroll 4
     for (int f = 0; f < F; ++f) {
-        const float4 m = *reinterpret_cast<const float4 *>(mp + (size_t)f * xrows);
-        const float4 yv = *reinterpret_cast<const float4 *>(yp + f * kTileY);
-        const float yo = yq[f * kTileY];
+        const float4 m = lds128(ma);
+        const float4 y0 = lds128(ya);
+        const float4 y1 = lds128(ya + 16);
+        ma += mstep;
+        ya += 4 * kTileY;
         const float mr[4] = {m.x, m.y, m.z, m.w};
-        const float yk[4] = {yv.x, yv.y, yv.z, yv.w};
+        const float yk[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
 #pragma unroll
         for (int r = 0; r < 4; ++r)
 #pragma unroll
-            for (int k = 0; k < 4; ++k) acc[r][k] = __fmaf_rn(mr[r], yk[k], acc[r][k]);
-        qsum = __fmaf_rn(yo, yo, qsum);
+            for (int k = 0; k < 8; ++k) acc[r][k] = __fmaf_rn(mr[r], yk[k], acc[r][k]);
     }
-    qsum *= -0.5f;
-    float q[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) q[k] = __shfl_sync(kFull, qsum, (k << 2) | yg);  // lane (xg=k, yg)
-    const int chunk = 4 * h + yg;               // 16-byte chunk of the 128-byte tile row
+    mbar_wait(qbar, qparity);  // -0.5|y|^2 of this slab (loader warp), long ready by now
+    const float4 qa = *reinterpret_cast<const float4 *>(ysq + 8 * yg);
+    const float4 qb = *reinterpret_cast<const float4 *>(ysq + 8 * yg + 4);
+    const float q[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
         const int x = x0 + r;
         const float msq = musq[x];
+        float o[8];
         // tts.py:495: y_square - y_mu_double + mu_square + const  (y_mu_double == -cross)
-        const float o0 = ((q[0] + acc[r][0]) + msq) + cst, o1 = ((q[1] + acc[r][1]) + msq) + cst;
-        const float o2 = ((q[2] + acc[r][2]) + msq) + cst, o3 = ((q[3] + acc[r][3]) + msq) + cst;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] = ((q[k] + acc[r][k]) + msq) + cst;
         const int pr = rm.row(x);  // physical row of token x in the staged tile (mas_dp.cuh)
-        *reinterpret_cast<float4 *>(tile + (pr << 5) + ((chunk ^ (pr & 7)) << 2)) =
-            make_float4(o0, o1, o2, o3);
+        float *row = tile + (pr << 5);
+        *reinterpret_cast<float4 *>(row + (((2 * yg) ^ (pr & 7)) << 2)) = make_float4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<float4 *>(row + (((2 * yg + 1) ^ (pr & 7)) << 2)) = make_float4(o[4], o[5], o[6], o[7]);
     }
 }
+
+// Optional coarse per-CTA cycle accounting (PriorArgs::stats, enabled by MAS_PRIOR_STATS=1;
+// read back by profiles/prior_stats.py).  clock64 at phase boundaries only: no cost when off.
+struct Stat {
+    long long acc = 0, t0 = 0;
+    bool on;
+    __device__ __forceinline__ explicit Stat(bool e) : on(e) {}
+    __device__ __forceinline__ void begin() { if (on) t0 = clock64(); }
+    __device__ __forceinline__ void end() { if (on) acc += clock64() - t0; }
+};
 
 __device__ __forceinline__ void fma_bar(int nthreads)
 {
@@ -196,9 +215,11 @@ __global__ void __launch_bounds__(kPriorThreads) mas_prior_kernel(const PriorArg
     float *mu_s = reinterpret_cast<float *>(extra + ps.off_mu);
     float *musq = reinterpret_cast<float *>(extra + ps.off_musq);
     float *yslab = reinterpret_cast<float *>(extra + ps.off_yslab);
+    float *ysq = reinterpret_cast<float *>(extra + ps.off_ysq);
     uint64_t *ybar = reinterpret_cast<uint64_t *>(extra + ps.off_ybar);
     volatile int *zdone = reinterpret_cast<volatile int *>(extra + ps.off_ctrl);
     uint32_t *zbuf = reinterpret_cast<uint32_t *>(extra + ps.off_zero);
+    uint32_t *bits2 = reinterpret_cast<uint32_t *>(extra + ps.off_bits2);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nfma = 3 * kFmaPerSmsp + a.extra_fma;
@@ -219,9 +240,12 @@ __global__ void __launch_bounds__(kPriorThreads) mas_prior_kernel(const PriorArg
         }
         for (int s = 0; s < kSlabs; ++s) {
             mbar_init(&ybar[s], 32);             // one cp.async arrival per loader lane
+            mbar_init(&ybar[2 * kSlabs + s], 1);  // qbar: loader lane 0 once ysq is stored
             mbar_init(&ybar[kSlabs + s], nfma);  // yfree: every FMA warp arrives once per tile
         }
-        *zdone = 0;
+        zdone[0] = 0;
+        zdone[1] = 0;
+        zdone[2] = 0;
         mbar_fence_init();
     }
     for (int i = tid; i < kZeroBytes / 4; i += kPriorThreads) zbuf[i] = 0u;
@@ -240,51 +264,135 @@ __global__ void __launch_bounds__(kPriorThreads) mas_prior_kernel(const PriorArg
         ntiles = active ? (ty + kTileY - 1) / kTileY : 0;
     };
 
+    // ctrl words (shared, volatile): [0] zdone   loader     -> backtrack warp: utterances whose output
+    //                                            path has been cleared
+    //                                [1] fwd_done DP warp    -> backtrack warp: forward passes finished
+    //                                [2] bt_done  backtrack  -> DP warp: direction-bit buffers released
+    volatile int *fwd_done = zdone + 1, *bt_done = zdone + 2;
+    const int bslots = a.bits_slots;  // direction-bit buffers in shared memory (0 = spilled to global)
+    auto bits_of = [&](int u, int k) -> uint32_t * {
+        if (!L.bits_in_smem) return a.bits_ws + (size_t)u * L.nch * L.xrows;
+        return (k & 1) && bslots == 2 ? bits2 : bits_smem;
+    };
+
     if (warp == kDpWarp) {
-        // ======================= DP warp =======================
+        // ======================= DP warp: forward recurrence only =======================
         int g = 0, k = 0;
+        Stat st_fwd(a.stats != nullptr), st_w(a.stats != nullptr), st_all(a.stats != nullptr);
+        long long dp_wait = 0;
+        st_all.begin();
         for (int u = blockIdx.x; u < a.B; u += gridDim.x, ++k) {
             int tx, ty, ntiles;
             bool degenerate;
             geometry(u, tx, ty, ntiles, degenerate);
-            uint32_t *bits = L.bits_in_smem ? bits_smem : a.bits_ws + (size_t)u * L.nch * L.xrows;
-            for (int x = lane; x < T_x; x += 32) dur[x] = 0;
-            __syncwarp();
             float score = 0.0f;
             if (ntiles > 0) {
-                score = prior_forward_dispatch<XPLMAX>(ring, bits, L.xrows, tx, ty, lane, g);
+                // the bit buffer of utterance k is free once utterance k-bslots has been backtracked
+                st_w.begin();
+                if (bslots > 0)
+                    while (*bt_done < k - bslots + 1) __nanosleep(32);
+                __threadfence_block();
+                st_w.end();
+                st_fwd.begin();
+                score = prior_forward_dispatch<XPLMAX>(ring, bits_of(u, k), L.xrows, tx, ty, lane, g,
+                                                       a.stats ? &dp_wait : nullptr);
                 g += ntiles;
-                __syncwarp();
-                if (lane == 0) backtrack_bits(bits, L.xrows, tx, ty, first, dur, L.bits_in_smem != 0);
+                st_fwd.end();
+                if (lane == 0 && a.score) a.score[u] = score;
+            }
+            __threadfence_block();
+            __syncwarp();
+            if (lane == 0) *fwd_done = k + 1;  // direction bits of utterance k are complete
+        }
+        st_all.end();
+        if (a.stats && lane == 0) {
+            long long *o = a.stats + (size_t)blockIdx.x * 16;
+            o[0] = st_all.acc; o[1] = st_fwd.acc; o[3] = st_w.acc;
+            o[5] = k; o[6] = g; o[7] = dp_wait;
+        }
+    } else if (warp == kBacktrackWarp) {
+        // ======================= backtrack warp: path, durations, frame index =======================
+        // Runs one utterance behind the DP warp on the second bit buffer, so the frame-sequential
+        // recurrence never pauses for the (equally sequential) backtrack.
+        int k = 0;
+        Stat st_bt(a.stats != nullptr), st_z(a.stats != nullptr), st_out(a.stats != nullptr),
+            st_w(a.stats != nullptr);
+        for (int u = blockIdx.x; u < a.B; u += gridDim.x, ++k) {
+            int tx, ty, ntiles;
+            bool degenerate;
+            geometry(u, tx, ty, ntiles, degenerate);
+            for (int x = lane; x < T_x; x += 32) dur[x] = 0;
+            st_w.begin();
+            while (*fwd_done <= k) __nanosleep(32);
+            __threadfence_block();
+            __syncwarp();
+            st_w.end();
+            st_bt.begin();
+            if (ntiles > 0) {
+                if (lane == 0) backtrack_bits(bits_of(u, k), L.xrows, tx, ty, first, dur, L.bits_in_smem != 0);
             } else if (degenerate) {
                 if (lane == 0) {  // reference semantics for t_x > t_y: raw prior values (mas_dp.cuh)
                     const float *mub = a.mu_x + (int64_t)u * F * T_x;
                     const float *yb = a.y + (int64_t)u * F * T_y;
                     auto val = [&](int x, int y) { return lp_cell(mub, yb, F, T_x, T_y, x, y, cst); };
                     backtrack_degenerate(val, tx, ty, first, dur);
-                    score = val(tx - 1, ty - 1);
+                    if (a.score) a.score[u] = val(tx - 1, ty - 1);
                 }
-                score = __shfl_sync(kFull, score, 0);
+            } else if (lane == 0 && a.score) {
+                a.score[u] = 0.0f;
             }
+            __threadfence_block();
             __syncwarp();
-            if (lane == 0 && a.score) a.score[u] = score;
+            if (lane == 0) *bt_done = k + 1;  // the DP warp may reuse this bit buffer
+            st_bt.end();
             // the output path of utterance k must have been cleared before its 1-cells are written
+            st_z.begin();
             if (a.path) {
                 while (*zdone <= k) __nanosleep(64);
                 __threadfence_block();
             }
+            st_z.end();
+            st_out.begin();
             char *pb = a.path ? static_cast<char *>(a.path) + (int64_t)u * T_x * T_y * a.path_esize : nullptr;
             write_path_ones(pb, a.durations ? a.durations + (int64_t)u * T_x : nullptr, first, dur, T_x,
                             T_y, a.path_esize, a.one, lane, 32);
             write_frame_idx(a.frame_idx ? a.frame_idx + (int64_t)u * T_y : nullptr, first, dur, T_x, ty,
                             a.T_y, lane, 32);
             __syncwarp();
+            st_out.end();
+        }
+        if (a.stats && lane == 0) {
+            long long *o = a.stats + (size_t)blockIdx.x * 16;
+            o[2] = st_bt.acc; o[4] = st_out.acc; o[13] = st_z.acc; o[14] = st_w.acc;
         }
     } else if (warp == kLoaderWarp) {
         // ======================= slab loader =======================
         // y[:, 32t..32t+31] -> shared (cp.async, completion signalled straight to the slab barrier),
         // and the zero-fill of the dense output path (bulk stores drained by the copy engine).
         const bool vec16 = (T_y % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.y) & 15) == 0);
+        constexpr int kLag = kSlabs - 2;  // slabs copying while an older one is being finished
+        int gfin = 0;                     // next slab to finish
+        auto finish_slab = [&](int gg) {
+            const int s = gg % kSlabs;
+            __syncwarp();                 // every lane's copies of this slab have landed
+            const float *src = yslab + (size_t)s * F * kTileY + lane;
+            float q = 0.0f;
+            int f = 0;
+            for (; f + 16 <= F; f += 16) {  // 16 loads in flight, then the ordered FMA chain
+                float v[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = src[(f + i) * kTileY];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) q = __fmaf_rn(v[i], v[i], q);
+            }
+            for (; f < F; ++f) {
+                const float v = src[f * kTileY];
+                q = __fmaf_rn(v, v, q);
+            }
+            ysq[s * kTileY + lane] = -0.5f * q;  // tts.py:488-490  y_square
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ybar[2 * kSlabs + s]);
+        };
         int g = 0, k = 0;
         for (int u = blockIdx.x; u < a.B; u += gridDim.x, ++k) {
             int tx, ty, ntiles;
@@ -300,6 +408,8 @@ __global__ void __launch_bounds__(kPriorThreads) mas_prior_kernel(const PriorArg
             } else {
                 zero_fill_part(pb, pbytes, 0, 1, lane, 32);
             }
+            // Software pipeline over the CTA-lifetime tile index: slab copies run kLag tiles ahead
+            // of the point where a slab is finished (-0.5|y|^2 per frame, then the ready barrier).
             for (int t = 0; t < ntiles; ++t, ++g) {
                 const int s = g % kSlabs;
                 if (g >= kSlabs)  // slot's previous slab (tile g-kSlabs) fully used by the FMA warps
@@ -320,8 +430,16 @@ __global__ void __launch_bounds__(kPriorThreads) mas_prior_kernel(const PriorArg
                     for (int f = 0; f < F; ++f)
                         cp_async4(dst + f * kTileY + lane, src + (int64_t)f * T_y, bytes);
                 }
-                cp_async_arrive(&ybar[s]);  // fires when this lane's copies have landed
+                cp_async_arrive(&ybar[s]);  // slab-landed barrier fires when this lane's copies arrive
+                asm volatile("cp.async.commit_group;" ::: "memory");
+                if (g - gfin >= kLag) {  // oldest unfinished slab has had kLag tiles to land
+                    asm volatile("cp.async.wait_group %0;" ::"n"(kLag) : "memory");
+                    finish_slab(gfin++);
+                }
             }
+            // drain: finish the slabs still in flight (the FMA warps of THIS utterance need them)
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            while (gfin < g) finish_slab(gfin++);
             // zeros of utterance k are in global memory -> the DP warp may write its 1-cells
             if (zbulk) bulk_wait_all();
             __threadfence_block();
@@ -330,7 +448,7 @@ __global__ void __launch_bounds__(kPriorThreads) mas_prior_kernel(const PriorArg
         }
     } else if (cw >= 0) {
         // ======================= FMA warps =======================
-        // Work items (tile, 32-token pass, 16-frame half) are dealt round-robin over the FMA warps,
+        // Work items (tile, 32-token pass) are dealt round-robin over the FMA warps,
         // continuing across tiles and utterances.  Every FMA warp waits for every slab and arrives
         // on every tile's `full` barrier (with or without work in it): parity waits are only sound
         // if no waiter can fall two phases behind or run a phase ahead of a barrier.
@@ -338,6 +456,9 @@ __global__ void __launch_bounds__(kPriorThreads) mas_prior_kernel(const PriorArg
         const int ftid = cw * 32 + lane;
         int g = 0;
         int item0 = 0;  // running item counter: keeps the deal balanced across tiles/utterances
+        const bool son = a.stats != nullptr && cw == 0;
+        Stat st_mu(son), st_e(son), st_y(son), st_c(son), st_all(son);
+        st_all.begin();
         for (int u = blockIdx.x; u < a.B; u += gridDim.x) {
             int tx, ty, ntiles;
             bool degenerate;
@@ -347,6 +468,7 @@ __global__ void __launch_bounds__(kPriorThreads) mas_prior_kernel(const PriorArg
             const int xr = npass * 32;  // token rows any pass may touch
             const float *mub = a.mu_x + (int64_t)u * F * T_x;
             const RowMap rm(tx);
+            st_mu.begin();
             fma_bar(nft);  // every FMA warp is done with the previous utterance's mu_s
             for (int i = ftid; i < F * xr; i += nft) {  // all requests in flight at once
                 const int f = i / xr, x = i - f * xr;
@@ -372,28 +494,41 @@ __global__ void __launch_bounds__(kPriorThreads) mas_prior_kernel(const PriorArg
                 musq[x] = -0.5f * s;  // tts.py:494  mu_square = sum(factor * mu^2)
             }
             fma_bar(nft);
-            const int nit = 2 * npass;  // items per tile
+            st_mu.end();
+            const int nit = npass;  // items per tile: one 32-token pass each
             for (int t = 0; t < ntiles; ++t, ++g) {
                 const int s = g % NS, ys = g % kSlabs;
                 const int lo = max(0, tx + t * kTileY - ty);
                 const int hi = min(tx - 1, t * kTileY + kTileY - 1);
+                st_e.begin();
                 if (g >= NS) mbar_wait(&ring.empty[s], ((g / NS) - 1) & 1);  // DP consumed tile g-NS
+                st_e.end();
+                st_y.begin();
                 mbar_wait(&ybar[ys], (g / kSlabs) & 1);                       // slab has landed
+                st_y.end();
+                st_c.begin();
                 int it = (cw - item0) % nfma;
                 if (it < 0) it += nfma;
                 for (; it < nit; it += nfma) {
-                    const int p = it >> 1, h = it & 1;
-                    if (32 * p <= hi && 32 * p + 31 >= lo && t * kTileY + 16 * h < ty)
-                        prior_item(mu_s, musq, yslab + (size_t)ys * F * kTileY,
-                                   stages + (size_t)s * ring.stage_floats, F, L.xrows, p, h, lane, cst, rm);
+                    const int p = it;
+                    if (32 * p <= hi && 32 * p + 31 >= lo)
+                        prior_pass(mu_s, musq, yslab + (size_t)ys * F * kTileY, ysq + ys * kTileY,
+                                   stages + (size_t)s * ring.stage_floats, F, L.xrows, p, lane, cst, rm,
+                                   &ybar[2 * kSlabs + ys], (g / kSlabs) & 1);
                 }
                 item0 = (item0 + nit) % nfma;
                 __syncwarp();
+                st_c.end();
                 if (lane == 0) {
                     mbar_arrive(&ring.full[s]);           // tile g produced (this warp's share)
                     mbar_arrive(&ybar[kSlabs + ys]);      // slab g no longer needed by this warp
                 }
             }
+        }
+        st_all.end();
+        if (son && lane == 0) {
+            long long *o = a.stats + (size_t)blockIdx.x * 16 + 8;
+            o[0] = st_all.acc; o[1] = st_mu.acc; o[2] = st_e.acc; o[3] = st_y.acc; o[4] = st_c.acc;
         }
     }
 }
