@@ -15,6 +15,7 @@ from . import build as _build
 MAS_F32, MAS_F16, MAS_BF16, MAS_F64, MAS_I32, MAS_U8, MAS_I64 = range(7)
 FLAG_FORCE_GENERAL = 1
 FLAG_NO_ASYNC = 2
+FLAG_SPILL_BITS = 4
 
 _DTYPES = {
     torch.float32: MAS_F32,

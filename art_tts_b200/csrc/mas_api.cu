@@ -57,7 +57,7 @@ Plan choose_plan(int T_x, int T_y, int flags, FastLayout *lay, size_t extra_smem
         return (size_t)S * stage_bytes + (bits_smem ? bits_bytes : 0) + misc;
     };
     if (T_x <= kMaxFastTx && !(flags & MAS_FLAG_FORCE_GENERAL)) {
-        const bool fits = total(2, true) <= (size_t)kSmemBudget;
+        const bool fits = !(flags & MAS_FLAG_SPILL_BITS) && total(2, true) <= (size_t)kSmemBudget;
         L.bits_in_smem = fits ? 1 : 0;
         plan = fits ? kPlanFastSmemBits : kPlanFastSpillBits;
         if (total(2, fits) > (size_t)kSmemBudget) plan = kPlanGeneral;  // cannot happen for T_x<=512
@@ -231,7 +231,11 @@ int mas_from_prior_f32(const float *mu_x, const float *logs, const float *y, con
     // forward pass of k+1); else one; else the bits spill to the workspace
     Plan plan = choose_plan(T_x, T_y, flags, &a.lay, prior_extra_smem(F, T_x, T_y, true), 3);
     a.bits_slots = 2;
-    if (plan != kPlanFastSmemBits) {
+    if (env_int("MAS_PRIOR_SPILL", 0)) {  // tuning knob: bits in L2/HBM, shared memory spent on a deeper ring
+        plan = choose_plan(T_x, T_y, flags | MAS_FLAG_SPILL_BITS, &a.lay,
+                           prior_extra_smem(F, T_x, T_y, false), 6);
+        a.bits_slots = 0;
+    } else if (plan != kPlanFastSmemBits) {
         plan = choose_plan(T_x, T_y, flags, &a.lay, prior_extra_smem(F, T_x, T_y, false), 3);
         a.bits_slots = (plan == kPlanFastSmemBits) ? 1 : 0;
     }
@@ -280,6 +284,8 @@ int mas_from_prior_f32(const float *mu_x, const float *logs, const float *y, con
             a.stats = reinterpret_cast<long long *>(static_cast<char *>(workspace) +
                                                     ((workspace_bytes - sbytes) & ~(size_t)15));
     }
+    a.fma_per_smsp = env_int("MAS_PRIOR_FMA_PER_SMSP", 2);
+    if (a.fma_per_smsp < 1 || a.fma_per_smsp > 4) a.fma_per_smsp = 2;
     a.extra_fma = env_int("MAS_PRIOR_EXTRA_FMA", 1);
     if (a.extra_fma < 0 || a.extra_fma > 1) a.extra_fma = 1;
     a.B = B;

@@ -67,6 +67,7 @@ struct PriorArgs {
     float *score;
     uint32_t *bits_ws;
     int bits_slots;        // direction-bit buffers in shared memory: 2, 1, or 0 (spilled to the workspace)
+    int fma_per_smsp;      // FMA warps on each of schedulers 0-2 (1..4)
     int extra_fma;         // FMA warps sharing the DP warp's scheduler (0..2), see mas_prior.cu
     long long *stats;      // optional [grid][16] cycle counters (MAS_PRIOR_STATS=1), else NULL
     int B, F, T_x, T_y;

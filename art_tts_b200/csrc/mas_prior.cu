@@ -48,11 +48,11 @@ constexpr int kZeroBytes = 4096;  // zeroed shared buffer behind the bulk stores
 constexpr int kSlabs = 4;         // y slabs in flight (own ring, see below)
 
 // FMA-warp index of a warp (or -1): schedulers 0-2 first, then the extras on scheduler 3
-__device__ __forceinline__ int fma_warp_index(int warp, int extra)
+__device__ __forceinline__ int fma_warp_index(int warp, int extra, int per_smsp)
 {
     const int sm = warp & 3, slot = warp >> 2;
-    if (sm != 3) return slot * 3 + sm;
-    return (slot >= 3 && slot - 3 < extra) ? 3 * kFmaPerSmsp + (slot - 3) : -1;
+    if (sm != 3) return slot < per_smsp ? slot * 3 + sm : -1;
+    return (slot >= 3 && slot - 3 < extra) ? 3 * per_smsp + (slot - 3) : -1;
 }
 
 // extra shared memory of the fused kernel (after the ring / bits / bars of FastLayout):
@@ -133,16 +133,18 @@ __device__ __forceinline__ float prior_forward_dispatch(const TileRing &ring, ui
 }
 
 // One work item = 32 tokens x 32 frames of the prior by one warp: thread (xg, yg) owns 4 tokens
-// x 8 frames, i.e. 32 independent fp32 FMA chains fed by 3 conflict-free LDS.128 per feature
-// (88% of the issued instructions are FFMA).  Accumulation runs over f in ascending order with
+// x 8 frames, i.e. 32 independent fp32 FMA chains (16 packed FFMA2 per feature) fed by 3
+// conflict-free LDS.128.  Accumulation runs over f in ascending order with
 // one FMA per term, exactly like log_prior_kernel / lp_cell: all three are bit-identical.
 __device__ __forceinline__ void prior_pass(const float *__restrict__ mu_s, const float *__restrict__ musq,
                                            const float *__restrict__ ys, const float *__restrict__ ysq,
-                                           float *__restrict__ tile, int F, int xrows, int p, int lane,
-                                           float cst, const RowMap rm, uint64_t *qbar, uint32_t qparity)
+                                           float *__restrict__ tile, int F, int xrows, int xbase,
+                                           int xlimit, int lane, float cst, const RowMap rm,
+                                           uint64_t *qbar, uint32_t qparity)
 {
+    // tokens xbase .. xbase+31 (xbase % 4 == 0); rows >= xlimit are neither needed nor stored
     const int xg = lane >> 2, yg = lane & 3;
-    const int x0 = 32 * p + 4 * xg;
+    const int x0 = xbase + 4 * xg;
     uint32_t ma = smem_u32(mu_s + x0);            // walks down the feature axis of mu_s
     const uint32_t mstep = 4u * (uint32_t)xrows;
     uint32_t ya = smem_u32(ys + 8 * yg);          // slab row stride is a constant 128 B
@@ -151,20 +153,28 @@ __device__ __forceinline__ void prior_pass(const float *__restrict__ mu_s, const
     for (int r = 0; r < 4; ++r)
 #pragma unroll
         for (int k = 0; k < 8; ++k) acc[r][k] = 0.0f;
-#pragma unroll 4
-    for (int f = 0; f < F; ++f) {
-        const float4 m = lds128(ma);
-        const float4 y0 = lds128(ya);
-        const float4 y1 = lds128(ya + 16);
-        ma += mstep;
-        ya += 4 * kTileY;
+    // software-pipelined: the operands of feature f+1 are in flight while feature f is consumed;
+    // packed FMAs (two frames per instruction) halve the issue slots of the 32 chains
+    auto fma_tile = [&](const float4 &m, const float4 &y0, const float4 &y1) {
         const float mr[4] = {m.x, m.y, m.z, m.w};
         const float yk[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
 #pragma unroll
         for (int r = 0; r < 4; ++r)
 #pragma unroll
-            for (int k = 0; k < 8; ++k) acc[r][k] = __fmaf_rn(mr[r], yk[k], acc[r][k]);
+            for (int k = 0; k < 8; k += 2) ffma2(acc[r][k], acc[r][k + 1], mr[r], yk[k], yk[k + 1]);
+    };
+    float4 m = lds128(ma), y0 = lds128(ya), y1 = lds128(ya + 16);
+#pragma unroll 4
+    for (int f = 1; f < F; ++f) {
+        ma += mstep;
+        ya += 4 * kTileY;
+        const float4 mn = lds128(ma), y0n = lds128(ya), y1n = lds128(ya + 16);
+        fma_tile(m, y0, y1);
+        m = mn;
+        y0 = y0n;
+        y1 = y1n;
     }
+    fma_tile(m, y0, y1);
     mbar_wait(qbar, qparity);  // -0.5|y|^2 of this slab (loader warp), long ready by now
     const float4 qa = *reinterpret_cast<const float4 *>(ysq + 8 * yg);
     const float4 qb = *reinterpret_cast<const float4 *>(ysq + 8 * yg + 4);
@@ -172,6 +182,7 @@ __device__ __forceinline__ void prior_pass(const float *__restrict__ mu_s, const
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
         const int x = x0 + r;
+        if (x >= xlimit) continue;
         const float msq = musq[x];
         float o[8];
         // tts.py:495: y_square - y_mu_double + mu_square + const  (y_mu_double == -cross)
@@ -222,8 +233,8 @@ __global__ void __launch_bounds__(kPriorThreads) mas_prior_kernel(const PriorArg
     uint32_t *bits2 = reinterpret_cast<uint32_t *>(extra + ps.off_bits2);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int nfma = 3 * kFmaPerSmsp + a.extra_fma;
-    const int cw = fma_warp_index(warp, a.extra_fma);
+    const int nfma = 3 * a.fma_per_smsp + a.extra_fma;
+    const int cw = fma_warp_index(warp, a.extra_fma, a.fma_per_smsp);
     const float cst = (float)(-0.5 * 1.8378770664093453 * (double)F);  // -0.5*log(2*pi)*F, tts.py:484
 
     uint32_t *bits_smem = reinterpret_cast<uint32_t *>(smem + L.off_bits);
@@ -495,11 +506,12 @@ __global__ void __launch_bounds__(kPriorThreads) mas_prior_kernel(const PriorArg
             }
             fma_bar(nft);
             st_mu.end();
-            const int nit = npass;  // items per tile: one 32-token pass each
             for (int t = 0; t < ntiles; ++t, ++g) {
                 const int s = g % NS, ys = g % kSlabs;
                 const int lo = max(0, tx + t * kTileY - ty);
                 const int hi = min(tx - 1, t * kTileY + kTileY - 1);
+                const int lo4 = lo & ~3;                   // passes start at the band's lower edge
+                const int nit = (hi - lo4 + 32) >> 5;      // 32-token passes needed by this tile
                 st_e.begin();
                 if (g >= NS) mbar_wait(&ring.empty[s], ((g / NS) - 1) & 1);  // DP consumed tile g-NS
                 st_e.end();
@@ -509,13 +521,10 @@ __global__ void __launch_bounds__(kPriorThreads) mas_prior_kernel(const PriorArg
                 st_c.begin();
                 int it = (cw - item0) % nfma;
                 if (it < 0) it += nfma;
-                for (; it < nit; it += nfma) {
-                    const int p = it;
-                    if (32 * p <= hi && 32 * p + 31 >= lo)
-                        prior_pass(mu_s, musq, yslab + (size_t)ys * F * kTileY, ysq + ys * kTileY,
-                                   stages + (size_t)s * ring.stage_floats, F, L.xrows, p, lane, cst, rm,
-                                   &ybar[2 * kSlabs + ys], (g / kSlabs) & 1);
-                }
+                for (; it < nit; it += nfma)
+                    prior_pass(mu_s, musq, yslab + (size_t)ys * F * kTileY, ysq + ys * kTileY,
+                               stages + (size_t)s * ring.stage_floats, F, L.xrows, lo4 + 32 * it, hi + 1,
+                               lane, cst, rm, &ybar[2 * kSlabs + ys], (g / kSlabs) & 1);
                 item0 = (item0 + nit) % nfma;
                 __syncwarp();
                 st_c.end();
@@ -534,29 +543,93 @@ __global__ void __launch_bounds__(kPriorThreads) mas_prior_kernel(const PriorArg
 }
 
 // ------------------------------------------------------------------------------------
-// unfused prior: lp[b,x,y] for every cell (same arithmetic order as the fused producers)
+// unfused prior: lp[b,x,y] for every cell, same arithmetic order as the fused producers
+// (ascending-f FMA chains, ((ysq + cross) + musq) + const) => bit-identical values.
+// Block = 4 warps = 128 tokens; it keeps its mu tile in shared memory and walks kLpSlabs
+// 32-frame slabs of y, each warp computing 32 tokens x 32 frames per slab with the 4x8
+// register tile of prior_pass.
 // ------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) log_prior_kernel(const float *__restrict__ mu_x,
+constexpr int kLpTokens = 128, kLpSlabs = 8;
+
+__global__ void __launch_bounds__(128) log_prior_kernel(const float *__restrict__ mu_x,
                                                         const float *__restrict__ y, float *lp,
                                                         int F, int T_x, int T_y)
 {
-    // block: 8 token rows x 32 frames; thread (r, s) accumulates one cell
-    const int b = blockIdx.z;
-    const int s = threadIdx.x & 31, r = threadIdx.x >> 5;
-    const int yy = blockIdx.x * 32 + s, x = blockIdx.y * 8 + r;
-    if (x >= T_x) return;
+    extern __shared__ __align__(16) unsigned char smem[];
+    float *mu_t = reinterpret_cast<float *>(smem);          // [F][128]
+    float *ys = mu_t + (size_t)F * kLpTokens;               // [F][32]
+    float *musq = ys + (size_t)F * kTileY;                  // [128]
+    float *ysq = musq + kLpTokens;                          // [32]
+    const int b = blockIdx.z, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int xb = blockIdx.y * kLpTokens;
     const float *mub = mu_x + (int64_t)b * F * T_x;
     const float *yb = y + (int64_t)b * F * T_y;
-    float ysq = 0.0f, c = 0.0f, msq = 0.0f;
-    for (int f = 0; f < F; ++f) {
-        const float m = __ldg(mub + (int64_t)f * T_x + x);
-        const float v = (yy < T_y) ? __ldg(yb + (int64_t)f * T_y + yy) : 0.0f;
-        ysq = __fmaf_rn(v, v, ysq);
-        c = __fmaf_rn(m, v, c);
-        msq = __fmaf_rn(m, m, msq);
-    }
     const float cst = (float)(-0.5 * 1.8378770664093453 * (double)F);
-    if (yy < T_y) lp[((int64_t)b * T_x + x) * T_y + yy] = ((-0.5f * ysq + c) + -0.5f * msq) + cst;
+    for (int i = tid; i < F * kLpTokens; i += 128) {
+        const int f = i >> 7, x = xb + (i & 127);
+        mu_t[i] = (x < T_x) ? __ldg(mub + (int64_t)f * T_x + x) : 0.0f;
+    }
+    __syncthreads();
+    {
+        float s = 0.0f;
+        for (int f = 0; f < F; ++f) {
+            const float m = mu_t[f * kLpTokens + tid];
+            s = __fmaf_rn(m, m, s);
+        }
+        musq[tid] = -0.5f * s;
+    }
+    const int xg = lane >> 2, yg = lane & 3;
+    const int xl = 32 * warp + 4 * xg;   // this thread's first token inside the block
+    for (int sl = 0; sl < kLpSlabs; ++sl) {
+        const int y0 = (blockIdx.x * kLpSlabs + sl) * kTileY;
+        if (y0 >= T_y) break;
+        __syncthreads();                 // previous slab fully consumed
+        for (int i = tid; i < F * kTileY; i += 128) {
+            const int f = i >> 5, yy = y0 + (i & 31);
+            ys[i] = (yy < T_y) ? __ldg(yb + (int64_t)f * T_y + yy) : 0.0f;
+        }
+        __syncthreads();
+        if (tid < kTileY) {
+            float q = 0.0f;
+            for (int f = 0; f < F; ++f) {
+                const float v = ys[f * kTileY + tid];
+                q = __fmaf_rn(v, v, q);
+            }
+            ysq[tid] = -0.5f * q;
+        }
+        __syncthreads();
+        uint32_t ma = smem_u32(mu_t + xl);
+        uint32_t ya = smem_u32(ys + 8 * yg);
+        float acc[4][8];
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[r][k] = 0.0f;
+#pragma unroll 4
+        for (int f = 0; f < F; ++f) {
+            const float4 m = lds128(ma);
+            const float4 v0 = lds128(ya);
+            const float4 v1 = lds128(ya + 16);
+            ma += 4 * kLpTokens;
+            ya += 4 * kTileY;
+            const float mr[4] = {m.x, m.y, m.z, m.w};
+            const float yk[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int k = 0; k < 8; k += 2) ffma2(acc[r][k], acc[r][k + 1], mr[r], yk[k], yk[k + 1]);
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int x = xb + xl + r;
+            if (x >= T_x) continue;
+            const float msq = musq[xl + r];
+            float *dst = lp + ((int64_t)b * T_x + x) * T_y + y0 + 8 * yg;
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (y0 + 8 * yg + k < T_y) dst[k] = ((ysq[8 * yg + k] + acc[r][k]) + msq) + cst;
+        }
+    }
 }
 
 static int sm_count()
@@ -599,8 +672,15 @@ cudaError_t launch_from_prior(const PriorArgs &a, cudaStream_t st)
 cudaError_t launch_log_prior(const float *mu_x, const float *y, float *lp, int B, int F, int T_x,
                              int T_y, cudaStream_t st)
 {
-    dim3 grid((T_y + 31) / 32, (T_x + 7) / 8, B);
-    log_prior_kernel<<<grid, 256, 0, st>>>(mu_x, y, lp, F, T_x, T_y);
+    const size_t smem = ((size_t)F * (kLpTokens + kTileY) + kLpTokens + kTileY) * sizeof(float);
+    if (smem > (size_t)kSmemBudget) return cudaErrorInvalidValue;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(log_prior_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    dim3 grid((T_y + kTileY * kLpSlabs - 1) / (kTileY * kLpSlabs), (T_x + kLpTokens - 1) / kLpTokens, B);
+    log_prior_kernel<<<grid, 128, smem, st>>>(mu_x, y, lp, F, T_x, T_y);
     count_launch();
     return cudaGetLastError();
 }

@@ -62,6 +62,42 @@ def all_gather_rows(local: torch.Tensor, n_total: int, group: Optional[dist.Proc
     return torch.cat(pieces)
 
 
+class DurationGatherer:
+    """Asynchronous, double-buffered all-gather of per-rank durations [B_local, T_x] int32.
+
+    The gather of step i runs on a side stream while the MAS kernel of step i+1 runs on the
+    caller's stream (the only exchange of the sharded path is this re-assembly).
+    `gather(dur)` returns the buffer that will hold all ranks' durations once `wait()` (or the
+    next-but-one `gather`) has been ordered after it."""
+
+    def __init__(self, b_local: int, t_x: int, device, group: Optional[dist.ProcessGroup] = None,
+                 depth: int = 2):
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.bufs = [torch.empty(self.world * b_local, t_x, dtype=torch.int32, device=device)
+                     for _ in range(depth)]
+        self.stream = torch.cuda.Stream(device=device)
+        self.done = [torch.cuda.Event() for _ in range(depth)]
+        self.i = 0
+
+    def gather(self, dur: torch.Tensor) -> torch.Tensor:
+        slot = self.i % len(self.bufs)
+        self.i += 1
+        main = torch.cuda.current_stream(dur.device)
+        ready = torch.cuda.Event()
+        ready.record(main)
+        self.stream.wait_event(ready)           # durations produced
+        with torch.cuda.stream(self.stream):
+            dist.all_gather_into_tensor(self.bufs[slot], dur, group=self.group)
+            self.done[slot].record(self.stream)
+        dur.record_stream(self.stream)          # keep the allocator from recycling it early
+        return self.bufs[slot]
+
+    def wait(self) -> None:
+        """Order the caller's stream after every gather issued so far."""
+        torch.cuda.current_stream().wait_stream(self.stream)
+
+
 def maximum_path_from_prior_sharded(mu_x, y, t_x, t_y, *, group=None, rebuild_path=False):
     """Every rank holds the FULL batch description (or just its shard, see below), computes MAS
     for its contiguous shard and all-gathers durations.  Returns (durations [B,T_x] int32 for

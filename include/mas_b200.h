@@ -54,7 +54,8 @@ enum {
 enum {
     MAS_FLAG_NONE = 0,
     MAS_FLAG_FORCE_GENERAL = 1, /* use the size-agnostic kernel even when the fast one fits */
-    MAS_FLAG_NO_ASYNC = 2       /* fast kernel: stage tiles with LDG/STS instead of cp.async */
+    MAS_FLAG_NO_ASYNC = 2,      /* fast kernel: stage tiles with LDG/STS instead of cp.async */
+    MAS_FLAG_SPILL_BITS = 4     /* keep the direction bits in the workspace even if they fit  */
 };
 
 int mas_abi_version(void);
