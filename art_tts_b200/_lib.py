@@ -32,6 +32,8 @@ EXPORTS = (
     "mas_abi_version", "mas_strerror", "mas_lengths_from_mask", "mas_workspace_bytes",
     "mas_maximum_path", "mas_from_prior_f32", "mas_from_prior_plan", "mas_generate_path", "mas_plan",
     "mas_launch_count",
+    "mas_frame_index", "mas_duration_loss_f32", "mas_crop_f32", "mas_path_segment",
+    "mas_align_workspace_bytes", "mas_align_gather_f32", "mas_align_gather_bwd_f32",
 )
 
 _lib = None
@@ -79,6 +81,20 @@ def load() -> ctypes.CDLL:
     lib.mas_plan.argtypes = [ci, ci, ci, ci]
     lib.mas_launch_count.restype = ctypes.c_uint64
     lib.mas_launch_count.argtypes = []
+    lib.mas_frame_index.restype = ci
+    lib.mas_frame_index.argtypes = [vp, vp, vp, vp, ci, ci, ci, vp]
+    lib.mas_duration_loss_f32.restype = ci
+    lib.mas_duration_loss_f32.argtypes = [vp, vp, vp, vp, vp, vp, ci, ci, vp]
+    lib.mas_crop_f32.restype = ci
+    lib.mas_crop_f32.argtypes = [vp, vp, vp, vp, ci, ci, ci, ci, vp]
+    lib.mas_path_segment.restype = ci
+    lib.mas_path_segment.argtypes = [vp, vp, vp, vp, ci, ci, ci, ci, ci, vp]
+    lib.mas_align_workspace_bytes.restype = sz
+    lib.mas_align_workspace_bytes.argtypes = [ci, ci, ci]
+    lib.mas_align_gather_f32.restype = ci
+    lib.mas_align_gather_f32.argtypes = [vp, vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, vp, sz, vp]
+    lib.mas_align_gather_bwd_f32.restype = ci
+    lib.mas_align_gather_bwd_f32.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, vp]
     if lib.mas_abi_version() != 1:
         raise MasError("libmas_sm100.so ABI version mismatch; rebuild it")
     _lib = lib

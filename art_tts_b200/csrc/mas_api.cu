@@ -3,6 +3,7 @@
 // plan selection, launches.  No allocation, no host synchronisation, no CPU fallback.
 #include <atomic>
 #include <cstdlib>
+#include <initializer_list>
 
 #include "mas_internal.h"
 
@@ -313,6 +314,112 @@ int mas_generate_path(const void *durations, int dur_dtype, const int32_t *t_x, 
     return (int)launch_generate_path(durations, dur_dtype, t_x, t_y, path, esize,
                                      one_pattern(path_dtype), B, T_x, T_y,
                                      static_cast<cudaStream_t>(stream));
+}
+
+static bool misaligned4(std::initializer_list<const void *> ps)
+{
+    for (const void *p : ps)
+        if ((uintptr_t)p % 4) return true;
+    return false;
+}
+
+int mas_frame_index(const int32_t *durations, const int32_t *t_x, const int32_t *t_y,
+                    int32_t *frame_idx, int B, int T_x, int T_y, void *stream)
+{
+    if (!durations || !frame_idx) return MAS_ERR_NULL;
+    if (!shape_ok(B, T_x, T_y) || (size_t)(T_x + 1) * 4 > (size_t)kSmemBudget) return MAS_ERR_SHAPE;
+    if (misaligned4({durations, t_x, t_y, frame_idx})) return MAS_ERR_ALIGN;
+    if (B == 0) return MAS_OK;
+    return (int)launch_frame_index(durations, t_x, t_y, frame_idx, B, T_x, T_y,
+                                   static_cast<cudaStream_t>(stream));
+}
+
+int mas_duration_loss_f32(const float *logw, const int32_t *durations, const int32_t *t_x,
+                          float *logw_target, float *grad_unit, float *loss, int B, int T_x,
+                          void *stream)
+{
+    if (!durations || !t_x) return MAS_ERR_NULL;
+    if (!logw_target && !grad_unit && !loss) return MAS_ERR_NULL;
+    if ((loss || grad_unit) && !logw) return MAS_ERR_NULL;
+    if (B < 0 || T_x < 1) return MAS_ERR_SHAPE;
+    if (misaligned4({logw, durations, t_x, logw_target, grad_unit, loss})) return MAS_ERR_ALIGN;
+    return (int)launch_duration_loss(logw, durations, t_x, logw_target, grad_unit, loss, B, T_x,
+                                     static_cast<cudaStream_t>(stream));
+}
+
+static bool segment_shape_ok(int B, int R, int T_y, int T_out)
+{
+    return B >= 0 && B <= 65535 && R >= 1 && T_y >= 1 && T_out >= 1 && R <= (1 << 24) &&
+           T_y <= (1 << 24) && T_out <= (1 << 24) && (R + 7) / 8 <= 65535;
+}
+
+int mas_crop_f32(const float *src, const int32_t *offset, const int32_t *seg_len, float *dst, int B,
+                 int R, int T_y, int T_out, void *stream)
+{
+    if (!src || !dst) return MAS_ERR_NULL;
+    if (!segment_shape_ok(B, R, T_y, T_out)) return MAS_ERR_SHAPE;
+    if (misaligned4({src, offset, seg_len, dst})) return MAS_ERR_ALIGN;
+    if (B == 0) return MAS_OK;
+    return (int)launch_crop_rows(src, offset, seg_len, dst, B, R, T_y, T_out,
+                                 static_cast<cudaStream_t>(stream));
+}
+
+int mas_path_segment(const int32_t *frame_idx, const int32_t *offset, const int32_t *seg_len,
+                     void *path, int path_dtype, int B, int T_x, int T_y, int T_out, void *stream)
+{
+    if (!frame_idx || !path) return MAS_ERR_NULL;
+    if (!segment_shape_ok(B, T_x, T_y, T_out)) return MAS_ERR_SHAPE;
+    const int esize = element_size(path_dtype);
+    if (esize == 0 || path_dtype == MAS_I64) return MAS_ERR_DTYPE;
+    if (misaligned4({frame_idx, offset, seg_len}) || (uintptr_t)path % esize) return MAS_ERR_ALIGN;
+    if (B == 0) return MAS_OK;
+    return (int)launch_path_segment(frame_idx, offset, seg_len, path, esize, one_pattern(path_dtype),
+                                    B, T_x, T_y, T_out, static_cast<cudaStream_t>(stream));
+}
+
+size_t mas_align_workspace_bytes(int B, int F, int T_out)
+{
+    if (B < 1 || F < 1 || T_out < 1) return 256;
+    return align_partials(B, F, T_out) * sizeof(float) + 256;
+}
+
+int mas_align_gather_f32(const float *mu_x, const int32_t *frame_idx, const int32_t *offset,
+                         const int32_t *seg_len, const float *y_seg, float *mu_y, float *prior_loss,
+                         int B, int F, int T_x, int T_y, int T_out, void *workspace,
+                         size_t workspace_bytes, void *stream)
+{
+    if (!mu_x || !frame_idx) return MAS_ERR_NULL;
+    if (!mu_y && !prior_loss) return MAS_ERR_NULL;
+    if (prior_loss && !y_seg) return MAS_ERR_NULL;
+    if (!segment_shape_ok(B, F, T_y, T_out) || T_x < 1 || T_x > (1 << 24)) return MAS_ERR_SHAPE;
+    if (misaligned4({mu_x, frame_idx, offset, seg_len, y_seg, mu_y, prior_loss, workspace}))
+        return MAS_ERR_ALIGN;
+    if (prior_loss && (!workspace || workspace_bytes < mas_align_workspace_bytes(B, F, T_out)))
+        return MAS_ERR_WORKSPACE;
+    if (B == 0) return MAS_OK;
+    return (int)launch_align_gather(mu_x, frame_idx, offset, seg_len, y_seg, mu_y, prior_loss,
+                                    static_cast<float *>(workspace), B, F, T_x, T_y, T_out,
+                                    static_cast<cudaStream_t>(stream));
+}
+
+int mas_align_gather_bwd_f32(const float *grad_mu_y, const float *y_seg, const float *mu_x,
+                             const float *grad_loss, const float *loss_norm,
+                             const int32_t *frame_idx, const int32_t *offset, const int32_t *seg_len,
+                             float *grad_mu_x, int B, int F, int T_x, int T_y, int T_out,
+                             void *stream)
+{
+    if (!frame_idx || !grad_mu_x) return MAS_ERR_NULL;
+    if (!segment_shape_ok(B, F, T_y, T_out) || T_x < 1 || (size_t)T_x * 8 > (size_t)kSmemBudget)
+        return MAS_ERR_SHAPE;
+    if (misaligned4({grad_mu_y, y_seg, mu_x, grad_loss, loss_norm, frame_idx, offset, seg_len,
+                     grad_mu_x}))
+        return MAS_ERR_ALIGN;
+    const bool with_loss = y_seg && mu_x && grad_loss && loss_norm;
+    if (B == 0) return MAS_OK;
+    return (int)launch_align_gather_bwd(grad_mu_y, with_loss ? y_seg : nullptr, mu_x,
+                                        with_loss ? grad_loss : nullptr, loss_norm, frame_idx, offset,
+                                        seg_len, grad_mu_x, B, F, T_x, T_y, T_out,
+                                        static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -80,6 +80,28 @@ size_t prior_extra_smem(int F, int T_x, int T_y, bool second_bits);
 cudaError_t launch_log_prior(const float *mu_x, const float *y, float *lp, int B, int F, int T_x,
                              int T_y, cudaStream_t st);
 
+// mas_align.cu: consumers of the alignment (durations / frame index)
+cudaError_t launch_frame_index(const int32_t *dur, const int32_t *t_x, const int32_t *t_y,
+                               int32_t *fidx, int B, int T_x, int T_y, cudaStream_t st);
+cudaError_t launch_duration_loss(const float *logw, const int32_t *dur, const int32_t *t_x,
+                                 float *logw_target, float *grad_unit, float *loss, int B, int T_x,
+                                 cudaStream_t st);
+cudaError_t launch_crop_rows(const float *src, const int32_t *offset, const int32_t *seg_len,
+                             float *dst, int B, int R, int T_y, int T_out, cudaStream_t st);
+cudaError_t launch_path_segment(const int32_t *fidx, const int32_t *offset, const int32_t *seg_len,
+                                void *path, int esize, unsigned long long one, int B, int T_x,
+                                int T_y, int T_out, cudaStream_t st);
+size_t align_partials(int B, int F, int T_out);
+cudaError_t launch_align_gather(const float *mu_x, const int32_t *fidx, const int32_t *offset,
+                                const int32_t *seg_len, const float *y_seg, float *mu_y,
+                                float *loss, float *partials, int B, int F, int T_x, int T_y,
+                                int T_out, cudaStream_t st);
+cudaError_t launch_align_gather_bwd(const float *g_mu_y, const float *y_seg, const float *mu_x,
+                                    const float *g_loss, const float *loss_norm,
+                                    const int32_t *fidx, const int32_t *offset,
+                                    const int32_t *seg_len, float *g_mu_x, int B, int F, int T_x,
+                                    int T_y, int T_out, cudaStream_t st);
+
 void count_launch(int n = 1);
 
 }  // namespace mas

@@ -147,6 +147,73 @@ int mas_generate_path(const void *durations, int dur_dtype, const int32_t *t_x,
                       const int32_t *t_y, void *path, int path_dtype, int B, int T_x, int T_y,
                       void *stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Consumers of the alignment: what GradTTS.compute_loss does with `attn` right
+ * after MAS, computed from the compact outputs (durations, frame index) instead of the dense
+ * path.  A "segment" is the window of frames [offset[b], offset[b]+seg_len[b]) of utterance b,
+ * written to output columns [0, seg_len[b]) of a [.., T_out] tensor; columns beyond are zero.
+ * offset == NULL means 0, seg_len == NULL means T_out (both clamped to the tensor).
+ * ------------------------------------------------------------------------------------------ */
+
+/* durations [B,T_x] int32 -> frame_idx [B,T_y] int32 (token of every frame, -1 on padding):
+ * the compact form of the path for callers of the drop-in mas_maximum_path. */
+int mas_frame_index(const int32_t *durations, const int32_t *t_x, const int32_t *t_y,
+                    int32_t *frame_idx, int B, int T_x, int T_y, void *stream);
+
+/*
+ * Duration targets and loss -- replaces tts.py:503-506 + duration_loss (model/utils.py:46-48):
+ *     logw_ = log(1e-8 + sum_y attn) * x_mask;  loss = sum((logw - logw_)^2) / sum(x_lengths)
+ *   logw         NULL or [B,T_x] fp32 (the duration predictor's output)
+ *   logw_target  NULL or [B,T_x] fp32: receives logw_
+ *   grad_unit    NULL or [B,T_x] fp32: d loss / d logw = 2 (logw - logw_) / sum(x_lengths)
+ *   loss         NULL or [1] fp32
+ */
+int mas_duration_loss_f32(const float *logw, const int32_t *durations, const int32_t *t_x,
+                          float *logw_target, float *grad_unit, float *loss, int B, int T_x,
+                          void *stream);
+
+/* out_size crop of a [B,R,T_y] fp32 tensor (y: R = n_feats) -- replaces the per-item slicing
+ * loop of tts.py:524-544: dst[b,r,j] = src[b,r,offset[b]+j] for j < seg_len[b], else 0. */
+int mas_crop_f32(const float *src, const int32_t *offset, const int32_t *seg_len, float *dst,
+                 int B, int R, int T_y, int T_out, void *stream);
+
+/* attn_cut of tts.py:524-544 straight from the frame index:
+ * path[b,x,j] = (frame_idx[b,offset[b]+j] == x) for j < seg_len[b], else 0, in path_dtype. */
+int mas_path_segment(const int32_t *frame_idx, const int32_t *offset, const int32_t *seg_len,
+                     void *path, int path_dtype, int B, int T_x, int T_y, int T_out, void *stream);
+
+/* scratch bytes of mas_align_gather_f32 when prior_loss != NULL (never 0) */
+size_t mas_align_workspace_bytes(int B, int F, int T_out);
+
+/*
+ * mu_y = (attn^T @ mu_x^T)^T -- replaces the one-hot GEMM of tts.py:552-555 by a gather:
+ *     mu_y[b,f,j] = mu_x[b,f,frame_idx[b,offset[b]+j]]   (j < seg_len[b], else 0)
+ * (bit-identical to the GEMM: 1.0*mu plus exact zeros), and optionally tts.py:562-563
+ *     prior_loss[0] = sum(0.5 * ((y - mu_y)^2 + log(2 pi)) * y_mask) / (sum(y_mask) * F)
+ *     prior_loss[1] = sum(y_mask) * F        (kept for the backward pass)
+ *   y_seg  [B,F,T_out] fp32, required iff prior_loss != NULL (the cropped y)
+ *   mu_y   NULL or [B,F,T_out] fp32
+ */
+int mas_align_gather_f32(const float *mu_x, const int32_t *frame_idx, const int32_t *offset,
+                         const int32_t *seg_len, const float *y_seg, float *mu_y,
+                         float *prior_loss, int B, int F, int T_x, int T_y, int T_out,
+                         void *workspace, size_t workspace_bytes, void *stream);
+
+/*
+ * Backward of the above w.r.t. mu_x (autograd's attn @ grad_mu_y^T, tts.py:552-563):
+ *     grad_mu_x[b,f,x] = sum_{j: frame_idx[b,offset+j]==x} ( grad_mu_y[b,f,j]
+ *                          + grad_loss[0] / loss_norm[0] * (mu_x[b,f,x] - y_seg[b,f,j]) )
+ * A token's frames are contiguous, so this is a segmented sum: deterministic, no atomics.
+ * grad_mu_y may be NULL (no decoder gradient); the loss term needs y_seg, mu_x, grad_loss and
+ * loss_norm (= prior_loss[1]) all non-NULL and is skipped otherwise.
+ * frame_idx must be non-decreasing over each segment (always true for MAS output).
+ */
+int mas_align_gather_bwd_f32(const float *grad_mu_y, const float *y_seg, const float *mu_x,
+                             const float *grad_loss, const float *loss_norm,
+                             const int32_t *frame_idx, const int32_t *offset,
+                             const int32_t *seg_len, float *grad_mu_x, int B, int F, int T_x,
+                             int T_y, int T_out, void *stream);
+
 /*
  * Which kernel a shape dispatches to (for tests, bench and DESIGN.md):
  * 0 = fast single-warp-DP kernel with bits in shared memory, 1 = fast kernel with the

@@ -14,8 +14,15 @@ Contents
   ref.py              loader for oracle/_ref (the real reference kernel, when built)
 """
 from .mas_oracle import (  # noqa: F401
+    align_mu_y,
+    align_mu_y_grad,
     build_oracle,
+    crop_offsets,
+    crop_segments,
+    duration_loss,
+    duration_targets,
     durations_from_path,
+    frame_index,
     generate_path,
     log_prior,
     log_prior_f64,
@@ -23,5 +30,6 @@ from .mas_oracle import (  # noqa: F401
     maximum_path_c,
     maximum_path_rowsweep,
     oracle_threads,
+    prior_loss,
     sequence_mask,
 )

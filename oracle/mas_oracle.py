@@ -185,3 +185,75 @@ def generate_path(duration, mask):
     path = sequence_mask(cum.reshape(b * t_x), t_y).astype(mask.dtype).reshape(b, t_x, t_y)
     path = path - np.pad(path, ((0, 0), (1, 0), (0, 0)))[:, :-1]
     return path * mask
+
+
+# ------------------------------------------------------------------------------------------
+# consumers of the alignment: numpy restatements of tts.py:503-563
+# ------------------------------------------------------------------------------------------
+def duration_targets(attn, x_mask):
+    """tts.py:503-505: logw_ = log(1e-8 + sum(attn.unsqueeze(1), -1)) * x_mask  -> [B,1,T_x]."""
+    attn = np.asarray(attn, dtype=np.float32)
+    s = attn.sum(-1, dtype=np.float32)[:, None, :]
+    return (np.log(np.float32(1e-8) + s).astype(np.float32) * np.asarray(x_mask, np.float32))
+
+
+def duration_loss(logw, logw_, lengths):
+    """model/utils.py:46-48 (fp64 accumulation: the checker, not a bit-pattern)."""
+    d = np.asarray(logw, np.float32) - np.asarray(logw_, np.float32)
+    return np.float32((d * d).astype(np.float32).sum(dtype=np.float64) / np.asarray(lengths).sum())
+
+
+def crop_offsets(y_lengths, out_size, rng):
+    """tts.py:509-521: max_offset = (y_lengths - out_size).clamp(0);
+    offset = random.choice(range(0, max_offset)) if max_offset > 0 else 0, in batch order."""
+    out = []
+    for n in np.asarray(y_lengths).tolist():
+        end = max(int(n) - int(out_size), 0)
+        out.append(rng.choice(range(0, end)) if end > 0 else 0)
+    return np.asarray(out, dtype=np.int64)
+
+
+def crop_segments(y, attn, y_lengths, out_size, out_offset):
+    """tts.py:523-549: the per-item slicing loop.  Returns (y_cut, attn_cut, y_cut_lengths)."""
+    y, attn = np.asarray(y), np.asarray(attn)
+    B, F = y.shape[:2]
+    attn_cut = np.zeros((B, attn.shape[1], out_size), attn.dtype)
+    y_cut = np.zeros((B, F, out_size), y.dtype)
+    lens = []
+    for i in range(B):
+        n = int(out_size + min(int(y_lengths[i]) - out_size, 0))
+        lo = int(out_offset[i])
+        y_cut[i, :, :n] = y[i, :, lo:lo + n]
+        attn_cut[i, :, :n] = attn[i, :, lo:lo + n]
+        lens.append(n)
+    return y_cut, attn_cut, np.asarray(lens, np.int64)
+
+
+def align_mu_y(attn, mu_x):
+    """tts.py:552-555: mu_y = (attn^T @ mu_x^T)^T -> [B,F,T_out]."""
+    attn = np.asarray(attn, np.float32)
+    mu_x = np.asarray(mu_x, np.float32)
+    return np.matmul(attn.transpose(0, 2, 1), mu_x.transpose(0, 2, 1)).transpose(0, 2, 1)
+
+
+def prior_loss(y, mu_y, y_mask, n_feats):
+    """tts.py:562-563 (elementwise in fp32, sums accumulated in fp64)."""
+    y, mu_y, y_mask = (np.asarray(a, np.float32) for a in (y, mu_y, y_mask))
+    e = (np.float32(0.5) * ((y - mu_y) ** 2 + np.float32(math.log(2 * math.pi)))) * y_mask
+    return np.float32(e.sum(dtype=np.float64) / (y_mask.sum(dtype=np.float64) * n_feats))
+
+
+def align_mu_y_grad(attn, g_mu_y):
+    """Backward of align_mu_y w.r.t. mu_x: g_mu_x = (attn @ g_mu_y^T)^T -> [B,F,T_x] (fp64 sums)."""
+    attn = np.asarray(attn, np.float64)
+    g = np.asarray(g_mu_y, np.float64)
+    return np.matmul(attn, g.transpose(0, 2, 1)).transpose(0, 2, 1)
+
+
+def frame_index(path, t_y):
+    """Token of every frame (argmax over the token axis), -1 beyond t_y."""
+    path = np.asarray(path)
+    idx = path.argmax(1).astype(np.int32)
+    idx[np.arange(path.shape[2])[None, :] >= np.asarray(t_y)[:, None]] = -1
+    idx[path.sum(1) == 0] = -1
+    return idx

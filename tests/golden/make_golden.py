@@ -13,8 +13,12 @@ Outputs (committed):
   prior_gradtts.npz  GradTTS(params_v2) random-init compute_loss: captured mu_x, y, log_prior,
                      attn durations, dur_loss, prior_loss        (F=80, tts.py:450-563)
   prior_arttts.npz   ArtTTS(params_v1) same capture              (F=16, tts.py:160-290)
+  loss_block_gradtts.npz  GradTTS compute_loss WITH the out_size crop (tts.py:503-563): y_cut,
+                     y_cut_mask, mu_y as handed to the decoder, dur_loss, prior_loss and the
+                     autograd gradients of (dur_loss + prior_loss) w.r.t. mu_x and logw
 
-Run:  python tests/golden/make_golden.py
+Run:  python tests/golden/make_golden.py            (everything)
+      python tests/golden/make_golden.py --only loss  (just loss_block_gradtts.npz)
 """
 from __future__ import annotations
 
@@ -84,11 +88,75 @@ def sha(a):
     return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
 
 
+def loss_block(shim):
+    """GradTTS.compute_loss with out_size (tts.py:450-565), decoder replaced by a recorder."""
+    import importlib
+    import random
+
+    import torch
+    from model import GradTTS, monotonic_align
+
+    p2 = importlib.import_module("configs.params_v2")
+    torch.manual_seed(p2.random_seed)
+    n_vocab = 149
+    g = GradTTS(n_vocab, p2.n_spks, p2.spk_emb_dim, p2.n_enc_channels, p2.filter_channels,
+                p2.filter_channels_dp, p2.n_heads, p2.n_enc_layers, p2.enc_kernel, p2.enc_dropout,
+                p2.window_size, p2.n_feats, p2.dec_dim, p2.beta_min, p2.beta_max, p2.pe_scale)
+    g.eval()
+    B, T_x, T_y, out_size, seed = 6, 40, 160, 64, 4242
+    x_lengths = torch.tensor([40, 31, 17, 36, 9, 25])
+    y_lengths = torch.tensor([160, 130, 80, 151, 40, 64])   # two items shorter/equal to out_size
+    x = torch.randint(0, n_vocab, (B, T_x))
+    y = torch.randn(B, p2.n_feats, T_y) * (torch.arange(T_y)[None, None, :] < y_lengths[:, None, None])
+    enc, dec, mas = {}, {}, {}
+
+    def enc_hook(m, i, o):
+        o[0].retain_grad()
+        o[1].retain_grad()
+        enc.update(mu_x=o[0], logw=o[1], x_mask=o[2])
+
+    def fake_decoder_loss(y_, y_mask_, mu_y_, spk=None):
+        dec.update(y=y_.detach().clone(), y_mask=y_mask_.detach().clone(), mu_y=mu_y_.detach().clone())
+        return torch.zeros(()), None
+
+    real_mp = monotonic_align.maximum_path
+
+    def spy(value, mask):
+        path = real_mp(value, mask)
+        mas["attn"] = path.detach().clone()
+        return path
+
+    h = g.encoder.register_forward_hook(enc_hook)
+    g.decoder.compute_loss = fake_decoder_loss
+    monotonic_align.maximum_path = spy
+    random.seed(seed)
+    dur_loss, prior_loss, _ = g.compute_loss(x, x_lengths, y, y_lengths, out_size=out_size)
+    (dur_loss + prior_loss).backward()
+    monotonic_align.maximum_path = real_mp
+    h.remove()
+    attn = mas["attn"].numpy()
+    np.savez_compressed(
+        os.path.join(HERE, "loss_block_gradtts.npz"),
+        mu_x=enc["mu_x"].detach().numpy(), logw=enc["logw"].detach().numpy(),
+        x_mask=enc["x_mask"].detach().numpy(), y=y.numpy(),
+        x_lengths=x_lengths.numpy().astype(np.int32), y_lengths=y_lengths.numpy().astype(np.int32),
+        out_size=np.int32(out_size), random_seed=np.int32(seed),
+        durations=attn.sum(-1).astype(np.int32),
+        y_cut=dec["y"].numpy(), y_cut_mask=dec["y_mask"].numpy(), mu_y=dec["mu_y"].numpy(),
+        dur_loss=np.float32(dur_loss.item()), prior_loss=np.float32(prior_loss.item()),
+        grad_mu_x=enc["mu_x"].grad.numpy(), grad_logw=enc["logw"].grad.numpy())
+
+
 def main():
     shim = make_shim()
     sys.path.insert(0, shim)
     import torch
     from model import monotonic_align  # the reference's own wrapper + compiled kernel
+
+    if "--only" in sys.argv and sys.argv[sys.argv.index("--only") + 1] == "loss":
+        loss_block(shim)
+        shutil.rmtree(shim, ignore_errors=True)
+        return
 
     def ref_path(value, mask):
         return monotonic_align.maximum_path(torch.from_numpy(value), torch.from_numpy(mask)).numpy()
@@ -234,6 +302,7 @@ def main():
     y = y * (torch.arange(T_y)[None, None, :] < y_lengths[:, None, None])
     capture(a, x, x_lengths, y, y_lengths, "prior_arttts.npz", {"x_traits": x.numpy()})
 
+    loss_block(shim)
     shutil.rmtree(shim, ignore_errors=True)
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):

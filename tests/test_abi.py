@@ -68,6 +68,23 @@ def test_argument_validation_without_gpu(maslib):
               null) == -3   # logs != NULL: the reference has no learned-variance prior
     lm = maslib.mas_lengths_from_mask
     assert lm(null, 0, 1, 4, 8, 32, 8, 1, one, one, null) == -1
+    # consumers of the alignment
+    assert maslib.mas_frame_index(null, one, one, one, 1, 4, 8, null) == -1
+    assert maslib.mas_frame_index(one, one, one, odd, 1, 4, 8, null) == -5
+    assert maslib.mas_duration_loss_f32(null, one, one, null, null, one, 1, 4, null) == -1  # loss needs logw
+    assert maslib.mas_duration_loss_f32(one, one, one, null, null, null, 1, 4, null) == -1  # nothing to do
+    assert maslib.mas_crop_f32(one, null, null, null, 1, 80, 8, 4, null) == -1
+    assert maslib.mas_crop_f32(one, null, null, one, 1, 80, 8, 0, null) == -2
+    assert maslib.mas_path_segment(one, null, null, one, 6, 1, 4, 8, 8, null) == -3
+    ag = maslib.mas_align_gather_f32
+    assert ag(one, one, null, null, null, null, null, 1, 80, 4, 8, 8, null, 0, null) == -1
+    assert ag(one, one, null, null, null, one, one, 1, 80, 4, 8, 8, null, 0, null) == -1   # loss needs y
+    assert ag(one, one, null, null, one, one, one, 1, 80, 4, 8, 8, null, 0, null) == -4    # and scratch
+    assert ag(one, one, null, null, null, one, null, 0, 80, 4, 8, 8, null, 0, null) == 0
+    assert maslib.mas_align_workspace_bytes(1024, 80, 872) >= 1024 * 7 * 4
+    bw = maslib.mas_align_gather_bwd_f32
+    assert bw(one, null, null, null, null, null, null, null, one, 1, 80, 4, 8, 8, null) == -1
+    assert bw(one, null, null, null, null, one, null, null, one, 1, 80, 1 << 20, 8, 8, null) == -2
 
 
 def test_python_surface_refuses_cpu_tensors(maslib):

@@ -107,3 +107,38 @@ def test_prior_restatement_matches_reference_model(fname, F):
     path = oracle.maximum_path(want, mask)
     assert np.array_equal(path.sum(-1).astype(np.int32), g["durations"])
     assert np.array_equal(np.packbits(path.astype(np.uint8), axis=-1), g["attn_packed"])
+
+
+def test_loss_block_restatement_matches_reference_compute_loss():
+    """tts.py:503-563 (duration targets, out_size crop, mu_y, prior loss) and the autograd
+    gradients, against what the reference's own GradTTS.compute_loss produced."""
+    import random
+    g = np.load(os.path.join(GOLDEN, "loss_block_gradtts.npz"))
+    mu_x, y, logw = g["mu_x"], g["y"], g["logw"]
+    x_len, y_len, out_size = g["x_lengths"], g["y_lengths"], int(g["out_size"])
+    B, F, T_x = mu_x.shape
+    mask = rect_mask(x_len, y_len, T_x, y.shape[2])
+    attn = oracle.maximum_path(oracle.log_prior(mu_x, y), mask)
+    assert np.array_equal(attn.sum(-1).astype(np.int32), g["durations"])
+    # duration loss
+    logw_ = oracle.duration_targets(attn, g["x_mask"])
+    assert np.isclose(oracle.duration_loss(logw, logw_, x_len), g["dur_loss"], rtol=1e-6)
+    # crop: the seeded `random` stream reproduces the reference's offsets => identical y_cut
+    rng = random.Random(int(g["random_seed"]))
+    off = oracle.crop_offsets(y_len, out_size, rng)
+    y_cut, attn_cut, cut_len = oracle.crop_segments(y, attn, y_len, out_size, off)
+    assert np.array_equal(y_cut, g["y_cut"])
+    y_cut_mask = oracle.sequence_mask(cut_len, out_size)[:, None, :].astype(np.float32)
+    assert np.array_equal(y_cut_mask, g["y_cut_mask"])
+    mu_y = oracle.align_mu_y(attn_cut, mu_x)
+    assert np.array_equal(mu_y, g["mu_y"])
+    assert np.isclose(oracle.prior_loss(y_cut, mu_y, y_cut_mask, F), g["prior_loss"], rtol=1e-6)
+    # gradients of (dur_loss + prior_loss): d/dmu_y = (mu_y - y) * mask / (sum(mask) * F)
+    g_mu_y = (mu_y - y_cut) * y_cut_mask / (y_cut_mask.sum() * F)
+    assert np.allclose(oracle.align_mu_y_grad(attn_cut, g_mu_y), g["grad_mu_x"], rtol=1e-4, atol=1e-9)
+    assert np.allclose(2 * (logw - logw_) / x_len.sum(), g["grad_logw"], rtol=1e-5, atol=1e-9)
+    # frame index is the compact form of the path
+    idx = oracle.frame_index(attn, y_len)
+    for b in range(B):
+        assert np.array_equal(attn[b, idx[b, :y_len[b]], np.arange(y_len[b])], np.ones(y_len[b]))
+        assert (idx[b, y_len[b]:] == -1).all()
