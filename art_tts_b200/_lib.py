@@ -16,6 +16,7 @@ MAS_F32, MAS_F16, MAS_BF16, MAS_F64, MAS_I32, MAS_U8, MAS_I64 = range(7)
 FLAG_FORCE_GENERAL = 1
 FLAG_NO_ASYNC = 2
 FLAG_SPILL_BITS = 4
+FLAG_HOST_NO_TRIM = 8
 
 _DTYPES = {
     torch.float32: MAS_F32,
@@ -34,6 +35,7 @@ EXPORTS = (
     "mas_launch_count",
     "mas_frame_index", "mas_duration_loss_f32", "mas_crop_f32", "mas_path_segment",
     "mas_align_workspace_bytes", "mas_align_gather_f32", "mas_align_gather_bwd_f32",
+    "mas_from_prior_host_f32",
 )
 
 _lib = None
@@ -95,6 +97,9 @@ def load() -> ctypes.CDLL:
     lib.mas_align_gather_f32.argtypes = [vp, vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, vp, sz, vp]
     lib.mas_align_gather_bwd_f32.restype = ci
     lib.mas_align_gather_bwd_f32.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, vp]
+    lib.mas_from_prior_host_f32.restype = ci
+    lib.mas_from_prior_host_f32.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, ci, vp, vp, vp, vp, vp,
+                                            ci, ci, ci, ci, vp, sz, ci, ci, vp, vp]
     if lib.mas_abi_version() != 1:
         raise MasError("libmas_sm100.so ABI version mismatch; rebuild it")
     _lib = lib

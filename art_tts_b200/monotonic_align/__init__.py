@@ -15,6 +15,7 @@ D2H/H2D copies, no CPU fallback.
 """
 from __future__ import annotations
 
+import ctypes
 from typing import Optional, Tuple
 
 import torch
@@ -25,6 +26,7 @@ __all__ = [
     "maximum_path",
     "maximum_path_lengths",
     "maximum_path_from_prior",
+    "maximum_path_from_prior_host",
     "lengths_from_mask",
 ]
 
@@ -190,3 +192,67 @@ def maximum_path_from_prior(mu_x: torch.Tensor, logs: Optional[torch.Tensor], y:
         if flag:
             out.append(t)
     return tuple(out) if len(out) > 1 else out[0]
+
+
+_staging = {}
+
+
+def maximum_path_from_prior_host(mu_x: torch.Tensor, y: torch.Tensor, x_lengths: torch.Tensor,
+                                 y_lengths: torch.Tensor, device=None, *, want_path: bool = True,
+                                 out_dtype: torch.dtype = torch.float32, chunk: int = 0,
+                                 durations_host: Optional[torch.Tensor] = None,
+                                 score_host: Optional[torch.Tensor] = None, flags: int = 0):
+    """Fused prior + MAS for a batch that still lives in HOST memory (the data loader's pinned
+    tensors; train_v2.py:203 -> tts.py:466 moves the whole padded batch first).
+
+    mu_x [B,F,T_x], y [B,F,T_y] fp32 CPU tensors (pin them: pageable memory makes the copies
+    synchronous), x_lengths / y_lengths int32 CPU tensors [B].  Only the frames/tokens MAS can
+    touch are copied (chunks of the length-bucketed batch trimmed to their longest utterance)
+    and each chunk's kernel starts as soon as its rows have landed.  Returns
+    (path or None, durations, score, h2d_bytes) on `device`; when `durations_host` /
+    `score_host` (pinned) are given they are filled asynchronously on the current stream --
+    synchronise it before reading them."""
+    for name, t in (("mu_x", mu_x), ("y", y), ("x_lengths", x_lengths), ("y_lengths", y_lengths)):
+        if t.is_cuda:
+            raise _lib.MasError(f"{name} is already on {t.device}: use maximum_path_from_prior")
+    if mu_x.dtype != torch.float32 or y.dtype != torch.float32:
+        raise TypeError("mu_x and y must be float32")
+    if mu_x.dim() != 3 or y.dim() != 3 or mu_x.shape[:2] != y.shape[:2]:
+        raise ValueError("mu_x must be [B,F,T_x] and y [B,F,T_y]")
+    dev = torch.device(device if device is not None else "cuda")
+    if dev.index is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
+    B, F, T_x = mu_x.shape
+    T_y = y.shape[2]
+    mu_x, y = mu_x.contiguous(), y.contiguous()
+    tx = x_lengths.to(torch.int32).contiguous()
+    ty = y_lengths.to(torch.int32).contiguous()
+    if tx.numel() != B or ty.numel() != B:
+        raise ValueError("x_lengths and y_lengths must have one entry per utterance")
+    lib = _lib.load()
+    if B and lib.mas_from_prior_plan(B, F, T_x, T_y, flags) != 0:
+        raise ValueError("shape needs the unfused plan; copy the batch and call maximum_path_from_prior")
+    key = (dev.index, B, F, T_x, T_y)
+    st = _staging.get(key)
+    if st is None:
+        _staging.clear()   # one shape at a time: the staging buffers are as large as the batch
+        st = (torch.empty((B, F, T_x), dtype=torch.float32, device=dev),
+              torch.empty((B, F, T_y), dtype=torch.float32, device=dev),
+              torch.empty((B,), dtype=torch.int32, device=dev),
+              torch.empty((B,), dtype=torch.int32, device=dev))
+        _staging[key] = st
+    path = torch.empty((B, T_x, T_y), dtype=out_dtype, device=dev) if want_path else None
+    dur = torch.empty((B, T_x), dtype=torch.int32, device=dev)
+    score = torch.empty((B,), dtype=torch.float32, device=dev)
+    moved = ctypes.c_uint64(0)
+    if B:
+        with torch.cuda.device(dev):
+            ws = _lib.workspace(dev, int(lib.mas_workspace_bytes(B, T_x, T_y)))
+            code = lib.mas_from_prior_host_f32(
+                _lib.ptr(mu_x), _lib.ptr(y), _lib.ptr(tx), _lib.ptr(ty), _lib.ptr(st[0]),
+                _lib.ptr(st[1]), _lib.ptr(st[2]), _lib.ptr(st[3]), _lib.ptr(path),
+                _lib.dtype_code(out_dtype), _lib.ptr(dur), None, _lib.ptr(score),
+                _lib.ptr(durations_host), _lib.ptr(score_host), B, F, T_x, T_y, _lib.ptr(ws),
+                ws.numel(), int(chunk), flags, _lib.stream_ptr(dev), ctypes.byref(moved))
+        _lib.check(code, "mas_from_prior_host_f32")
+    return path, dur, score, int(moved.value)

@@ -56,6 +56,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-dropin", action="store_true")
+    ap.add_argument("--e2e-chunk", type=int, default=0, help="utterances per H2D chunk (0 = library default)")
+    ap.add_argument("--e2e-no-trim", action="store_true", help="copy whole padded rows")
     return ap.parse_args()
 
 
@@ -369,31 +371,40 @@ def run_ours(args):
                     t_y.cpu().pin_memory()]
         else:
             h_in = [value.cpu().pin_memory(), t_x.cpu().pin_memory(), t_y.cpu().pin_memory()]
-        d_in = [torch.empty_like(h, device=dev) for h in h_in]
+        d_in = [torch.empty_like(h, device=dev) for h in h_in] if args.op != "fused" else []
         h_dur = torch.empty(B, T_X, dtype=torch.int32).pin_memory()
         h_score = torch.empty(B, dtype=torch.float32).pin_memory()
         h2d = sum(h.numel() * h.element_size() for h in h_in)
         d2h = h_dur.numel() * 4 + h_score.numel() * 4
 
+        moved = [h2d]
+
         def e2e_step():
-            for h, d in zip(h_in, d_in):
-                d.copy_(h, non_blocking=True)
             if args.op == "fused":
-                path, dur, score = monotonic_align.maximum_path_from_prior(
-                    d_in[0], None, d_in[1], d_in[2], d_in[3], return_score=True)
+                # host-buffer entry point: trimmed, chunked H2D overlapped with the kernels,
+                # D2H of durations + score enqueued behind the last chunk
+                path, dur, score, moved[0] = monotonic_align.maximum_path_from_prior_host(
+                    h_in[0], h_in[1], h_in[2], h_in[3], dev, chunk=args.e2e_chunk,
+                    durations_host=h_dur, score_host=h_score,
+                    flags=_lib.FLAG_HOST_NO_TRIM if args.e2e_no_trim else 0)
+                if world > 1:
+                    dist.all_gather_into_tensor(dur_all, dur)
             else:
+                for h, d in zip(h_in, d_in):
+                    d.copy_(h, non_blocking=True)
                 path, dur, score = monotonic_align.maximum_path_lengths(
                     d_in[0], d_in[1], d_in[2], return_durations=True, return_score=True)
-            if world > 1:
-                dist.all_gather_into_tensor(dur_all, dur)
-            h_dur.copy_(dur, non_blocking=True)
-            h_score.copy_(score, non_blocking=True)
+                if world > 1:
+                    dist.all_gather_into_tensor(dur_all, dur)
+                h_dur.copy_(dur, non_blocking=True)
+                h_score.copy_(score, non_blocking=True)
             torch.cuda.current_stream().synchronize()   # the caller reads the result every step
 
         e_ms, _ = timed(e2e_step, max(3, args.steps // 2), 2)
         e2e = {"value": cells * world / (e_ms * 1e-3), "unit": UNIT, "ms_per_step": e_ms,
-               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-               "api": "art_tts_b200.monotonic_align.maximum_path_from_prior" if args.op == "fused"
+               "h2d_bytes_per_step": int(moved[0]), "d2h_bytes_per_step": d2h,
+               "padded_input_bytes": h2d,
+               "api": "art_tts_b200.monotonic_align.maximum_path_from_prior_host" if args.op == "fused"
                       else "art_tts_b200.monotonic_align.maximum_path_lengths"}
 
     if world > 1:

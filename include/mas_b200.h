@@ -55,7 +55,8 @@ enum {
     MAS_FLAG_NONE = 0,
     MAS_FLAG_FORCE_GENERAL = 1, /* use the size-agnostic kernel even when the fast one fits */
     MAS_FLAG_NO_ASYNC = 2,      /* fast kernel: stage tiles with LDG/STS instead of cp.async */
-    MAS_FLAG_SPILL_BITS = 4     /* keep the direction bits in the workspace even if they fit  */
+    MAS_FLAG_SPILL_BITS = 4,    /* keep the direction bits in the workspace even if they fit  */
+    MAS_FLAG_HOST_NO_TRIM = 8   /* mas_from_prior_host_f32: copy whole padded rows            */
 };
 
 int mas_abi_version(void);
@@ -126,6 +127,29 @@ int mas_from_prior_f32(const float *mu_x, const float *logs, const float *y,
                        int32_t *durations, int32_t *frame_idx, float *score,
                        float *log_prior_out, int B, int F, int T_x, int T_y,
                        void *workspace, size_t workspace_bytes, int flags, void *stream);
+
+/*
+ * Host-buffer variant of mas_from_prior_f32: the batch is still in (pinned) HOST memory, as
+ * when the reference's training loop hands y to compute_loss (train_v2.py:203 ->
+ * tts.py:466 relocate_input, which moves the whole padded batch).  Copies only what MAS can
+ * touch -- each chunk of `chunk` consecutive utterances (0 = 128) is trimmed to its longest
+ * utterance, so length-bucketed batches move ~35 % fewer bytes -- on an internal copy stream,
+ * and launches the chunk's kernel on `stream` as soon as its rows have landed, so transfers
+ * and kernels overlap.  Optionally copies durations / score back to host at the end.
+ *   *_host     host pointers (pinned for asynchronous copies); t_x_host/t_y_host are READ by
+ *              the CPU inside the call (chunk extents)
+ *   *_dev      device staging of the full padded shapes [B,F,T_x], [B,F,T_y], [B], [B]
+ *   h2d_bytes_out  NULL or receives the host->device bytes this call enqueued
+ * Everything is enqueued asynchronously; the caller synchronises `stream` before reading the
+ * host outputs.  Requires the fused plan (mas_from_prior_plan() == 0).
+ */
+int mas_from_prior_host_f32(const float *mu_x_host, const float *y_host, const int32_t *t_x_host,
+                            const int32_t *t_y_host, float *mu_x_dev, float *y_dev,
+                            int32_t *t_x_dev, int32_t *t_y_dev, void *path, int path_dtype,
+                            int32_t *durations, int32_t *frame_idx, float *score,
+                            int32_t *durations_host, float *score_host, int B, int F, int T_x,
+                            int T_y, void *workspace, size_t workspace_bytes, int chunk, int flags,
+                            void *stream, uint64_t *h2d_bytes_out);
 
 /*
  * 0 when mas_from_prior_f32 runs fused for this shape; 1 when mu_x (F*T_x floats) does not

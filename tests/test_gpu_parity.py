@@ -333,3 +333,34 @@ def test_fused_unfused_plan_for_long_text(cuda):
     path, dur, lp = fused(mu_x, y, x_len, y_len, cuda, return_log_prior=True)
     self_path = oracle.maximum_path(lp.cpu().numpy(), mask, n_threads=2)
     assert np.array_equal(path.cpu().numpy(), self_path)
+
+
+@pytest.mark.parametrize("chunk,trim", [(0, True), (5, True), (64, False)])
+def test_host_buffer_entry_equals_device_entry(cuda, chunk, trim):
+    """mas_from_prior_host_f32 (trimmed, chunked H2D overlapped with the kernels) must give
+    exactly what mas_from_prior_f32 gives on the same batch already resident in HBM."""
+    from art_tts_b200 import _lib, monotonic_align
+    B, F, T_x, T_y = 37, 80, 70, 300
+    rng = np.random.default_rng(21)
+    x_len = rng.integers(5, T_x + 1, B).astype(np.int32)
+    y_len = np.minimum(T_y, 4 * x_len + rng.integers(0, 20, B)).astype(np.int32)
+    order = np.argsort(-(x_len.astype(np.int64) * y_len), kind="stable")
+    x_len, y_len = x_len[order], y_len[order]
+    mu_x = rng.standard_normal((B, F, T_x)).astype(np.float32)
+    y = rng.standard_normal((B, F, T_y)).astype(np.float32)
+    h = [torch.from_numpy(a).pin_memory() for a in (mu_x, y, x_len, y_len)]
+    h_dur = torch.zeros(B, T_x, dtype=torch.int32).pin_memory()
+    h_score = torch.zeros(B, dtype=torch.float32).pin_memory()
+    # poison the staging buffers first so that stale padding would show up
+    monotonic_align.maximum_path_from_prior_host(
+        torch.full_like(h[0], float("nan")), torch.full_like(h[1], float("nan")), h[2], h[3], cuda)
+    path, dur, score, moved = monotonic_align.maximum_path_from_prior_host(
+        h[0], h[1], h[2], h[3], cuda, chunk=chunk, durations_host=h_dur, score_host=h_score,
+        flags=0 if trim else _lib.FLAG_HOST_NO_TRIM)
+    torch.cuda.synchronize()
+    p2, d2, s2 = monotonic_align.maximum_path_from_prior(
+        h[0].to(cuda), None, h[1].to(cuda), h[2], h[3], return_score=True)
+    assert torch.equal(path, p2) and torch.equal(dur, d2) and torch.equal(score, s2)
+    assert torch.equal(h_dur, d2.cpu()) and torch.equal(h_score, s2.cpu())
+    full = (mu_x.nbytes + y.nbytes + 8 * B)
+    assert moved == full if not trim else (moved < full if chunk else moved <= full)
