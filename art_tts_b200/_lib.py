@@ -17,6 +17,7 @@ FLAG_FORCE_GENERAL = 1
 FLAG_NO_ASYNC = 2
 FLAG_SPILL_BITS = 4
 FLAG_HOST_NO_TRIM = 8
+FLAG_NO_TENSOR = 16
 
 _DTYPES = {
     torch.float32: MAS_F32,

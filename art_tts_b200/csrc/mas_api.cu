@@ -227,6 +227,38 @@ int mas_from_prior_f32(const float *mu_x, const float *logs, const float *y, con
     if (B == 0) return MAS_OK;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
 
+    // tensor-core prior (mas_prior_tc.cu) for every shape it covers; MAS_PRIOR_TC=0 forces the
+    // CUDA-core kernel (A/B measurements, and the shapes beyond 256 tokens / 96 features)
+    if (env_int("MAS_PRIOR_TC", 1) && !(flags & (MAS_FLAG_FORCE_GENERAL | MAS_FLAG_SPILL_BITS | MAS_FLAG_NO_TENSOR))) {
+        PriorTcArgs t{};
+        t.lay = tc_layout(F, T_x, T_y);
+        if (t.lay.ok) {
+            t.mu_x = mu_x;
+            t.y = y;
+            t.t_x = t_x;
+            t.t_y = t_y;
+            t.path = path;
+            t.durations = durations;
+            t.frame_idx = frame_idx;
+            t.score = score;
+            t.lp_out = log_prior_out;
+            t.stats = nullptr;
+            if (env_int("MAS_PRIOR_STATS", 0)) {  // profiling aid: counters at the tail of an over-sized workspace
+                const size_t need = mas_workspace_bytes(B, T_x, T_y), sbytes = (size_t)1024 * 32 * 8;
+                if (workspace && workspace_bytes >= need + sbytes + 16)
+                    t.stats = reinterpret_cast<long long *>(static_cast<char *>(workspace) +
+                                                            ((workspace_bytes - sbytes) & ~(size_t)15));
+            }
+            t.B = B;
+            t.F = F;
+            t.T_x = T_x;
+            t.T_y = T_y;
+            t.path_esize = path ? esize : 4;
+            t.one = one_pattern(path_dtype);
+            return (int)launch_from_prior_tc(t, st);
+        }
+    }
+
     PriorArgs a{};
     // prefer two direction-bit buffers in shared memory (backtrack of utterance k overlaps the
     // forward pass of k+1); else one; else the bits spill to the workspace

@@ -55,6 +55,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
     }
 }
 
+// wait used by agents that are NOT on the critical path: back off between polls so the spin
+// does not take issue slots from the warps sharing the scheduler (DP warp, MMA issuer)
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t *bar, uint32_t parity, unsigned ns = 64)
+{
+    while (!mbar_try_wait(bar, parity)) __nanosleep(ns);
+}
+
 __device__ __forceinline__ float4 lds128(uint32_t addr)
 {
     float4 v;

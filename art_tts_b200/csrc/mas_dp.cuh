@@ -327,4 +327,40 @@ __device__ __forceinline__ void write_frame_idx(int32_t *fi, const int *first, c
     }
 }
 
+// one cell of the prior, same operation order as the producers / log_prior_kernel
+__device__ __forceinline__ float lp_cell(const float *mub, const float *yb, int F, int T_x,
+                                         int64_t T_y, int x, int y, float cst)
+{
+    float ysq = 0.0f, c = 0.0f, msq = 0.0f;
+    for (int f = 0; f < F; ++f) {
+        const float m = __ldg(mub + (int64_t)f * T_x + x);
+        const float v = __ldg(yb + (int64_t)f * T_y + y);
+        ysq = __fmaf_rn(v, v, ysq);
+        c = __fmaf_rn(m, v, c);
+        msq = __fmaf_rn(m, m, msq);
+    }
+    return ((-0.5f * ysq + c) + -0.5f * msq) + cst;
+}
+
+template <int XPLMAX>
+__device__ __forceinline__ float prior_forward_dispatch(const TileRing &ring, uint32_t *bits,
+                                                        int xrows, int tx, int ty, int lane, int g0,
+                                                        long long *wacc)
+{
+    const int xpl = (tx + 31) >> 5;
+#define MAS_CASE(N)                                                                           \
+    case N:                                                                                   \
+        if constexpr (N <= XPLMAX) return dp_forward<N>(ring, bits, xrows, tx, ty, lane, g0, wacc); \
+        break;
+    switch (xpl) {
+        MAS_CASE(1) MAS_CASE(2) MAS_CASE(3) MAS_CASE(4) MAS_CASE(5) MAS_CASE(6) MAS_CASE(7)
+        MAS_CASE(8) MAS_CASE(9) MAS_CASE(10) MAS_CASE(11) MAS_CASE(12) MAS_CASE(13) MAS_CASE(14)
+        MAS_CASE(15) MAS_CASE(16)
+    default: break;
+    }
+#undef MAS_CASE
+    return 0.0f;
+}
+
+
 }  // namespace mas

@@ -102,6 +102,35 @@ cudaError_t launch_align_gather_bwd(const float *g_mu_y, const float *y_seg, con
                                     const int32_t *seg_len, float *g_mu_x, int B, int F, int T_x,
                                     int T_y, int T_out, cudaStream_t st);
 
+// mas_prior_tc.cu: tensor-core variant of the fused kernel
+struct TcLayout {
+    int ok;                // 0: shape not eligible (use the CUDA-core kernel)
+    int Fp;                // F rounded up to the MMA K step (8)
+    int xrows, nch, nstages, bits_slots;
+    int nb;                // accumulator buffers in TMEM
+    int col_ahi, col_alo, col_d;   // TMEM column map
+    size_t off_stages, off_slabs, off_staging, off_bits, off_ysq, off_musq, off_first, off_dur, off_zero, off_bars, total;
+};
+struct PriorTcArgs {
+    const float *mu_x;
+    const float *y;
+    const int32_t *t_x;
+    const int32_t *t_y;
+    void *path;
+    int32_t *durations;
+    int32_t *frame_idx;
+    float *score;
+    long long *stats;      // optional [grid][32] cycle counters (MAS_PRIOR_STATS=1), else NULL
+    float *lp_out;         // optional parity tap [B,T_x,T_y]: the prior exactly as the DP consumed it
+    int B, F, T_x, T_y;
+    int path_esize;
+    unsigned long long one;
+    TcLayout lay;
+};
+TcLayout tc_layout(int F, int T_x, int T_y);
+cudaError_t launch_from_prior_tc(const PriorTcArgs &a, cudaStream_t st);
+
+int sm_count();
 void count_launch(int n = 1);
 
 }  // namespace mas

@@ -97,41 +97,6 @@ size_t prior_extra_smem(int F, int T_x, int T_y, bool second_bits)
     return prior_smem(F, (int)xrows, second_bits ? nch * xrows * 4 : 0).total_extra;
 }
 
-// one cell of the prior, same operation order as the producers / log_prior_kernel
-__device__ __forceinline__ float lp_cell(const float *mub, const float *yb, int F, int T_x,
-                                         int64_t T_y, int x, int y, float cst)
-{
-    float ysq = 0.0f, c = 0.0f, msq = 0.0f;
-    for (int f = 0; f < F; ++f) {
-        const float m = __ldg(mub + (int64_t)f * T_x + x);
-        const float v = __ldg(yb + (int64_t)f * T_y + y);
-        ysq = __fmaf_rn(v, v, ysq);
-        c = __fmaf_rn(m, v, c);
-        msq = __fmaf_rn(m, m, msq);
-    }
-    return ((-0.5f * ysq + c) + -0.5f * msq) + cst;
-}
-
-template <int XPLMAX>
-__device__ __forceinline__ float prior_forward_dispatch(const TileRing &ring, uint32_t *bits,
-                                                        int xrows, int tx, int ty, int lane, int g0,
-                                                        long long *wacc)
-{
-    const int xpl = (tx + 31) >> 5;
-#define MAS_CASE(N)                                                                           \
-    case N:                                                                                   \
-        if constexpr (N <= XPLMAX) return dp_forward<N>(ring, bits, xrows, tx, ty, lane, g0, wacc); \
-        break;
-    switch (xpl) {
-        MAS_CASE(1) MAS_CASE(2) MAS_CASE(3) MAS_CASE(4) MAS_CASE(5) MAS_CASE(6) MAS_CASE(7)
-        MAS_CASE(8) MAS_CASE(9) MAS_CASE(10) MAS_CASE(11) MAS_CASE(12) MAS_CASE(13) MAS_CASE(14)
-        MAS_CASE(15) MAS_CASE(16)
-    default: break;
-    }
-#undef MAS_CASE
-    return 0.0f;
-}
-
 // One work item = 32 tokens x 32 frames of the prior by one warp: thread (xg, yg) owns 4 tokens
 // x 8 frames, i.e. 32 independent fp32 FMA chains (16 packed FFMA2 per feature) fed by 3
 // conflict-free LDS.128.  Accumulation runs over f in ascending order with
@@ -632,7 +597,7 @@ __global__ void __launch_bounds__(128) log_prior_kernel(const float *__restrict_
     }
 }
 
-static int sm_count()
+int sm_count()
 {
     static int cached[64] = {0};
     int dev = 0;

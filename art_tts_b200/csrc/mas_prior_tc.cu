@@ -1,0 +1,711 @@
+// mas_prior_tc.cu -- fused Gaussian log-prior + MAS with the prior on the 5th-gen tensor cores.
+//
+// Same contract as mas_prior_kernel (mas_prior.cu; replaces tts.py:483-505), different engine
+// for the cross term sum_f mu[f,x]*y[f,j]: the reference computes it with an fp32 GEMM
+// (torch.matmul, tts.py:491-493), and so does this kernel -- tcgen05.mma kind::tf32 with the
+// 3xTF32 split, which restores fp32-level accuracy from tf32 products:
+//
+//     a = a_hi + a_lo,  b = b_hi + b_lo   (a_hi = tf32(a), a_lo = tf32(a - a_hi), same for b)
+//     a*b ~= a_lo*b_hi + a_hi*b_lo + a_hi*b_hi          (dropped a_lo*b_lo ~ 2^-22 |a*b|)
+//
+// accumulated in fp32 in tensor memory (measured on B200, profiles/microbench/tc_prior.cu:
+// max error 3e-5 on sums of magnitude 35, vs 1e-5 for a sequential fp32 FMA chain and 1e-2 for
+// plain tf32).  The FMA pipe was the binding resource of the CUDA-core kernel (80 FMA per
+// cell); here one utterance's mu_x lives in TENSOR MEMORY as the A operand (hi and lo parts,
+// one column per feature, one lane per token) and each 32-frame slab of y is the B operand
+// in shared memory, so a tile costs 60 MMAs of 128x32x8 and no CUDA-core arithmetic beyond
+// the three adds of tts.py:495.
+//
+// Persistent CTA per SM, 12 warps, all hand-offs are mbarriers:
+//   warps 0-3  epilogue (TMEM lane quarter = warp id): per tile tcgen05.ld the accumulator,
+//              add the y / mu / const terms and write the swizzled tile the DP warp consumes
+//              (same ring layout as the other kernels)
+//   warps 8-11 mu_x movers (TMEM lane quarter = warp id - 8): run one utterance AHEAD -- hold
+//              the next utterance's mu_x in registers (global loads issued while the current
+//              one is still being multiplied) and, the moment its last MMA has retired, split
+//              it into tf32 hi/lo and tcgen05.st it into TMEM; also produce -0.5|mu|^2
+//   warp 4     DP warp        (mas_dp.cuh dp_forward, unchanged)
+//   warp 5     MMA issuer     (one lane): tiles are issued in PAIRS, interleaving the MMAs of
+//              their (up to four) independent accumulators -- back-to-back MMAs into the same
+//              accumulator serialise at ~100 cycles each (measured), independent ones overlap
+//   warp 6     slab loader    (cp.async y slabs in the MN-major SWIZZLE_128B_BASE32B layout,
+//              tf32 hi/lo split in place, -0.5|y|^2 per frame, bulk zero-fill of the path)
+//   warp 7     backtrack warp (unchanged: one utterance behind, second direction-bit buffer)
+#include <algorithm>
+
+#include "mas_dp.cuh"
+#include "mas_internal.h"
+
+namespace mas {
+
+namespace {
+
+constexpr int kTcThreads = 416;
+constexpr int kTcDp = 4, kTcMma = 5, kTcLoader = 6, kTcBack = 7;   // warps 0-3 epilogue, 8-11 mu_x movers
+constexpr int kTcLoader2 = 12;    // second slab loader (odd tiles)
+constexpr int kTcSlabs = 4;       // y slabs (hi+lo) in flight
+constexpr int kTcLag = 1;         // a slab is finished one loader iteration after its copy was issued
+constexpr int kTcYsq = 8;         // ring of per-slab -0.5|y|^2 vectors (> kTcSlabs + D buffers)
+constexpr int kTcStage = 2;        // staging buffers [F][32 frames] behind the cp.async copies: one per loader warp
+constexpr int kTcMsq = 4;         // ring of per-utterance -0.5|mu|^2 vectors (> utterances an accumulator lags)
+constexpr int kTcZeroBytes = 4096;
+constexpr int kTcTmemCols = 512;
+
+// ---------------------------------------------------------------- tcgen05 wrappers
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t *bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem descriptor]; `acc` = 0 overwrites D
+__device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t acc)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+                 "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc)
+                 : "memory");
+}
+// B operand = one 32-frame slab of y, K-MAJOR in shared memory, SWIZZLE_32B: per k step (8
+// features) a [32 frames][8 features] block of 32-byte rows, 1 KB contiguous; the two 16-byte
+// halves of row j are swapped when (j >> 2) & 1.  SBO = 256 B between groups of 8 rows.
+// Measured on B200 (profiles/microbench/tc_prior.cu, 128x32x8 tf32, A in TMEM, 4 accumulators in
+// flight): 33 cycles/MMA with this layout, 45-190 with SWIZZLE_128B rows, 135 with the MN-major
+// layout y has in HBM -- hence the transposing loader.
+__device__ __forceinline__ uint64_t tc_bdesc(uint32_t saddr)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3fff);
+    d |= (uint64_t)(16 >> 4) << 16;
+    d |= (uint64_t)(256 >> 4) << 32;
+    d |= (uint64_t)1 << 46;  // descriptor version of sm_100
+    d |= (uint64_t)6 << 61;  // SWIZZLE_32B
+    return d;
+}
+// one elected lane of a converged warp (operands stay warp-uniform for the tcgen05 issue)
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
+__device__ __forceinline__ float tf32_rn(float x)
+{
+    return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
+}
+
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8])
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(r[0]),
+                 "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+
+// coarse cycle accounting (PriorTcArgs::stats, MAS_PRIOR_STATS=1; profiles/prior_tc_stats.py)
+struct TcStat {
+    long long acc = 0, t0 = 0;
+    bool on;
+    __device__ __forceinline__ explicit TcStat(bool e) : on(e) {}
+    __device__ __forceinline__ void begin() { if (on) t0 = clock64(); }
+    __device__ __forceinline__ void end() { if (on) acc += clock64() - t0; }
+};
+
+}  // namespace
+
+// Shared-memory carve-up and TMEM column map of the tensor-core kernel, or ok == 0 when the
+// shape does not qualify (T_x > 256, F > 96, or the buffers do not fit): the CUDA-core kernel
+// of mas_prior.cu takes those.
+TcLayout tc_layout(int F, int T_x, int T_y)
+{
+    TcLayout L{};
+    L.ok = 0;
+    L.Fp = (F + 7) / 8 * 8;
+    L.xrows = (T_x + 31) / 32 * 32;
+    L.nch = (T_y + 31) / 32;
+    if (T_x > 256 || L.Fp > 96) return L;
+    const int mt = (T_x + 127) / 128;          // M tiles of 128 tokens
+    L.col_ahi = 0;
+    L.col_alo = mt * L.Fp;
+    L.col_d = 2 * mt * L.Fp;
+    L.nb = std::min(4, (kTcTmemCols - L.col_d) / 64);   // accumulator buffers of 2 x 32 columns
+    if (L.nb < 2) return L;
+    const size_t stage = (size_t)L.xrows * 128, bits = (size_t)L.nch * L.xrows * 4;
+    const size_t slabs = (size_t)kTcSlabs * 2 * L.Fp * 128;   // hi + lo, K-major: 1 KB per k step of 8 features
+    const size_t misc = (size_t)kTcYsq * 128 + (size_t)kTcMsq * 256 * 4 + (((size_t)T_x * 8 + 15) & ~(size_t)15) +
+                        kTcZeroBytes + 512 + (size_t)kTcStage * L.Fp * 128;
+    for (int slots = 2; slots >= 1 && !L.ok; --slots)
+        for (int ns = 4; ns >= 2; --ns)
+            if ((size_t)ns * stage + slots * bits + slabs + misc <= (size_t)kSmemBudget) {
+                L.nstages = ns;
+                L.bits_slots = slots;
+                L.ok = 1;
+                break;
+            }
+    if (!L.ok) return L;
+    L.off_stages = 0;
+    L.off_slabs = (size_t)L.nstages * stage;                  // both multiples of 1024
+    L.off_staging = L.off_slabs + slabs;
+    L.off_bits = L.off_staging + (size_t)kTcStage * L.Fp * 128;
+    L.off_ysq = L.off_bits + (size_t)L.bits_slots * bits;
+    L.off_musq = L.off_ysq + (size_t)kTcYsq * 128;
+    L.off_first = L.off_musq + (size_t)kTcMsq * 256 * 4;
+    L.off_dur = L.off_first + (size_t)T_x * 4;
+    L.off_zero = (L.off_dur + (size_t)T_x * 4 + 15) & ~(size_t)15;
+    L.off_bars = L.off_zero + kTcZeroBytes;
+    L.total = L.off_bars + 512;
+    // one CTA per SM: each CTA allocates all 512 TMEM columns
+    L.total = std::max(L.total, (size_t)(kSmemBudget / 2 + 1024));
+    return L;
+}
+
+template <int XPLMAX>
+__global__ void __launch_bounds__(kTcThreads, 1) mas_prior_tc_kernel(const PriorTcArgs a)
+{
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const TcLayout &L = a.lay;
+    const int F = a.F, Fp = L.Fp, T_x = a.T_x, NS = L.nstages, NB = L.nb;
+    const int64_t T_y = a.T_y;
+    float *stages = reinterpret_cast<float *>(smem + L.off_stages);
+    float *slabs = reinterpret_cast<float *>(smem + L.off_slabs);
+    float *staging = reinterpret_cast<float *>(smem + L.off_staging);   // [kTcStage][Fp][32]
+    uint32_t *bits_a = reinterpret_cast<uint32_t *>(smem + L.off_bits);
+    uint32_t *bits_b = bits_a + (size_t)L.nch * L.xrows;
+    float *ysq = reinterpret_cast<float *>(smem + L.off_ysq);
+    float *musq = reinterpret_cast<float *>(smem + L.off_musq);   // [kTcMsq][256]
+    int *first = reinterpret_cast<int *>(smem + L.off_first);
+    int *dur = reinterpret_cast<int *>(smem + L.off_dur);
+    uint32_t *zbuf = reinterpret_cast<uint32_t *>(smem + L.off_zero);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + L.off_bars);
+    // barrier map
+    uint64_t *ring_full = bars, *ring_empty = bars + 4;
+    uint64_t *slab_full = bars + 8, *slab_free = bars + 12;
+    uint64_t *d_full = bars + 16, *d_empty = bars + 20;
+    uint64_t *a_ready = bars + 24, *a_free = bars + 25;
+    volatile int *ctrl = reinterpret_cast<volatile int *>(bars + 32);   // [0] zdone [1] fwd_done [2] bt_done
+    uint32_t *tslot = reinterpret_cast<uint32_t *>(bars + 40);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int part_floats = Fp * kTileY;              // one K-major part: [Fp/8 k steps][32 frames][8 features]
+    const int slab_floats = 2 * part_floats;          // hi then lo
+    const float cst = (float)(-0.5 * 1.8378770664093453 * (double)F);  // -0.5*log(2*pi)*F, tts.py:484
+
+    TileRing ring;
+    ring.stages = stages;
+    ring.full = ring_full;
+    ring.empty = ring_empty;
+    ring.nstages = NS;
+    ring.stage_floats = L.xrows * kTileY;
+    if (tid == 0) {
+        for (int s = 0; s < 4; ++s) {
+            mbar_init(&ring_full[s], 4);    // the four epilogue warps
+            mbar_init(&ring_empty[s], 1);
+            mbar_init(&slab_full[s], 1);
+            mbar_init(&slab_free[s], 1);
+            mbar_init(&d_full[s], 1);
+            mbar_init(&d_empty[s], 4);
+        }
+        mbar_init(a_ready, 4);
+        mbar_init(a_free, 1);
+        ctrl[0] = 0;
+        ctrl[1] = 0;
+        ctrl[2] = 0;
+        mbar_fence_init();
+    }
+    for (int i = tid; i < kTcZeroBytes / 4; i += kTcThreads) zbuf[i] = 0u;
+    for (int i = tid; i < kTcSlabs * slab_floats; i += kTcThreads) slabs[i] = 0.0f;
+    for (int i = tid; i < kTcStage * Fp * kTileY; i += kTcThreads) staging[i] = 0.0f;  // rows F..Fp-1 stay zero
+    fence_proxy_async_smem();
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tslot)),
+                     "r"(kTcTmemCols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tbase = *tslot;
+
+    auto geometry = [&](int u, int &tx, int &ty, int &ntiles, bool &degenerate) {
+        tx = min(max(a.t_x[u], 0), T_x);
+        ty = min(max(a.t_y[u], 0), a.T_y);
+        degenerate = tx > ty && ty >= 1;
+        const bool active = tx >= 1 && ty >= 1 && !degenerate;
+        ntiles = active ? (ty + kTileY - 1) / kTileY : 0;
+    };
+    // which 128-token M tiles of tile t hold band cells (all of them when the parity tap is on)
+    auto tile_mask = [&](int tx, int ty, int t) -> int {
+        const int mt = (tx + 127) >> 7;
+        if (a.lp_out) return (1 << mt) - 1;
+        const int lo = max(0, tx + t * kTileY - ty), hi = min(tx - 1, t * kTileY + kTileY - 1);
+        int m = 0;
+        for (int i = 0; i < mt; ++i)
+            if (128 * i <= hi && 128 * i + 127 >= lo) m |= 1 << i;
+        return m;
+    };
+    volatile int *zdone = ctrl, *fwd_done = ctrl + 1, *bt_done = ctrl + 2;
+    const bool son = a.stats != nullptr;
+    long long *so = son ? a.stats + (size_t)blockIdx.x * 32 : nullptr;
+    const int bslots = L.bits_slots;
+    auto bits_of = [&](int k) -> uint32_t * { return ((k & 1) && bslots == 2) ? bits_b : bits_a; };
+
+    if (warp == kTcDp) {
+        // ======================= DP warp: forward recurrence =======================
+        int g = 0, k = 0;
+        TcStat s_all(son);
+        long long dp_wait = 0;
+        s_all.begin();
+        for (int u = blockIdx.x; u < a.B; u += gridDim.x, ++k) {
+            int tx, ty, ntiles;
+            bool degenerate;
+            geometry(u, tx, ty, ntiles, degenerate);
+            if (ntiles > 0) {
+                while (*bt_done < k - bslots + 1) __nanosleep(32);
+                __threadfence_block();
+                const float score = prior_forward_dispatch<XPLMAX>(ring, bits_of(k), L.xrows, tx, ty, lane, g,
+                                                                   son ? &dp_wait : nullptr);
+                g += ntiles;
+                if (lane == 0 && a.score) a.score[u] = score;
+            }
+            __threadfence_block();
+            __syncwarp();
+            if (lane == 0) *fwd_done = k + 1;
+        }
+        s_all.end();
+        if (son && lane == 0) { so[0] = s_all.acc; so[1] = dp_wait; so[2] = g; so[3] = k; }
+    } else if (warp == kTcBack) {
+        // ======================= backtrack warp =======================
+        int k = 0;
+        for (int u = blockIdx.x; u < a.B; u += gridDim.x, ++k) {
+            int tx, ty, ntiles;
+            bool degenerate;
+            geometry(u, tx, ty, ntiles, degenerate);
+            for (int x = lane; x < T_x; x += 32) dur[x] = 0;
+            while (*fwd_done <= k) __nanosleep(32);
+            __threadfence_block();
+            __syncwarp();
+            if (ntiles > 0) {
+                if (lane == 0) backtrack_bits(bits_of(k), L.xrows, tx, ty, first, dur, true);
+            } else if (degenerate) {
+                if (lane == 0) {  // reference semantics for t_x > t_y: raw prior values (mas_dp.cuh)
+                    const float *mub = a.mu_x + (int64_t)u * F * T_x;
+                    const float *yb = a.y + (int64_t)u * F * T_y;
+                    auto val = [&](int x, int y) { return lp_cell(mub, yb, F, T_x, T_y, x, y, cst); };
+                    backtrack_degenerate(val, tx, ty, first, dur);
+                    if (a.score) a.score[u] = val(tx - 1, ty - 1);
+                }
+            } else if (lane == 0 && a.score) {
+                a.score[u] = 0.0f;
+            }
+            __threadfence_block();
+            __syncwarp();
+            if (lane == 0) *bt_done = k + 1;
+            if (a.path) {
+                while (*zdone <= k) __nanosleep(64);
+                __threadfence_block();
+            }
+            char *pb = a.path ? static_cast<char *>(a.path) + (int64_t)u * T_x * T_y * a.path_esize : nullptr;
+            write_path_ones(pb, a.durations ? a.durations + (int64_t)u * T_x : nullptr, first, dur, T_x, T_y,
+                            a.path_esize, a.one, lane, 32);
+            write_frame_idx(a.frame_idx ? a.frame_idx + (int64_t)u * T_y : nullptr, first, dur, T_x, ty, a.T_y,
+                            lane, 32);
+            __syncwarp();
+        }
+    } else if (warp == kTcLoader || warp == kTcLoader2) {
+        // ======================= slab loader =======================
+        // y[:, 32t..32t+31] -> staging buffer in shared memory (cp.async, 16-byte pieces, the natural
+        // [feature][32 frames] layout) -> one pass per slab that transposes into the K-major hi/lo slab:
+        // lane (r, c) = (lane / 8, lane % 8) owns frames 4c..4c+3 of the feature groups {4(r+4n)..+3}:
+        // four 16-byte reads, a 4x4 transpose in registers, the tf32 split, four + four 16-byte stores
+        // (frame rows), plus -0.5|y|^2 per frame.  Loops stay rolled on purpose: with six different
+        // roles resident it is the instruction cache, not a pipe, that a warp waits for (ncu:
+        // stall_no_inst dominated the unrolled version of this pass).
+        // Also: the bulk (TMA) zero-fill of the dense output path.
+        const bool vec16 = (T_y % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.y) & 15) == 0);
+        const int c = lane & 7, r = lane >> 3;
+        TcStat l_all(son), l_free(son), l_fin(son), l_cp(son), l_ld(son), l_fence(son), l_issue(son);
+        l_all.begin();
+        auto finish = [&](int gg) {
+            l_cp.begin();
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            l_cp.end();
+            l_fin.begin();
+            __syncwarp();                 // every lane's copies of this slab have landed
+            const float *st = staging + (size_t)(gg & 1) * Fp * kTileY + 4 * c;   // tile parity == owning loader
+            float *hi = slabs + (size_t)(gg % kTcSlabs) * slab_floats, *lo = hi + part_floats;
+            float q0 = 0.0f, q1 = 0.0f, q2 = 0.0f, q3 = 0.0f;   // frames 4c .. 4c+3
+#pragma unroll 1
+            for (int fg = r; 4 * fg < Fp; fg += 4) {   // feature group: features 4fg .. 4fg+3
+                const float *sp = st + (fg << 7);
+                const float4 a0 = *reinterpret_cast<const float4 *>(sp);
+                const float4 a1 = *reinterpret_cast<const float4 *>(sp + 32);
+                const float4 a2 = *reinterpret_cast<const float4 *>(sp + 64);
+                const float4 a3 = *reinterpret_cast<const float4 *>(sp + 96);
+                q0 = __fmaf_rn(a0.x, a0.x, q0); q0 = __fmaf_rn(a1.x, a1.x, q0); q0 = __fmaf_rn(a2.x, a2.x, q0); q0 = __fmaf_rn(a3.x, a3.x, q0);
+                q1 = __fmaf_rn(a0.y, a0.y, q1); q1 = __fmaf_rn(a1.y, a1.y, q1); q1 = __fmaf_rn(a2.y, a2.y, q1); q1 = __fmaf_rn(a3.y, a3.y, q1);
+                q2 = __fmaf_rn(a0.z, a0.z, q2); q2 = __fmaf_rn(a1.z, a1.z, q2); q2 = __fmaf_rn(a2.z, a2.z, q2); q2 = __fmaf_rn(a3.z, a3.z, q2);
+                q3 = __fmaf_rn(a0.w, a0.w, q3); q3 = __fmaf_rn(a1.w, a1.w, q3); q3 = __fmaf_rn(a2.w, a2.w, q3); q3 = __fmaf_rn(a3.w, a3.w, q3);
+                const float rows[4][4] = {{a0.x, a1.x, a2.x, a3.x}, {a0.y, a1.y, a2.y, a3.y},
+                                          {a0.z, a1.z, a2.z, a3.z}, {a0.w, a1.w, a2.w, a3.w}};
+                // k step fg/2, 16-byte half fg%2 (swapped on rows with (j >> 2) & 1 == c & 1)
+                const int base = ((fg >> 1) << 8) + (c << 5) + (((fg & 1) ^ (c & 1)) << 2);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {   // frame row j = 4c + e
+                    const float4 h = make_float4(tf32_rn(rows[e][0]), tf32_rn(rows[e][1]), tf32_rn(rows[e][2]),
+                                                 tf32_rn(rows[e][3]));
+                    *reinterpret_cast<float4 *>(hi + base + (e << 3)) = h;
+                    *reinterpret_cast<float4 *>(lo + base + (e << 3)) =
+                        make_float4(tf32_rn(rows[e][0] - h.x), tf32_rn(rows[e][1] - h.y), tf32_rn(rows[e][2] - h.z),
+                                    tf32_rn(rows[e][3] - h.w));
+                }
+            }
+#pragma unroll
+            for (int o = 8; o <= 16; o <<= 1) {   // the four feature-group phases r of a frame
+                q0 += __shfl_xor_sync(kFull, q0, o);
+                q1 += __shfl_xor_sync(kFull, q1, o);
+                q2 += __shfl_xor_sync(kFull, q2, o);
+                q3 += __shfl_xor_sync(kFull, q3, o);
+            }
+            if (r == 0)   // tts.py:488-490  y_square
+                *reinterpret_cast<float4 *>(ysq + (gg % kTcYsq) * kTileY + 4 * c) =
+                    make_float4(-0.5f * q0, -0.5f * q1, -0.5f * q2, -0.5f * q3);
+            l_fence.begin();
+            fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core's reads
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&slab_full[gg % kTcSlabs]);
+            l_fence.end();
+            l_fin.end();
+        };
+        // Two loader warps split the tiles by parity of the CTA-lifetime tile index; each owns one
+        // staging buffer: copy of its tile g in flight -> (at its next tile) transpose pass -> next copy.
+        const int lp = (warp == kTcLoader) ? 0 : 1;
+        int g = 0, pend = -1, k = 0;
+        for (int u = blockIdx.x; u < a.B; u += gridDim.x, ++k) {
+            int tx, ty, ntiles;
+            bool degenerate;
+            geometry(u, tx, ty, ntiles, degenerate);
+            const float *yb = a.y + (int64_t)u * F * T_y;
+            char *pb = a.path ? static_cast<char *>(a.path) + (int64_t)u * T_x * T_y * a.path_esize : nullptr;
+            const int64_t pbytes = a.path ? (int64_t)T_x * T_y * a.path_esize : 0;
+            const bool zbulk = bulk_zero_ok(pb, pbytes);
+            if (lp == 0) {   // the even loader also clears the dense output path of the utterance
+                if (zbulk) {
+                    zero_fill_bulk_part(pb, pbytes, 0, 1, zbuf, kTcZeroBytes, lane, 32);
+                    bulk_commit();
+                } else {
+                    zero_fill_part(pb, pbytes, 0, 1, lane, 32);
+                }
+            }
+            for (int t = 0; t < ntiles; ++t, ++g) {
+                if ((g & 1) != lp) continue;
+                if (pend >= 0) finish(pend);   // my previous tile: its copy has had a whole trip to land
+                const int s = g % kTcSlabs;
+                l_free.begin();
+                if (g >= kTcSlabs) mbar_wait_relaxed(&slab_free[s], ((g / kTcSlabs) - 1) & 1);  // MMAs of tile g-kTcSlabs done
+                l_free.end();
+                float *dst = staging + (size_t)lp * Fp * kTileY;
+                const int y0 = t * kTileY;
+                l_issue.begin();
+                if (vec16) {
+                    const int left = ty - (y0 + 4 * c);
+                    const uint32_t bytes = left >= 4 ? 16u : (left > 0 ? 4u * left : 0u);
+                    const float *src = yb + (bytes ? y0 + 4 * c : 0);
+#pragma unroll 5
+                    for (int f = r; f < F; f += 4) cp_async16(dst + (f << 5) + 4 * c, src + (int64_t)f * T_y, bytes);
+                } else {
+                    const int y = y0 + lane;
+                    const uint32_t bytes = y < ty ? 4u : 0u;
+                    const float *src = yb + (y < ty ? y : 0);
+#pragma unroll 4
+                    for (int f = 0; f < F; ++f) cp_async4(dst + (f << 5) + lane, src + (int64_t)f * T_y, bytes);
+                }
+                asm volatile("cp.async.commit_group;" ::: "memory");
+                pend = g;
+                l_issue.end();
+            }
+            if (lp == 0) {
+                // the utterance's zeros must be in HBM before the backtrack warp writes its 1-cells; the
+                // tile in flight is finished first so that the wait for the stores delays nobody
+                if (pend >= 0) { finish(pend); pend = -1; }
+                if (zbulk) bulk_wait_all();
+                __threadfence_block();
+                __syncwarp();
+                if (lane == 0) *zdone = k + 1;
+            }
+        }
+        if (pend >= 0) finish(pend);
+        l_all.end();
+        if (son && lane == 0 && lp == 0) {
+            so[4] = l_all.acc; so[5] = l_free.acc; so[6] = l_fin.acc; so[7] = l_cp.acc;
+            so[23] = l_ld.acc; so[24] = l_fence.acc; so[25] = l_issue.acc;
+        }
+    } else if (warp == kTcMma) {
+        // ======================= MMA issuer =======================
+        // The whole warp runs the loop (converged, warp-uniform operands); one elected lane issues.
+        {
+            // instruction descriptor: D fp32, A/B tf32, A and B K-major, N = 32, M = 128
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
+            const int ksteps = Fp >> 3;
+            int g = 0, ka = 0;
+            TcStat m_all(son), m_a(son), m_s(son), m_d(son), m_i(son);
+            m_all.begin();
+            for (int u = blockIdx.x; u < a.B; u += gridDim.x) {
+                int tx, ty, ntiles;
+                bool degenerate;
+                geometry(u, tx, ty, ntiles, degenerate);
+                if (ntiles == 0) continue;
+                m_a.begin();
+                mbar_wait(a_ready, ka & 1);   // mu_x of this utterance is in TMEM
+                m_a.end();
+                tc_fence_after();
+                for (int t = 0; t < ntiles;) {
+                    // a pair of tiles (g, g+1): up to four independent accumulators in flight
+                    // (accumulator c = 2*e + i: tile e of the pair, M tile i); everything the issue
+                    // loop needs lives in registers -- the single issuing thread is the bottleneck
+                    const int np = (t + 1 < ntiles) ? 2 : 1;
+                    uint32_t dcol[4];
+                    uint64_t bh[2], bl[2];
+                    int am = 0;
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        if (e >= np) break;
+                        const int gg = g + e, s = gg % kTcSlabs, b = gg % NB;
+                        m_s.begin();
+                        mbar_wait(&slab_full[s], (gg / kTcSlabs) & 1);
+                        m_s.end();
+                        m_d.begin();
+                        if (gg >= NB) mbar_wait(&d_empty[b], ((gg / NB) - 1) & 1);  // epilogue drained tile gg-NB
+                        m_d.end();
+                        const uint32_t sb = smem_u32(slabs + (size_t)s * slab_floats);
+                        bh[e] = tc_bdesc(sb);
+                        bl[e] = tc_bdesc(sb + (uint32_t)part_floats * 4u);
+                        am |= tile_mask(tx, ty, t + e) << (2 * e);
+                        dcol[2 * e] = tbase + L.col_d + (b * 2) * 32;
+                        dcol[2 * e + 1] = dcol[2 * e] + 32;
+                    }
+                    tc_fence_after();
+                    m_i.begin();
+                    const uint32_t ahi0 = tbase + L.col_ahi, alo0 = tbase + L.col_alo;
+                    // small terms first: a_lo*b_hi + a_hi*b_lo, then a_hi*b_hi.  One k step = 8 features
+                    // = 8 TMEM columns of A = 1 KB of B (64 descriptor address units).
+                    for (int pass = 0; pass < 3; ++pass) {
+                        const uint32_t abase = (pass == 0) ? alo0 : ahi0;
+                        const uint64_t b0 = (pass == 1) ? bl[0] : bh[0], b1 = (pass == 1) ? bl[1] : bh[1];
+                        for (int j = 0; j < ksteps; ++j) {
+                            const uint32_t acc = (pass | j) != 0;
+                            const uint32_t ac = abase + 8 * j;
+                            const uint32_t bo = (uint32_t)(64 * j);
+                            const uint64_t d0 = b0 + bo, d1 = b1 + bo;
+                            if (elect_one()) {
+                                if (am & 1) tc_mma_ts(dcol[0], ac, d0, idesc, acc);
+                                if (am & 2) tc_mma_ts(dcol[1], ac + Fp, d0, idesc, acc);
+                                if (am & 4) tc_mma_ts(dcol[2], ac, d1, idesc, acc);
+                                if (am & 8) tc_mma_ts(dcol[3], ac + Fp, d1, idesc, acc);
+                            }
+                            __syncwarp();
+                        }
+                    }
+                    if (elect_one()) {
+                        for (int e = 0; e < np; ++e) {
+                            tc_commit(&slab_free[(g + e) % kTcSlabs]);   // slab reusable once these MMAs have read it
+                            tc_commit(&d_full[(g + e) % NB]);            // accumulators ready for the epilogue warps
+                        }
+                    }
+                    __syncwarp();
+                    m_i.end();
+                    t += np;
+                    g += np;
+                }
+                if (elect_one()) tc_commit(a_free);   // mu_x in TMEM no longer needed
+                __syncwarp();
+                ++ka;
+            }
+            m_all.end();
+            if (son && lane == 0) { so[8] = m_all.acc; so[9] = m_a.acc; so[10] = m_s.acc; so[11] = m_d.acc; so[12] = m_i.acc; }
+        }
+    } else if (warp >= 8 && warp < 12) {
+        // ======================= mu_x movers (TMEM lane quarter q = warp - 8) =======================
+        const int q = warp - 8;
+        const uint32_t lane_base = tbase + ((uint32_t)(32 * q) << 16);
+        const bool aon = son && q == 0;
+        TcStat a_all(aon), a_ld(aon), a_w(aon), a_st(aon);
+        a_all.begin();
+        int ka = 0;
+        for (int u = blockIdx.x; u < a.B; u += gridDim.x) {
+            int tx, ty, ntiles;
+            bool degenerate;
+            geometry(u, tx, ty, ntiles, degenerate);
+            if (ntiles == 0) continue;
+            const int mt = (tx + 127) >> 7;
+            const float *mub = a.mu_x + (int64_t)u * F * T_x;
+            float *msq = musq + (ka % kTcMsq) * 256;
+            for (int i = 0; i < mt; ++i) {
+                const bool any = 128 * i + 32 * q < tx;   // some of this warp's tokens exist
+                const int x = 128 * i + 32 * q + lane;
+                const bool xv = x < tx;
+                // every feature of "my" token into registers: all loads in flight at once, issued
+                // while the previous utterance is still being multiplied
+                float v[96];
+                a_ld.begin();
+                if (any) {
+#pragma unroll
+                    for (int f = 0; f < 96; ++f)
+                        v[f] = (xv && f < F) ? __ldg(mub + (int64_t)f * T_x + x) : 0.0f;
+                }
+                a_ld.end();
+                a_w.begin();
+                if (i == 0 && ka > 0) mbar_wait_relaxed(a_free, (ka - 1) & 1, 128);  // previous utterance's MMAs have read A
+                a_w.end();
+                tc_fence_after();
+                a_st.begin();
+                if (any) {
+                    float s = 0.0f;
+#pragma unroll
+                    for (int f0 = 0; f0 < 96; f0 += 8) {
+                        if (f0 >= Fp) break;
+                        uint32_t rh[8], rl[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            const float m = v[f0 + e];
+                            s = __fmaf_rn(m, m, s);
+                            const float h = tf32_rn(m);
+                            rh[e] = __float_as_uint(h);
+                            rl[e] = __float_as_uint(tf32_rn(m - h));
+                        }
+                        tmem_st8(lane_base + L.col_ahi + i * Fp + f0, rh);
+                        tmem_st8(lane_base + L.col_alo + i * Fp + f0, rl);
+                    }
+                    msq[x] = -0.5f * s;   // tts.py:494  mu_square
+                }
+                a_st.end();
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(a_ready);
+            ++ka;
+        }
+        a_all.end();
+        if (aon && lane == 0) { so[19] = a_all.acc; so[20] = a_ld.acc; so[21] = a_w.acc; so[22] = a_st.acc; }
+    } else {
+        // ======================= epilogue warps (TMEM lane quarter q = warp) =======================
+        const int q = warp;
+        const uint32_t lane_base = tbase + ((uint32_t)(32 * q) << 16);
+        int g = 0, ka = 0;
+        const bool eon = son && q == 0;
+        TcStat e_all(eon), e_df(eon), e_re(eon), e_w(eon);
+        e_all.begin();
+        for (int u = blockIdx.x; u < a.B; u += gridDim.x) {
+            int tx, ty, ntiles;
+            bool degenerate;
+            geometry(u, tx, ty, ntiles, degenerate);
+            if (ntiles == 0) continue;
+            const RowMap rm(tx);
+            const float *msq = musq + (ka % kTcMsq) * 256;
+            for (int t = 0; t < ntiles; ++t, ++g) {
+                const int b = g % NB, sidx = g % NS;
+                const int mask = tile_mask(tx, ty, t);
+                e_df.begin();
+                mbar_wait_relaxed(&d_full[b], (g / NB) & 1, 32);
+                e_df.end();
+                tc_fence_after();
+                e_w.begin();
+                uint32_t acc[2][32];
+                bool have[2];
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    have[i] = (mask >> i & 1) && (128 * i + 32 * q < tx);
+                    if (have[i]) tmem_ld32(lane_base + L.col_d + (b * 2 + i) * 32, acc[i]);
+                }
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&d_empty[b]);       // accumulator buffer free again
+                e_w.end();
+                e_re.begin();
+                if (g >= NS) mbar_wait_relaxed(&ring_empty[sidx], ((g / NS) - 1) & 1, 32);  // DP consumed tile g-NS
+                e_re.end();
+                e_w.begin();
+                const float *qs = ysq + (g % kTcYsq) * kTileY;
+                float *tile = stages + (size_t)sidx * ring.stage_floats;
+                const int y0 = t * kTileY;
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    if (!have[i]) continue;
+                    const int x = 128 * i + 32 * q + lane;
+                    if (x >= tx) continue;
+                    const float ms = msq[x];
+                    const int pr = rm.row(x);
+                    float *row = tile + (pr << 5);
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const float4 qq = *reinterpret_cast<const float4 *>(qs + 4 * c);
+                        float4 o;
+                        // tts.py:495: y_square - y_mu_double + mu_square + const
+                        o.x = ((qq.x + __uint_as_float(acc[i][4 * c + 0])) + ms) + cst;
+                        o.y = ((qq.y + __uint_as_float(acc[i][4 * c + 1])) + ms) + cst;
+                        o.z = ((qq.z + __uint_as_float(acc[i][4 * c + 2])) + ms) + cst;
+                        o.w = ((qq.w + __uint_as_float(acc[i][4 * c + 3])) + ms) + cst;
+                        *reinterpret_cast<float4 *>(row + ((c ^ (pr & 7)) << 2)) = o;
+                    }
+                }
+                if (a.lp_out) {   // parity tap (cold path): copy this warp's rows of the tile to HBM
+                    __syncwarp();
+                    for (int i = 0; i < 2; ++i) {
+                        const int x = 128 * i + 32 * q + lane;
+                        if (!have[i] || x >= tx) continue;
+                        const int pr = rm.row(x);
+                        const float *row = tile + (pr << 5);
+                        float *tap = a.lp_out + ((int64_t)u * T_x + x) * T_y + y0;
+                        for (int e = 0; e < kTileY && y0 + e < ty; ++e) tap[e] = row[(((e >> 2) ^ (pr & 7)) << 2) + (e & 3)];
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&ring_full[sidx]);   // this warp's rows of tile g are written
+                e_w.end();
+            }
+            ++ka;
+        }
+        e_all.end();
+        if (eon && lane == 0) { so[13] = e_all.acc; so[16] = e_df.acc; so[17] = e_re.acc; so[18] = e_w.acc; }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tbase), "r"(kTcTmemCols));
+}
+
+cudaError_t launch_from_prior_tc(const PriorTcArgs &a, cudaStream_t st)
+{
+    const int xplmax = (a.T_x + 31) / 32;
+    void (*k)(const PriorTcArgs) = nullptr;
+    if (xplmax <= 2) k = mas_prior_tc_kernel<2>;
+    else if (xplmax <= 4) k = mas_prior_tc_kernel<4>;
+    else if (xplmax <= 6) k = mas_prior_tc_kernel<6>;
+    else k = mas_prior_tc_kernel<8>;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a.lay.total);
+    if (e != cudaSuccess) return e;
+    if (a.lp_out) {   // parity tap: cells the kernel does not produce (padding) read as zero
+        e = cudaMemsetAsync(a.lp_out, 0, (size_t)a.B * a.T_x * a.T_y * sizeof(float), st);
+        if (e != cudaSuccess) return e;
+    }
+    const int grid = std::min(a.B, sm_count());
+    k<<<grid, kTcThreads, a.lay.total, st>>>(a);
+    count_launch();
+    return cudaGetLastError();
+}
+
+}  // namespace mas
