@@ -41,8 +41,10 @@ namespace mas {
 namespace {
 
 constexpr int kTcThreads = 416;
-constexpr int kTcDp = 4, kTcMma = 5, kTcLoader = 6, kTcBack = 7;   // warps 0-3 epilogue, 8-11 mu_x movers
-constexpr int kTcLoader2 = 12;    // second slab loader (odd tiles)
+// warps 0-3 epilogue, 8-11 mu_x movers (TMEM lane quarter = warp % 4 is a hardware rule); the rest is
+// placed by scheduler (warp % 4): the DP warp shares its scheduler with the latency-bound backtrack
+// warp, not with a loader
+constexpr int kTcDp = 4, kTcMma = 5, kTcLoader = 6, kTcLoader2 = 7, kTcBack = 12;
 constexpr int kTcSlabs = 4;       // y slabs (hi+lo) in flight
 constexpr int kTcLag = 1;         // a slab is finished one loader iteration after its copy was issued
 constexpr int kTcYsq = 8;         // ring of per-slab -0.5|y|^2 vectors (> kTcSlabs + D buffers)
