@@ -29,18 +29,22 @@ namespace mas {
 
 // Per-utterance token -> physical row mapping (see above).  `inv` = ceil(65536 / XPL) makes
 // x / XPL an exact multiply-shift for x < 512, XPL <= 16.
+// `lsh` = log2 of the lanes that share an utterance: 5 for the single-warp recurrence, 6 when two
+// DP warps split the token axis (dp_forward2): lane L of 2^lsh owns tokens L*xpl .. L*xpl+xpl-1.
 struct RowMap {
     int xpl;
     uint32_t inv;
-    __device__ __forceinline__ explicit RowMap(int tx)
+    int lsh;
+    __device__ __forceinline__ explicit RowMap(int tx, int lane_shift = 5)
     {
-        xpl = max(1, (tx + 31) >> 5);
+        lsh = lane_shift;
+        xpl = max(1, (tx + (1 << lsh) - 1) >> lsh);
         inv = (65536u + xpl - 1) / xpl;
     }
     __device__ __forceinline__ int row(int x) const
     {
         const int q = (int)((uint32_t)x * inv >> 16);
-        return ((x - q * xpl) << 5) + q;
+        return ((x - q * xpl) << lsh) + q;
     }
 };
 
@@ -216,19 +220,19 @@ __device__ __forceinline__ uint32_t bt_word(const uint32_t *bits, uint32_t sbits
 
 template <bool SMEM>
 __device__ __forceinline__ void backtrack_bits_impl(const uint32_t *bits, int xrows, int tx, int ty,
-                                                    int *first, int *dur)
+                                                    int *first, int *dur, int lsh = 5)
 {
-    const RowMap rm(tx);
+    const RowMap rm(tx, lsh);
     const int xpl = rm.xpl;
     const uint32_t sbits = SMEM ? smem_u32(bits) : 0u;
     int idx = tx - 1, y = ty - 1, top = ty - 1;
     int q = idx / xpl, j = idx - q * xpl;          // token idx = lane q, slot j -> row (j<<5)+q
-    int row = (j << 5) + q;
+    int row = (j << lsh) + q;
     // row of token idx-1
     auto step_row = [&](int &jj, int &qq) {
         if (jj > 0) --jj;
         else { jj = xpl - 1; --qq; }
-        return (jj << 5) + qq;
+        return (jj << lsh) + qq;
     };
     int jn = j, qn = q;
     int rown = idx > 0 ? step_row(jn, qn) : 0;
@@ -270,10 +274,10 @@ __device__ __forceinline__ void backtrack_bits_impl(const uint32_t *bits, int xr
 }
 
 __device__ __forceinline__ void backtrack_bits(const uint32_t *bits, int xrows, int tx, int ty,
-                                               int *first, int *dur, bool bits_in_smem)
+                                               int *first, int *dur, bool bits_in_smem, int lsh = 5)
 {
-    if (bits_in_smem) backtrack_bits_impl<true>(bits, xrows, tx, ty, first, dur);
-    else backtrack_bits_impl<false>(bits, xrows, tx, ty, first, dur);
+    if (bits_in_smem) backtrack_bits_impl<true>(bits, xrows, tx, ty, first, dur, lsh);
+    else backtrack_bits_impl<false>(bits, xrows, tx, ty, first, dur, lsh);
 }
 
 // The reference's degenerate case t_x > t_y: the band of core.pyx:18 is empty, the
@@ -325,6 +329,178 @@ __device__ __forceinline__ void write_frame_idx(int32_t *fi, const int *first, c
         const int d = dur[x], f0 = first[x];
         for (int k = 0; k < d; ++k) fi[f0 + k] = x;
     }
+}
+
+// ------------------------------------------------------------------------------------
+// Two DP warps per utterance.  The 64 lanes of warps w = 0, 1 own consecutive token ranges
+// (global lane L = 32w + lane owns tokens L*XPL .. L*XPL+XPL-1, XPL = ceil(t_x/64)), so each warp
+// runs the recurrence of dp_step on half the tokens.  The one value that crosses the warp
+// boundary -- warp 0's last token of frame y, which warp 1's first token needs at frame y+1 --
+// travels through a small ring in shared memory (`edge`, 4 tiles x 32 frames) and warp 1 simply
+// runs at least one tile behind warp 0 (mbarrier `edge_full` per tile): no per-frame handshake.
+// Warp 0 cannot lap warp 1 by more than the tile ring's depth (<= 3), so the 4-tile edge ring
+// needs no back-pressure of its own.  Tiles use the row map RowMap(tx, 6).
+// ------------------------------------------------------------------------------------
+template <int XPL, bool DIAG>
+__device__ __forceinline__ float dp_step2(float (&V)[XPL], uint32_t (&acc)[XPL], const float (&v)[XPL],
+                                          float &left, int lane, int x0, int y, uint32_t bit,
+                                          float lane0_left)
+{
+    float nxt = 0.0f, last = 0.0f;
+#pragma unroll
+    for (int j = XPL - 1; j >= 0; --j) {
+        const float up = (j == 0) ? left : V[j > 0 ? j - 1 : 0];   // V[x-1, y-1]
+        const bool take_prev = up > V[j];                          // core.pyx:30 max()
+        const float m = take_prev ? up : V[j];
+        float nv = __fadd_rn(m, v[j]);
+        if (DIAG) nv = (x0 + j <= y) ? nv : kNeg;                  // x > y: not reachable yet
+        if (take_prev) acc[j] |= bit;
+        V[j] = nv;
+        if (j == XPL - 1) {
+            last = nv;
+            nxt = __shfl_up_sync(kFull, nv, 1);                    // in flight during the rest
+        }
+    }
+    left = (lane == 0) ? lane0_left : nxt;
+    return last;
+}
+
+template <int XPL, bool DIAG, bool FULL>
+__device__ __forceinline__ void dp_tile2(float (&V)[XPL], uint32_t (&acc)[XPL], float &left,
+                                         const float *__restrict__ stage, float *__restrict__ edge_tile,
+                                         int w, int lane, int x0, int y0, int nsteps)
+{
+    const uint32_t rowbase = smem_u32(stage + ((32 * w + lane) << 5));
+    const uint32_t edgebase = smem_u32(edge_tile);
+    const int sw = lane & 7;
+#pragma unroll 1
+    for (int g = 0; g < 8; ++g) {
+        const int s0 = g << 2;
+        if (!FULL && s0 >= nsteps) break;
+        float4 vv[XPL];
+#pragma unroll
+        for (int j = 0; j < XPL; ++j) vv[j] = lds128(rowbase + (j << 13) + ((g ^ sw) << 4));   // rows j*64 + L
+        // warp 1: warp 0's last token at these four frames (already published: it is a tile ahead)
+        const float4 ev = (w == 1) ? lds128(edgebase + (g << 4)) : make_float4(kNeg, kNeg, kNeg, kNeg);
+        float4 out;
+        float v[XPL];
+#pragma unroll
+        for (int j = 0; j < XPL; ++j) v[j] = f4_get<0>(vv[j]);
+        out.x = dp_step2<XPL, DIAG>(V, acc, v, left, lane, x0, y0 + s0, 1u << s0, ev.x);
+        out.y = out.z = out.w = 0.0f;
+        if (FULL || s0 + 1 < nsteps) {
+#pragma unroll
+            for (int j = 0; j < XPL; ++j) v[j] = f4_get<1>(vv[j]);
+            out.y = dp_step2<XPL, DIAG>(V, acc, v, left, lane, x0, y0 + s0 + 1, 2u << s0, ev.y);
+        }
+        if (FULL || s0 + 2 < nsteps) {
+#pragma unroll
+            for (int j = 0; j < XPL; ++j) v[j] = f4_get<2>(vv[j]);
+            out.z = dp_step2<XPL, DIAG>(V, acc, v, left, lane, x0, y0 + s0 + 2, 4u << s0, ev.z);
+        }
+        if (FULL || s0 + 3 < nsteps) {
+#pragma unroll
+            for (int j = 0; j < XPL; ++j) v[j] = f4_get<3>(vv[j]);
+            out.w = dp_step2<XPL, DIAG>(V, acc, v, left, lane, x0, y0 + s0 + 3, 8u << s0, ev.w);
+        }
+        if (w == 0 && lane == 31)   // publish my last token (token 32*XPL - 1) for warp 1
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(edgebase + (g << 4)), "f"(out.x),
+                         "f"(out.y), "f"(out.z), "f"(out.w)
+                         : "memory");
+    }
+}
+
+// Forward pass of one utterance by DP warp `w` of two.  `edge` = 4 x 32 floats, `edge_full` = 4
+// mbarriers (count 1); ring.empty barriers must expect TWO arrivals per tile.  Returns
+// V[t_x-1, t_y-1] in every lane of the warp that owns token t_x-1 (`*owns` = 1), else *owns = 0.
+template <int XPL>
+__device__ __noinline__ float dp_forward2(const TileRing ring, uint32_t *bits, int xrows, int tx, int ty,
+                                          int lane, int w, int g0, float *edge, uint64_t *edge_full,
+                                          int *owns, long long *wait_acc = nullptr)
+{
+    float V[XPL];
+    uint32_t acc[XPL];
+#pragma unroll
+    for (int j = 0; j < XPL; ++j) {
+        V[j] = kNeg;
+        acc[j] = 0u;
+    }
+    const int L = 32 * w + lane;
+    const int x0 = L * XPL;                     // this lane's first token
+    float left = (L == 0) ? 0.0f : kNeg;        // frame 0: v_prev(x=0) = 0, everything else -1e9
+    const int ntiles = (ty + kTileY - 1) / kTileY;
+    int stage = g0 % ring.nstages;
+    uint32_t phase = (uint32_t)(g0 / ring.nstages) & 1u;
+    for (int t = 0; t < ntiles; ++t) {
+        const int gt = g0 + t;
+        long long t0 = 0;
+        if (wait_acc) t0 = clock64();
+        mbar_wait(&ring.full[stage], phase);
+        if (w == 1) mbar_wait(&edge_full[gt & 3], (uint32_t)(gt >> 2) & 1u);   // warp 0 finished this tile
+        if (wait_acc) *wait_acc += clock64() - t0;
+        const float *tile = ring.stages + stage * ring.stage_floats;
+        float *etile = edge + ((gt & 3) << 5);
+        const int y0 = t * kTileY;
+        const int nsteps = min(kTileY, ty - y0);
+        const bool diag = y0 < tx;  // some token x > y still exists in this tile
+        if (nsteps == kTileY) {
+            if (diag) dp_tile2<XPL, true, true>(V, acc, left, tile, etile, w, lane, x0, y0, nsteps);
+            else dp_tile2<XPL, false, true>(V, acc, left, tile, etile, w, lane, x0, y0, nsteps);
+        } else {
+            dp_tile2<XPL, true, false>(V, acc, left, tile, etile, w, lane, x0, y0, nsteps);
+        }
+        __syncwarp();
+        if (lane == 0) {
+            mbar_arrive(&ring.empty[stage]);
+            if (w == 0) mbar_arrive(&edge_full[gt & 3]);   // release: lane 31's stores are ordered by __syncwarp
+        }
+        if (++stage == ring.nstages) {
+            stage = 0;
+            phase ^= 1u;
+        }
+        // x == y always steps down (core.pyx:34 `index == y`), token 0 never does.
+        if (diag) {
+#pragma unroll
+            for (int j = 0; j < XPL; ++j)
+                if (((x0 + j) >> 5) == t) acc[j] |= 1u << ((x0 + j) & 31);
+        }
+        if (L == 0) acc[0] = 0u;
+        uint32_t *dst = bits + (size_t)t * xrows + L;
+#pragma unroll
+        for (int j = 0; j < XPL; ++j) {
+            dst[j << 6] = acc[j];
+            acc[j] = 0u;
+        }
+    }
+    // total alignment score: token tx-1 = global lane (tx-1)/XPL, slot (tx-1)%XPL
+    const int ql = (tx - 1) / XPL, qj = (tx - 1) - ql * XPL;
+    *owns = (ql >> 5) == w;
+    float s = 0.0f;
+#pragma unroll
+    for (int j = 0; j < XPL; ++j)
+        if (j == qj) s = V[j];
+    return __shfl_sync(kFull, s, ql & 31);
+}
+
+template <int XPLMAX>
+__device__ __forceinline__ float prior_forward2_dispatch(const TileRing &ring, uint32_t *bits, int xrows,
+                                                         int tx, int ty, int lane, int w, int g0,
+                                                         float *edge, uint64_t *edge_full, int *owns,
+                                                         long long *wacc)
+{
+    const int xpl = (tx + 63) >> 6;
+#define MAS_CASE2(N)                                                                                       \
+    case N:                                                                                                \
+        if constexpr (N <= XPLMAX)                                                                         \
+            return dp_forward2<N>(ring, bits, xrows, tx, ty, lane, w, g0, edge, edge_full, owns, wacc);    \
+        break;
+    switch (xpl) {
+        MAS_CASE2(1) MAS_CASE2(2) MAS_CASE2(3) MAS_CASE2(4)
+    default: break;
+    }
+#undef MAS_CASE2
+    *owns = 0;
+    return 0.0f;
 }
 
 // one cell of the prior, same operation order as the producers / log_prior_kernel

@@ -40,11 +40,11 @@ namespace mas {
 
 namespace {
 
-constexpr int kTcThreads = 416;
+constexpr int kTcThreads = 448;
 // warps 0-3 epilogue, 8-11 mu_x movers (TMEM lane quarter = warp % 4 is a hardware rule); the rest is
 // placed by scheduler (warp % 4): the DP warp shares its scheduler with the latency-bound backtrack
 // warp, not with a loader
-constexpr int kTcDp = 4, kTcMma = 5, kTcLoader = 6, kTcLoader2 = 7, kTcBack = 12;
+constexpr int kTcDp = 4, kTcMma = 5, kTcLoader = 6, kTcLoader2 = 7, kTcBack = 12, kTcDp2 = 13;
 constexpr int kTcSlabs = 4;       // y slabs (hi+lo) in flight
 constexpr int kTcLag = 1;         // a slab is finished one loader iteration after its copy was issued
 constexpr int kTcYsq = 8;         // ring of per-slab -0.5|y|^2 vectors (> kTcSlabs + D buffers)
@@ -137,7 +137,7 @@ TcLayout tc_layout(int F, int T_x, int T_y)
     TcLayout L{};
     L.ok = 0;
     L.Fp = (F + 7) / 8 * 8;
-    L.xrows = (T_x + 31) / 32 * 32;
+    L.xrows = (T_x + 63) / 64 * 64;            // two DP warps: 64 lanes share the token axis
     L.nch = (T_y + 31) / 32;
     if (T_x > 256 || L.Fp > 96) return L;
     const int mt = (T_x + 127) / 128;          // M tiles of 128 tokens
@@ -148,8 +148,8 @@ TcLayout tc_layout(int F, int T_x, int T_y)
     if (L.nb < 2) return L;
     const size_t stage = (size_t)L.xrows * 128, bits = (size_t)L.nch * L.xrows * 4;
     const size_t slabs = (size_t)kTcSlabs * 2 * L.Fp * 128;   // hi + lo, K-major: 1 KB per k step of 8 features
-    const size_t misc = (size_t)kTcYsq * 128 + (size_t)kTcMsq * 256 * 4 + (((size_t)T_x * 8 + 15) & ~(size_t)15) +
-                        kTcZeroBytes + 512 + (size_t)kTcStage * L.Fp * 128;
+    const size_t misc = (size_t)kTcYsq * 128 + (size_t)kTcMsq * 256 * 4 + (((size_t)T_x * 8 + 15) & ~(size_t)15) + 16 +
+                        kTcZeroBytes + 1024 + (size_t)kTcStage * L.Fp * 128;
     for (int slots = 2; slots >= 1 && !L.ok; --slots)
         for (int ns = 4; ns >= 2; --ns)
             if ((size_t)ns * stage + slots * bits + slabs + misc <= (size_t)kSmemBudget) {
@@ -169,7 +169,7 @@ TcLayout tc_layout(int F, int T_x, int T_y)
     L.off_dur = L.off_first + (size_t)T_x * 4;
     L.off_zero = (L.off_dur + (size_t)T_x * 4 + 15) & ~(size_t)15;
     L.off_bars = L.off_zero + kTcZeroBytes;
-    L.total = L.off_bars + 512;
+    L.total = L.off_bars + 1024;
     // one CTA per SM: each CTA allocates all 512 TMEM columns
     L.total = std::max(L.total, (size_t)(kSmemBudget / 2 + 1024));
     return L;
@@ -200,6 +200,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) mas_prior_tc_kernel(const Prior
     uint64_t *a_ready = bars + 24, *a_free = bars + 25;
     volatile int *ctrl = reinterpret_cast<volatile int *>(bars + 32);   // [0] zdone [1] fwd_done [2] bt_done
     uint32_t *tslot = reinterpret_cast<uint32_t *>(bars + 40);
+    uint64_t *edge_full = bars + 26;                            // [4] DP warp 0 -> DP warp 1, per tile
+    float *edge = reinterpret_cast<float *>(bars + 64);         // [4 tiles][32 frames] boundary values
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int part_floats = Fp * kTileY;              // one K-major part: [Fp/8 k steps][32 frames][8 features]
@@ -215,7 +217,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) mas_prior_tc_kernel(const Prior
     if (tid == 0) {
         for (int s = 0; s < 4; ++s) {
             mbar_init(&ring_full[s], 4);    // the four epilogue warps
-            mbar_init(&ring_empty[s], 1);
+            mbar_init(&ring_empty[s], 2);   // both DP warps
+            mbar_init(&edge_full[s], 1);
             mbar_init(&slab_full[s], 1);
             mbar_init(&slab_free[s], 1);
             mbar_init(&d_full[s], 1);
@@ -226,6 +229,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mas_prior_tc_kernel(const Prior
         ctrl[0] = 0;
         ctrl[1] = 0;
         ctrl[2] = 0;
+        ctrl[3] = 0;
         mbar_fence_init();
     }
     for (int i = tid; i < kTcZeroBytes / 4; i += kTcThreads) zbuf[i] = 0u;
@@ -259,14 +263,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) mas_prior_tc_kernel(const Prior
             if (128 * i <= hi && 128 * i + 127 >= lo) m |= 1 << i;
         return m;
     };
-    volatile int *zdone = ctrl, *fwd_done = ctrl + 1, *bt_done = ctrl + 2;
+    volatile int *zdone = ctrl, *fwd_done = ctrl + 1, *bt_done = ctrl + 2, *fwd_done2 = ctrl + 3;
     const bool son = a.stats != nullptr;
     long long *so = son ? a.stats + (size_t)blockIdx.x * 32 : nullptr;
     const int bslots = L.bits_slots;
     auto bits_of = [&](int k) -> uint32_t * { return ((k & 1) && bslots == 2) ? bits_b : bits_a; };
 
-    if (warp == kTcDp) {
-        // ======================= DP warp: forward recurrence =======================
+    if (warp == kTcDp || warp == kTcDp2) {
+        // ======================= DP warps: forward recurrence (mas_dp.cuh dp_forward2) =======================
+        const int w = (warp == kTcDp) ? 0 : 1;
         int g = 0, k = 0;
         TcStat s_all(son);
         long long dp_wait = 0;
@@ -278,17 +283,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) mas_prior_tc_kernel(const Prior
             if (ntiles > 0) {
                 while (*bt_done < k - bslots + 1) __nanosleep(32);
                 __threadfence_block();
-                const float score = prior_forward_dispatch<XPLMAX>(ring, bits_of(k), L.xrows, tx, ty, lane, g,
-                                                                   son ? &dp_wait : nullptr);
+                int owns = 0;
+                const float score = prior_forward2_dispatch<XPLMAX>(ring, bits_of(k), L.xrows, tx, ty, lane, w, g,
+                                                                    edge, edge_full, &owns,
+                                                                    son ? &dp_wait : nullptr);
                 g += ntiles;
-                if (lane == 0 && a.score) a.score[u] = score;
+                if (owns && lane == 0 && a.score) a.score[u] = score;
             }
             __threadfence_block();
             __syncwarp();
-            if (lane == 0) *fwd_done = k + 1;
+            if (lane == 0) *(w == 0 ? fwd_done : fwd_done2) = k + 1;
         }
         s_all.end();
-        if (son && lane == 0) { so[0] = s_all.acc; so[1] = dp_wait; so[2] = g; so[3] = k; }
+        if (son && lane == 0 && w == 0) { so[0] = s_all.acc; so[1] = dp_wait; so[2] = g; so[3] = k; }
+        if (son && lane == 0 && w == 1) { so[26] = s_all.acc; so[27] = dp_wait; }
     } else if (warp == kTcBack) {
         // ======================= backtrack warp =======================
         int k = 0;
@@ -297,11 +305,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) mas_prior_tc_kernel(const Prior
             bool degenerate;
             geometry(u, tx, ty, ntiles, degenerate);
             for (int x = lane; x < T_x; x += 32) dur[x] = 0;
-            while (*fwd_done <= k) __nanosleep(32);
+            while (*fwd_done <= k || *fwd_done2 <= k) __nanosleep(32);
             __threadfence_block();
             __syncwarp();
             if (ntiles > 0) {
-                if (lane == 0) backtrack_bits(bits_of(k), L.xrows, tx, ty, first, dur, true);
+                if (lane == 0) backtrack_bits(bits_of(k), L.xrows, tx, ty, first, dur, true, 6);
             } else if (degenerate) {
                 if (lane == 0) {  // reference semantics for t_x > t_y: raw prior values (mas_dp.cuh)
                     const float *mub = a.mu_x + (int64_t)u * F * T_x;
@@ -616,7 +624,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mas_prior_tc_kernel(const Prior
             bool degenerate;
             geometry(u, tx, ty, ntiles, degenerate);
             if (ntiles == 0) continue;
-            const RowMap rm(tx);
+            const RowMap rm(tx, 6);
             const float *msq = musq + (ka % kTcMsq) * 256;
             for (int t = 0; t < ntiles; ++t, ++g) {
                 const int b = g % NB, sidx = g % NS;
@@ -692,12 +700,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) mas_prior_tc_kernel(const Prior
 
 cudaError_t launch_from_prior_tc(const PriorTcArgs &a, cudaStream_t st)
 {
-    const int xplmax = (a.T_x + 31) / 32;
+    const int xplmax = (a.T_x + 63) / 64;   // tokens per lane of the two DP warps
     void (*k)(const PriorTcArgs) = nullptr;
     if (xplmax <= 2) k = mas_prior_tc_kernel<2>;
-    else if (xplmax <= 4) k = mas_prior_tc_kernel<4>;
-    else if (xplmax <= 6) k = mas_prior_tc_kernel<6>;
-    else k = mas_prior_tc_kernel<8>;
+    else if (xplmax <= 3) k = mas_prior_tc_kernel<3>;
+    else k = mas_prior_tc_kernel<4>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a.lay.total);
     if (e != cudaSuccess) return e;
     if (a.lp_out) {   // parity tap: cells the kernel does not produce (padding) read as zero
