@@ -18,6 +18,7 @@ FLAG_NO_ASYNC = 2
 FLAG_SPILL_BITS = 4
 FLAG_HOST_NO_TRIM = 8
 FLAG_NO_TENSOR = 16
+FLAG_FORCE_TENSOR = 32
 
 _DTYPES = {
     torch.float32: MAS_F32,

@@ -232,7 +232,9 @@ int mas_from_prior_f32(const float *mu_x, const float *logs, const float *y, con
     if (env_int("MAS_PRIOR_TC", 1) && !(flags & (MAS_FLAG_FORCE_GENERAL | MAS_FLAG_SPILL_BITS | MAS_FLAG_NO_TENSOR))) {
         PriorTcArgs t{};
         t.lay = tc_layout(F, T_x, T_y);
-        if (t.lay.ok) {
+        // measured (profiles/config_sweep.py): below ~32 features the FMA work is so small that the
+        // CUDA-core kernel is as fast or faster (F=16: 0.157 vs 0.166 ms at B=1024, 160x512)
+        if (t.lay.ok && (F >= env_int("MAS_PRIOR_TC_MIN_F", 32) || (flags & MAS_FLAG_FORCE_TENSOR))) {
             t.mu_x = mu_x;
             t.y = y;
             t.t_x = t_x;

@@ -57,8 +57,9 @@ enum {
     MAS_FLAG_NO_ASYNC = 2,      /* fast kernel: stage tiles with LDG/STS instead of cp.async */
     MAS_FLAG_SPILL_BITS = 4,    /* keep the direction bits in the workspace even if they fit  */
     MAS_FLAG_HOST_NO_TRIM = 8,  /* mas_from_prior_host_f32: copy whole padded rows            */
-    MAS_FLAG_NO_TENSOR = 16     /* mas_from_prior_f32: fp32 FMA prior on CUDA cores instead of  */
+    MAS_FLAG_NO_TENSOR = 16,    /* mas_from_prior_f32: fp32 FMA prior on CUDA cores instead of  */
                                 /* the 3xTF32 tensor-core prior                                 */
+    MAS_FLAG_FORCE_TENSOR = 32  /* tensor-core prior whenever the shape allows it (default: F >= 32) */
 };
 
 int mas_abi_version(void);

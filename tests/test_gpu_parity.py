@@ -296,10 +296,15 @@ def test_fused_matches_reference_model_capture(cuda, fname):
         assert (fi[b, y_len[b]:] == -1).all()
 
 
+ENGINES = {"auto": 0, "cuda_core": 16, "tensor_core": 32}   # MAS_FLAG_NO_TENSOR / MAS_FLAG_FORCE_TENSOR
+
+
+@pytest.mark.parametrize("engine", list(ENGINES))
 @pytest.mark.parametrize("F,B,T_x,T_y,seed", [(16, 32, 160, 512, 1), (80, 16, 190, 870, 2),
                                               (80, 3, 33, 95, 3), (7, 2, 5, 40, 4)])
-def test_fused_vs_oracle_configs(cuda, F, B, T_x, T_y, seed):
-    """BASELINE config 2 (articulatory, F=16, ragged) and the LJSpeech shape (F=80)."""
+def test_fused_vs_oracle_configs(cuda, F, B, T_x, T_y, seed, engine):
+    """BASELINE config 2 (articulatory, F=16, ragged) and the LJSpeech shape (F=80), through both
+    engines of the fused kernel: fp32 FMA on CUDA cores and 3xTF32 on the tensor cores."""
     rng = np.random.default_rng(seed)
     x_len = rng.integers(max(1, T_x // 8), T_x + 1, B).astype(np.int32)
     y_len = np.minimum(T_y, 3 * x_len + rng.integers(0, 61, B)).astype(np.int32)
@@ -314,11 +319,64 @@ def test_fused_vs_oracle_configs(cuda, F, B, T_x, T_y, seed):
     lp_ref = oracle.log_prior(mu_x, y)
     path_ref = oracle.maximum_path(lp_ref, mask, n_threads=8)
     path, dur, score, lp = fused(mu_x, y, x_len, y_len, cuda, return_score=True,
-                                 return_log_prior=True)
+                                 return_log_prior=True, flags=ENGINES[engine])
     prior_bars(lp.cpu().numpy(), path.cpu().numpy(), score.cpu().numpy(), lp_ref, path_ref, mask)
     self_path = oracle.maximum_path(lp.cpu().numpy(), mask, n_threads=8)
     assert np.array_equal(path.cpu().numpy(), self_path)
     assert np.array_equal(dur.cpu().numpy(), self_path.sum(-1).astype(np.int32))
+    # without the tap (band-only production of the prior) the path must not change
+    p2, d2 = fused(mu_x, y, x_len, y_len, cuda, flags=ENGINES[engine])
+    assert torch.equal(p2, path) and torch.equal(d2, dur)
+
+
+@pytest.mark.parametrize("T_x", [1, 31, 32, 33, 63, 64, 65, 127, 128, 129, 191, 192, 255, 256, 257])
+def test_tensor_core_engine_token_axis_edges(cuda, T_x):
+    """Token counts around every ownership boundary of the tensor-core kernel: 32 lanes x 2 DP
+    warps (64), the 128-token M tile, and its 256-token limit (257 falls back to CUDA cores)."""
+    rng = np.random.default_rng(100 + T_x)
+    B, F = 5, 24
+    T_y = max(T_x + 40, 3 * T_x // 2)
+    x_len = np.array([T_x, max(1, T_x - 1), max(1, T_x // 2), 1, max(1, T_x - 33)], np.int32)
+    y_len = np.array([T_y, T_y - 7, max(1, T_x // 2), 33, T_y - 1], np.int32)   # incl. t_x == t_y
+    mu_x = rng.standard_normal((B, F, T_x)).astype(np.float32)
+    y = rng.standard_normal((B, F, T_y)).astype(np.float32)
+    mask = rect_mask(x_len, y_len, T_x, T_y)
+    path, dur, score, fidx, lp = fused(mu_x, y, x_len, y_len, cuda, return_score=True,
+                                       return_frame_idx=True, return_log_prior=True,
+                                       flags=ENGINES["tensor_core"])
+    lp_ref = oracle.log_prior(mu_x, y)
+    prior_bars(lp.cpu().numpy(), path.cpu().numpy(), score.cpu().numpy(), lp_ref,
+               oracle.maximum_path(lp_ref, mask), mask)
+    self_path = oracle.maximum_path(lp.cpu().numpy(), mask)
+    assert np.array_equal(path.cpu().numpy(), self_path)
+    assert np.array_equal(dur.cpu().numpy(), self_path.sum(-1).astype(np.int32))
+    assert np.array_equal(fidx.cpu().numpy(), oracle.frame_index(self_path, y_len))
+
+
+def test_fused_engines_agree_at_b1024(cuda):
+    """Bench shape: both engines see the same inputs; their priors differ by rounding only, so
+    durations agree on >= 99.9 % of tokens and every invariant of the path holds for both."""
+    B, F, T_x, T_y = 1024, 80, 190, 872
+    rng = np.random.default_rng(7)
+    x_len = rng.integers(60, T_x + 1, B).astype(np.int32)
+    y_len = np.minimum(870, 4 * x_len + rng.integers(0, 100, B)).astype(np.int32)
+    gen = torch.Generator(device=cuda).manual_seed(3)
+    mu_x = torch.randn(B, F, T_x, device=cuda, generator=gen)
+    y = torch.randn(B, F, T_y, device=cuda, generator=gen)
+    from art_tts_b200 import monotonic_align
+    tx, ty = torch.from_numpy(x_len).to(cuda), torch.from_numpy(y_len).to(cuda)
+    outs = {}
+    for name, fl in ENGINES.items():
+        path, dur, score = monotonic_align.maximum_path_from_prior(mu_x, None, y, tx, ty, return_score=True,
+                                                                   flags=fl)
+        assert torch.equal(path.sum(1)[torch.arange(T_y, device=cuda)[None] < ty[:, None]],
+                           torch.ones(int(ty.sum()), device=cuda))            # one token per valid frame
+        assert torch.equal(dur.sum(1), ty) and torch.equal(path.sum(2).int(), dur)
+        outs[name] = (dur, score)
+    agree = (outs["cuda_core"][0] == outs["tensor_core"][0]).float().mean().item()
+    assert agree >= 0.999, agree
+    assert torch.allclose(outs["cuda_core"][1], outs["tensor_core"][1], rtol=1e-5)
+    assert torch.equal(outs["auto"][0], outs["tensor_core"][0])                  # F = 80 -> tensor cores
 
 
 def test_fused_unfused_plan_for_long_text(cuda):
