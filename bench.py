@@ -47,8 +47,8 @@ B_PER_GPU, T_X, T_Y, T_Y_MAXLEN, N_FEATS = 1024, 190, 872, 870, 80
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--op", default="fused", choices=["fused", "dropin"])
     ap.add_argument("--batch", type=int, default=B_PER_GPU)
@@ -58,6 +58,8 @@ def parse():
     ap.add_argument("--no-dropin", action="store_true")
     ap.add_argument("--e2e-chunk", type=int, default=0, help="utterances per H2D chunk (0 = library default)")
     ap.add_argument("--e2e-no-trim", action="store_true", help="copy whole padded rows")
+    ap.add_argument("--engine", default="auto", choices=["auto", "tensor", "cuda"],
+                    help="prior engine of the fused kernel (auto: 3xTF32 tensor cores for F >= 32)")
     return ap.parse_args()
 
 
@@ -77,7 +79,7 @@ def config_dict(args, world):
         "workload": "config5: B=1024/GPU LJSpeech-shape length-bucketed, fused prior+MAS+durations"
                     if args.op == "fused" else
                     "config5: B=1024/GPU LJSpeech-shape length-bucketed, maximum_path(value, mask)",
-        "op": args.op, "batch_per_gpu": args.batch, "global_batch": args.batch * world,
+        "op": args.op, "engine": args.engine, "batch_per_gpu": args.batch, "global_batch": args.batch * world,
         "T_text": T_X, "T_mel": T_Y, "n_feats": N_FEATS, "ragged": True,
         "cells_definition": "B*T_text*T_mel (padded)",
         "l2_policy": "inputs+outputs per step (>= 1 GB) exceed the 126 MB L2; no explicit flush",
@@ -267,8 +269,11 @@ def run_ours(args):
     if args.op == "dropin" or not args.no_dropin:
         value = -(torch.rand(B, T_X, T_Y, device=dev) * 100 + 50)
 
+    eng_flags = {"auto": 0, "tensor": _lib.FLAG_FORCE_TENSOR, "cuda": _lib.FLAG_NO_TENSOR}[args.engine]
+    tensor_engine = args.engine == "tensor" or (args.engine == "auto" and N_FEATS >= 32)
+
     def step_fused():
-        path, dur = monotonic_align.maximum_path_from_prior(mu_x, None, y, t_x, t_y)
+        path, dur = monotonic_align.maximum_path_from_prior(mu_x, None, y, t_x, t_y, flags=eng_flags)
         if world > 1:
             gatherer.gather(dur)
         return path, dur
@@ -318,7 +323,7 @@ def run_ours(args):
     # ---- per-kernel time for the roofline: CUDA events around the kernel launch alone
     def kernel_only():
         if args.op == "fused":
-            monotonic_align.maximum_path_from_prior(mu_x, None, y, t_x, t_y)
+            monotonic_align.maximum_path_from_prior(mu_x, None, y, t_x, t_y, flags=eng_flags)
         else:
             monotonic_align.maximum_path_lengths(value, t_x, t_y, return_durations=True)
 
@@ -337,11 +342,25 @@ def run_ours(args):
     else:
         alg_bytes = 8 * cells   # read value fp32 once + write dense fp32 path once
     ach = alg_bytes / (k_ms * 1e-3) / 1e9
+    kname = ("mas_prior_tc_kernel" if tensor_engine else "mas_prior_kernel") if args.op == "fused" \
+        else "mas_fast_kernel"
+    # measured DRAM bytes per launch of this kernel on this workload (ncu --set full,
+    # dram__bytes_read.sum + dram__bytes_write.sum; profiles/r1_traffic.json names the capture)
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+            tj = json.load(f)
+        if B == B_PER_GPU:
+            traffic = tj.get(kname, {}).get("dram_bytes_per_launch")
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
-                "frac": ach / hbm_peak, "traffic": None, "peak_source": peak_src,
-                "kernel": "mas_prior_kernel" if args.op == "fused" else "mas_fast_kernel",
-                "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg_bytes}
-    if args.op == "fused":
+                "frac": ach / hbm_peak, "traffic": traffic, "peak_source": peak_src,
+                "kernel": kname, "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg_bytes}
+    if args.op == "fused" and tensor_engine:
+        roofline["engine"] = ("tcgen05.mma kind::tf32, 3xTF32 split (fp32-level accuracy), mu_x in TMEM; "
+                              "the CUDA-core engine (--engine cuda) is the fp32 FMA variant")
+    if args.op == "fused" and not tensor_engine:
         # the binding resource at F=80 is the fp32 FMA pipe, not HBM: report it too
         sm_mhz = (clk or {}).get("sm_mhz") or 1965.0
         fma_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
@@ -360,7 +379,9 @@ def run_ours(args):
         d_ach = 8 * cells / (d_ms * 1e-3) / 1e9
         drop = {"value": cells / (d_ms * 1e-3), "unit": UNIT, "ms_per_step": d_ms,
                 "roofline": {"bound": "hbm", "achieved": d_ach, "peak": hbm_peak, "unit": "GB/s",
-                             "frac": d_ach / hbm_peak, "traffic": None,
+                             "frac": d_ach / hbm_peak,
+                             "traffic": (tj.get("mas_fast_kernel", {}).get("dram_bytes_per_launch")
+                                         if traffic is not None else None),
                              "kernel": "mas_fast_kernel", "algorithmic_bytes_per_launch": 8 * cells}}
 
     # ---- e2e: pinned host buffers in, durations + score out, every step
@@ -386,7 +407,7 @@ def run_ours(args):
                 path, dur, score, moved[0] = monotonic_align.maximum_path_from_prior_host(
                     h_in[0], h_in[1], h_in[2], h_in[3], dev, chunk=args.e2e_chunk,
                     durations_host=h_dur, score_host=h_score,
-                    flags=_lib.FLAG_HOST_NO_TRIM if args.e2e_no_trim else 0)
+                    flags=(_lib.FLAG_HOST_NO_TRIM if args.e2e_no_trim else 0) | eng_flags)
                 if world > 1:
                     dist.all_gather_into_tensor(dur_all, dur)
             else:
