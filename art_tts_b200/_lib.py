@@ -37,7 +37,7 @@ EXPORTS = (
     "mas_launch_count",
     "mas_frame_index", "mas_duration_loss_f32", "mas_crop_f32", "mas_path_segment",
     "mas_align_workspace_bytes", "mas_align_gather_f32", "mas_align_gather_bwd_f32",
-    "mas_from_prior_host_f32",
+    "mas_from_prior_host_f32", "mas_set_sm_reserve",
 )
 
 _lib = None
@@ -102,6 +102,8 @@ def load() -> ctypes.CDLL:
     lib.mas_from_prior_host_f32.restype = ci
     lib.mas_from_prior_host_f32.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, ci, vp, vp, vp, vp, vp,
                                             ci, ci, ci, ci, vp, sz, ci, ci, vp, vp]
+    lib.mas_set_sm_reserve.restype = ci
+    lib.mas_set_sm_reserve.argtypes = [ci]
     if lib.mas_abi_version() != 1:
         raise MasError("libmas_sm100.so ABI version mismatch; rebuild it")
     _lib = lib

@@ -10,6 +10,18 @@
 namespace mas {
 
 static std::atomic<uint64_t> g_launches{0};
+static std::atomic<int> g_sm_reserve{-1};
+int sm_reserve()
+{
+    int v = g_sm_reserve.load(std::memory_order_relaxed);
+    if (v < 0) {
+        const char *e = std::getenv("MAS_RESERVE_SMS");
+        v = (e && *e) ? std::atoi(e) : 0;
+        if (v < 0) v = 0;
+        g_sm_reserve.store(v, std::memory_order_relaxed);
+    }
+    return v;
+}
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 
 int element_size(int dtype)
@@ -118,6 +130,13 @@ const char *mas_strerror(int code)
 }
 
 uint64_t mas_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int mas_set_sm_reserve(int n_sms)
+{
+    if (n_sms < 0 || n_sms > 1024) return MAS_ERR_SHAPE;
+    g_sm_reserve.store(n_sms, std::memory_order_relaxed);
+    return MAS_OK;
+}
 
 size_t mas_workspace_bytes(int B, int T_x, int T_y)
 {

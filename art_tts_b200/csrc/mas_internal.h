@@ -131,6 +131,7 @@ TcLayout tc_layout(int F, int T_x, int T_y);
 cudaError_t launch_from_prior_tc(const PriorTcArgs &a, cudaStream_t st);
 
 int sm_count();
+int sm_reserve();   // SMs the persistent kernels leave free (mas_set_sm_reserve)
 void count_launch(int n = 1);
 
 }  // namespace mas

@@ -628,7 +628,7 @@ cudaError_t launch_from_prior(const PriorArgs &a, cudaStream_t st)
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kPriorThreads, a.lay.total) != cudaSuccess ||
         per_sm < 1)
         per_sm = 1;
-    const int grid = std::min(a.B, sm_count() * per_sm);
+    const int grid = std::min(a.B, std::max(1, sm_count() - sm_reserve()) * per_sm);
     k<<<grid, kPriorThreads, a.lay.total, st>>>(a);
     count_launch();
     return cudaGetLastError();

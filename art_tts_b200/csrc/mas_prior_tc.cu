@@ -711,7 +711,9 @@ cudaError_t launch_from_prior_tc(const PriorTcArgs &a, cudaStream_t st)
         e = cudaMemsetAsync(a.lp_out, 0, (size_t)a.B * a.T_x * a.T_y * sizeof(float), st);
         if (e != cudaSuccess) return e;
     }
-    const int grid = std::min(a.B, sm_count());
+    // persistent: one CTA per SM; `sm_limit` (mas_set_sm_limit) leaves SMs free for a concurrent kernel,
+    // e.g. the NCCL all-gather of the previous step's durations
+    const int grid = std::min(a.B, std::max(1, sm_count() - sm_reserve()));
     k<<<grid, kTcThreads, a.lay.total, st>>>(a);
     count_launch();
     return cudaGetLastError();

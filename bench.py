@@ -58,6 +58,11 @@ def parse():
     ap.add_argument("--no-dropin", action="store_true")
     ap.add_argument("--e2e-chunk", type=int, default=0, help="utterances per H2D chunk (0 = library default)")
     ap.add_argument("--e2e-no-trim", action="store_true", help="copy whole padded rows")
+    ap.add_argument("--gather", default="overlap", choices=["overlap", "serial"],
+                    help="N>1: all-gather of step i on a side stream under the kernel of step i+1, or in line")
+    ap.add_argument("--reserve-sms", type=int, default=-1,
+                    help="SMs the persistent kernel leaves to the overlapped collective (default 0: measured "
+                         "at N=8, reserving 8 SMs costs 8%% and the gather overlaps anyway)")
     ap.add_argument("--engine", default="auto", choices=["auto", "tensor", "cuda"],
                     help="prior engine of the fused kernel (auto: 3xTF32 tensor cores for F >= 32)")
     return ap.parse_args()
@@ -83,7 +88,7 @@ def config_dict(args, world):
         "T_text": T_X, "T_mel": T_Y, "n_feats": N_FEATS, "ragged": True,
         "cells_definition": "B*T_text*T_mel (padded)",
         "l2_policy": "inputs+outputs per step (>= 1 GB) exceed the 126 MB L2; no explicit flush",
-        "collective": "all_gather(durations int32 [B,T_text])" if world > 1 else "none",
+        "collective": (f"all_gather(durations int32 [B,T_text]), {args.gather}" if world > 1 else "none"),
     }
 
 
@@ -261,9 +266,13 @@ def run_ours(args):
     y = torch.randn(B, N_FEATS, T_Y, device=dev) * ym[:, None, :]
     dur_all = torch.empty(world * B, T_X, dtype=torch.int32, device=dev) if world > 1 else None
     gatherer = None
-    if world > 1:
+    reserve = 0
+    if world > 1 and args.gather == "overlap":
         from art_tts_b200.distributed import DurationGatherer
         gatherer = DurationGatherer(B, T_X, dev)   # gather of step i overlaps the kernel of step i+1
+        # the fused kernel is persistent (one CTA per SM): leave a few SMs to the collective's CTAs
+        reserve = 0 if args.reserve_sms < 0 else args.reserve_sms
+        _lib.check(_lib.load().mas_set_sm_reserve(reserve), "mas_set_sm_reserve")
 
     value = None
     if args.op == "dropin" or not args.no_dropin:
@@ -274,17 +283,26 @@ def run_ours(args):
 
     def step_fused():
         path, dur = monotonic_align.maximum_path_from_prior(mu_x, None, y, t_x, t_y, flags=eng_flags)
-        if world > 1:
+        if gatherer is not None:
             gatherer.gather(dur)
+        elif world > 1:
+            dist.all_gather_into_tensor(dur_all, dur)
         return path, dur
 
     def step_dropin():
         path, dur = monotonic_align.maximum_path_lengths(value, t_x, t_y, return_durations=True)
-        if world > 1:
+        if gatherer is not None:
             gatherer.gather(dur)
+        elif world > 1:
+            dist.all_gather_into_tensor(dur_all, dur)
         return path, dur
 
     step = step_fused if args.op == "fused" else step_dropin
+    if world > 1:   # bring up every NCCL channel/connection before anything is timed
+        for _ in range(8):
+            dist.all_gather_into_tensor(dur_all, dur_all[:B])
+        torch.cuda.synchronize()
+        dist.barrier()
 
     def barrier():
         torch.cuda.synchronize()

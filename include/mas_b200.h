@@ -248,6 +248,14 @@ int mas_align_gather_bwd_f32(const float *grad_mu_y, const float *y_seg, const f
  */
 int mas_plan(int B, int T_x, int T_y, int flags);
 
+/*
+ * The fused kernels are PERSISTENT (one CTA per SM for the whole batch).  A kernel that should run
+ * concurrently -- the NCCL all-gather of the previous step's durations in data-parallel training
+ *  -- finds no free SM until they finish.  n_sms > 0 makes them leave that many SMs
+ * idle (default 0, or the MAS_RESERVE_SMS environment variable).  Process-wide setting.
+ */
+int mas_set_sm_reserve(int n_sms);
+
 /* Kernel launches enqueued by this library in this process (bench.py's gpu_launches). */
 uint64_t mas_launch_count(void);
 
