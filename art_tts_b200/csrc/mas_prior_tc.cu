@@ -32,6 +32,7 @@
 //              tf32 hi/lo split in place, -0.5|y|^2 per frame, bulk zero-fill of the path)
 //   warp 7     backtrack warp (unchanged: one utterance behind, second direction-bit buffer)
 #include <algorithm>
+#include <type_traits>
 
 #include "mas_dp.cuh"
 #include "mas_internal.h"
@@ -197,7 +198,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mas_prior_tc_kernel(const Prior
     uint64_t *ring_full = bars, *ring_empty = bars + 4;
     uint64_t *slab_full = bars + 8, *slab_free = bars + 12;
     uint64_t *d_full = bars + 16, *d_empty = bars + 20;
-    uint64_t *a_ready = bars + 24, *a_free = bars + 25;
+    uint64_t *a_ready = bars + 24, *a_free = bars + 30;   // [2] each: one pair per 128-token M tile
     volatile int *ctrl = reinterpret_cast<volatile int *>(bars + 32);   // [0] zdone [1] fwd_done [2] bt_done
     uint32_t *tslot = reinterpret_cast<uint32_t *>(bars + 40);
     uint64_t *edge_full = bars + 26;                            // [4] DP warp 0 -> DP warp 1, per tile
@@ -224,8 +225,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) mas_prior_tc_kernel(const Prior
             mbar_init(&d_full[s], 1);
             mbar_init(&d_empty[s], 4);
         }
-        mbar_init(a_ready, 4);
-        mbar_init(a_free, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&a_ready[i], 4);
+            mbar_init(&a_free[i], 1);
+        }
         ctrl[0] = 0;
         ctrl[1] = 0;
         ctrl[2] = 0;
@@ -244,7 +247,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mas_prior_tc_kernel(const Prior
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tbase = *tslot;
+    const uint32_t tbase = __shfl_sync(kFull, *tslot, 0);
 
     auto geometry = [&](int u, int &tx, int &ty, int &ntiles, bool &degenerate) {
         tx = min(max(a.t_x[u], 0), T_x);
@@ -478,10 +481,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) mas_prior_tc_kernel(const Prior
                 bool degenerate;
                 geometry(u, tx, ty, ntiles, degenerate);
                 if (ntiles == 0) continue;
-                m_a.begin();
-                mbar_wait(a_ready, ka & 1);   // mu_x of this utterance is in TMEM
-                m_a.end();
-                tc_fence_after();
+                // A operand readiness / release is tracked per M tile: the first ~4 tiles of an utterance
+                // only touch tokens < 128, and its last tiles only tokens >= 128, so the movers can
+                // refill one half of TMEM while the other is still (or already) being multiplied
+                bool a_ok[2] = {false, false}, a_rel[2] = {false, false};
+                // last tile whose band still reaches into M tile 0 (tokens < 128)
+                const int t0_last = a.lp_out ? ntiles - 1 : min(ntiles - 1, (127 - tx + ty) >> 5);   // tap: every tile
                 for (int t = 0; t < ntiles;) {
                     // a pair of tiles (g, g+1): up to four independent accumulators in flight
                     // (accumulator c = 2*e + i: tile e of the pair, M tile i); everything the issue
@@ -507,28 +512,57 @@ __global__ void __launch_bounds__(kTcThreads, 1) mas_prior_tc_kernel(const Prior
                         dcol[2 * e] = tbase + L.col_d + (b * 2) * 32;
                         dcol[2 * e + 1] = dcol[2 * e] + 32;
                     }
+#pragma unroll
+                    for (int i = 0; i < 2; ++i)
+                        if (!a_ok[i] && ((am >> i) & 1 || (am >> (i + 2)) & 1)) {
+                            m_a.begin();
+                            mbar_wait(&a_ready[i], ka & 1);   // this half of mu_x is in TMEM
+                            m_a.end();
+                            a_ok[i] = true;
+                        }
                     tc_fence_after();
                     m_i.begin();
+                    // Everything the issue loop uses is re-derived from lane 0's copy: the compiler then
+                    // knows these values are warp-uniform and keeps them (and the loop arithmetic on them)
+                    // in uniform registers -- otherwise every operand of every MMA goes through an R2UR.
+#pragma unroll
+                    for (int c4 = 0; c4 < 4; ++c4) dcol[c4] = __shfl_sync(kFull, dcol[c4], 0);
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        bh[e] = __shfl_sync(kFull, bh[e], 0);
+                        bl[e] = __shfl_sync(kFull, bl[e], 0);
+                    }
+                    am = __shfl_sync(kFull, am, 0);
                     const uint32_t ahi0 = tbase + L.col_ahi, alo0 = tbase + L.col_alo;
                     // small terms first: a_lo*b_hi + a_hi*b_lo, then a_hi*b_hi.  One k step = 8 features
                     // = 8 TMEM columns of A = 1 KB of B (64 descriptor address units).
-                    for (int pass = 0; pass < 3; ++pass) {
-                        const uint32_t abase = (pass == 0) ? alo0 : ahi0;
-                        const uint64_t b0 = (pass == 1) ? bl[0] : bh[0], b1 = (pass == 1) ? bl[1] : bh[1];
-                        for (int j = 0; j < ksteps; ++j) {
-                            const uint32_t acc = (pass | j) != 0;
-                            const uint32_t ac = abase + 8 * j;
-                            const uint32_t bo = (uint32_t)(64 * j);
-                            const uint64_t d0 = b0 + bo, d1 = b1 + bo;
-                            if (elect_one()) {
+                    auto issue_all = [&](auto ks_tag) {
+                        constexpr int KS = decltype(ks_tag)::value;   // 0 = run-time k-step count (rolled loop)
+                        const int nk = KS ? KS : ksteps;
+#pragma unroll
+                        for (int pass = 0; pass < 3; ++pass) {
+                            const uint32_t abase = (pass == 0) ? alo0 : ahi0;
+                            const uint64_t b0 = (pass == 1) ? bl[0] : bh[0], b1 = (pass == 1) ? bl[1] : bh[1];
+#pragma unroll
+                            for (int j = 0; j < nk; ++j) {
+                                const uint32_t acc = (pass | j) != 0;
+                                const uint32_t ac = abase + 8 * j;
+                                const uint32_t bo = (uint32_t)(64 * j);
+                                const uint64_t d0 = b0 + bo, d1 = b1 + bo;
                                 if (am & 1) tc_mma_ts(dcol[0], ac, d0, idesc, acc);
                                 if (am & 2) tc_mma_ts(dcol[1], ac + Fp, d0, idesc, acc);
                                 if (am & 4) tc_mma_ts(dcol[2], ac, d1, idesc, acc);
                                 if (am & 8) tc_mma_ts(dcol[3], ac + Fp, d1, idesc, acc);
                             }
-                            __syncwarp();
                         }
+                    };
+                    // one elected lane issues the whole pair; with the k-step count known at compile time
+                    // the loop unrolls and the operands of all 120 MMAs are immediates off a few registers
+                    if (elect_one()) {
+                        if (ksteps == 10) issue_all(std::integral_constant<int, 10>{});
+                        else issue_all(std::integral_constant<int, 0>{});
                     }
+                    __syncwarp();
                     if (elect_one()) {
                         for (int e = 0; e < np; ++e) {
                             tc_commit(&slab_free[(g + e) % kTcSlabs]);   // slab reusable once these MMAs have read it
@@ -539,9 +573,22 @@ __global__ void __launch_bounds__(kTcThreads, 1) mas_prior_tc_kernel(const Prior
                     m_i.end();
                     t += np;
                     g += np;
+                    if (!a_rel[0] && t > t0_last) {   // no later tile touches tokens < 128
+                        if (!a_ok[0]) mbar_wait(&a_ready[0], ka & 1);
+                        if (elect_one()) tc_commit(&a_free[0]);
+                        __syncwarp();
+                        a_rel[0] = a_ok[0] = true;
+                    }
                 }
-                if (elect_one()) tc_commit(a_free);   // mu_x in TMEM no longer needed
-                __syncwarp();
+                // every barrier sees every utterance, used or not
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    if (!a_ok[i]) mbar_wait(&a_ready[i], ka & 1);
+                    if (!a_rel[i]) {
+                        if (elect_one()) tc_commit(&a_free[i]);
+                        __syncwarp();
+                    }
+                }
                 ++ka;
             }
             m_all.end();
@@ -563,8 +610,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) mas_prior_tc_kernel(const Prior
             const int mt = (tx + 127) >> 7;
             const float *mub = a.mu_x + (int64_t)u * F * T_x;
             float *msq = musq + (ka % kTcMsq) * 256;
-            for (int i = 0; i < mt; ++i) {
-                const bool any = 128 * i + 32 * q < tx;   // some of this warp's tokens exist
+            for (int i = 0; i < 2; ++i) {
+                const bool any = i < mt && 128 * i + 32 * q < tx;   // some of this warp's tokens exist
                 const int x = 128 * i + 32 * q + lane;
                 const bool xv = x < tx;
                 // every feature of "my" token into registers: all loads in flight at once, issued
@@ -578,7 +625,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mas_prior_tc_kernel(const Prior
                 }
                 a_ld.end();
                 a_w.begin();
-                if (i == 0 && ka > 0) mbar_wait_relaxed(a_free, (ka - 1) & 1, 128);  // previous utterance's MMAs have read A
+                if (ka > 0) mbar_wait_relaxed(&a_free[i], (ka - 1) & 1, 128);  // previous utterance's MMAs have read this half
                 a_w.end();
                 tc_fence_after();
                 a_st.begin();
@@ -601,12 +648,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) mas_prior_tc_kernel(const Prior
                     }
                     msq[x] = -0.5f * s;   // tts.py:494  mu_square
                 }
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&a_ready[i]);
                 a_st.end();
             }
-            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(a_ready);
             ++ka;
         }
         a_all.end();

@@ -114,6 +114,7 @@ __global__ void __launch_bounds__(192) tc_test(const float *mu, const float *y, 
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)));
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar + 1)));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar + 2)));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -325,6 +326,62 @@ __global__ void __launch_bounds__(192) tc_test(const float *mu, const float *y, 
             if (lane == 0) cyc[slot++] = (clock64() - t0) / 4;
         }
     }
+    // ---- accumulator placement: four 32-column accumulators, M=128 N=32, different column offsets / issue orders
+    if (warp == 4) {
+        int slot = 28;
+        uint32_t ph = 0;
+        const uint32_t id = (1u << 4) | (2u << 7) | (2u << 10) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
+        const uint32_t offs[4][4] = {{0, 32, 64, 96}, {0, 64, 32, 96}, {0, 64, 128, 192}, {0, 128, 32, 160}};
+        for (int v = 0; v < 4; ++v) {
+            const long long t0 = clock64();
+            for (int r = 0; r < 100; ++r)
+                for (int j = 0; j < 10; ++j) {
+                    const uint64_t bd = make_desc(smem_u32(A_lo) + 3 * 16384 + j * 1024, 16, 256, 6);
+                    uint32_t pred;
+                    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+                    if (pred) {
+                        mma_ts(tbase + offs[v][0], tbase + 256 + 8 * j, bd, id, 1);
+                        mma_ts(tbase + offs[v][1], tbase + 336 + 8 * j, bd, id, 1);
+                        mma_ts(tbase + offs[v][2], tbase + 256 + 8 * j, bd, id, 1);
+                        mma_ts(tbase + offs[v][3], tbase + 336 + 8 * j, bd, id, 1);
+                    }
+                    __syncwarp();
+                }
+            if (lane == 0) commit(bar + 2);
+            mbar_wait(bar + 2, ph);
+            ph ^= 1;
+            if (lane == 0) cyc[slot++] = (clock64() - t0) / 4;
+        }
+    }
+    __syncwarp();
+    // ---- cost model: uniform issue, TS, K-major SWIZZLE_32B B, 4 accumulators; M in {64,128} x N in {32,64}
+    if (warp == 4) {
+        int slot = 24;
+        uint32_t ph = 0;
+        for (int mm = 0; mm < 2; ++mm)
+            for (int nn = 0; nn < 2; ++nn) {
+                const uint32_t Mv = mm ? 128u : 64u, Nv = nn ? 64u : 32u;
+                const uint32_t id = (1u << 4) | (2u << 7) | (2u << 10) | ((Nv >> 3) << 17) | ((Mv >> 4) << 24);
+                const long long t0 = clock64();
+                for (int r = 0; r < 100; ++r)
+                    for (int j = 0; j < 10; ++j) {
+                        const uint64_t bd = make_desc(smem_u32(A_lo) + 3 * 16384 + j * 1024, 16, 256, 6);
+                        uint32_t pred;
+                        asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+                        if (pred) {
+                            mma_ts(tbase + 0, tbase + 256 + 8 * j, bd, id, 1);
+                            mma_ts(tbase + 64, tbase + 336 + 8 * j, bd, id, 1);
+                            mma_ts(tbase + 128, tbase + 256 + 8 * j, bd, id, 1);
+                            mma_ts(tbase + 192, tbase + 336 + 8 * j, bd, id, 1);
+                        }
+                        __syncwarp();
+                    }
+                if (lane == 0) commit(bar);
+                ph ^= 1;
+                mbar_wait(bar, ph);
+                if (lane == 0) cyc[slot++] = (clock64() - t0) / 4;
+            }
+    }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tbase), "r"(512));
@@ -397,6 +454,10 @@ int main()
     for (int mode = 0; mode < 2; ++mode)
         for (int i = 0; i < 2; ++i)
             printf("K-major B: %s N=32, %d independent accumulators: %.1f cyc/MMA\n", mode ? "SS" : "TS", i ? 4 : 1, (double)cyc[17 + mode * 2 + i] / 1000.0);
+    const char *pl[4] = {"cols 0,32,64,96", "cols 0,64,32,96", "cols 0,64,128,192", "cols 0,128,32,160"};
+    for (int i = 0; i < 4; ++i) printf("placement %s: %.1f cyc/MMA\n", pl[i], (double)cyc[28 + i] / 1000.0);
+    for (int i = 0; i < 4; ++i)
+        printf("cost model: TS, SWIZZLE_32B, 4 accumulators, M=%d N=%d: %.1f cyc/MMA\n", (i >> 1) ? 128 : 64, (i & 1) ? 64 : 32, (double)cyc[24 + i] / 1000.0);
     const char *ln[3] = {"SWIZZLE_128B", "SWIZZLE_32B", "no swizzle"};
     for (int i = 0; i < 3; ++i)
         printf("uniform issue, TS, K-major B %s, 4 accumulators: %.1f cyc/MMA\n", ln[i], (double)cyc[21 + i] / 1000.0);
