@@ -88,7 +88,7 @@ def load() -> ctypes.CDLL:
     lib.mas_frame_index.restype = ci
     lib.mas_frame_index.argtypes = [vp, vp, vp, vp, ci, ci, ci, vp]
     lib.mas_duration_loss_f32.restype = ci
-    lib.mas_duration_loss_f32.argtypes = [vp, vp, vp, vp, vp, vp, ci, ci, vp]
+    lib.mas_duration_loss_f32.argtypes = [vp, vp, vp, vp, vp, vp, ci, ci, vp, sz, vp]
     lib.mas_crop_f32.restype = ci
     lib.mas_crop_f32.argtypes = [vp, vp, vp, vp, ci, ci, ci, ci, vp]
     lib.mas_path_segment.restype = ci

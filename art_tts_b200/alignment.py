@@ -68,10 +68,12 @@ def _duration_loss_call(logw, durations, x_lengths, want_target, want_grad, want
     target = torch.empty((B, T_x), dtype=torch.float32, device=dev) if want_target else None
     grad = torch.empty((B, T_x), dtype=torch.float32, device=dev) if want_grad else None
     loss = torch.empty((1,), dtype=torch.float32, device=dev) if want_loss else None
+    lib = _lib.load()
     with torch.cuda.device(dev):
-        code = _lib.load().mas_duration_loss_f32(_lib.ptr(logw), _lib.ptr(d), _lib.ptr(tx),
-                                                 _lib.ptr(target), _lib.ptr(grad), _lib.ptr(loss), B,
-                                                 T_x, _lib.stream_ptr(dev))
+        ws = _lib.workspace(dev, int(lib.mas_align_workspace_bytes(max(B, 1), 1, 1))) if want_loss else None
+        code = lib.mas_duration_loss_f32(_lib.ptr(logw), _lib.ptr(d), _lib.ptr(tx), _lib.ptr(target),
+                                         _lib.ptr(grad), _lib.ptr(loss), B, T_x, _lib.ptr(ws),
+                                         ws.numel() if ws is not None else 0, _lib.stream_ptr(dev))
     _lib.check(code, "mas_duration_loss_f32")
     return target, grad, loss
 

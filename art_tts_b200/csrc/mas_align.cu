@@ -15,6 +15,8 @@
 // All of this is HBM-bound elementwise / gather work: coalesced along the frame axis, one
 // pass over the data, deterministic two-stage reductions (no atomics), fp32 arithmetic in the
 // reference's operation order.
+#include <algorithm>
+
 #include "mas_common.cuh"
 #include "mas_internal.h"
 
@@ -102,27 +104,29 @@ __global__ void __launch_bounds__(256) frame_index_kernel(const int32_t *__restr
 
 // ------------------------------------------------------------------------------------
 // duration targets and loss: logw_ = log(1e-8 + dur) * x_mask; sum((logw - logw_)^2) / sum(len)
-// One block; B*T_x is a few hundred thousand elements at most.
+// Grid-stride over B*T_x elements, per-block partial sums (fp64) -> one finalize block: deterministic.
 // ------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) duration_loss_kernel(const float *__restrict__ logw,
-                                                             const int32_t *__restrict__ dur,
-                                                             const int32_t *__restrict__ t_x,
-                                                             float *__restrict__ logw_target,
-                                                             float *__restrict__ grad_unit,
-                                                             float *__restrict__ loss, int B, int T_x)
+constexpr int kDurBlocks = 148, kDurThreads = 256;
+
+__global__ void __launch_bounds__(kDurThreads) duration_loss_kernel(const float *__restrict__ logw,
+                                                                    const int32_t *__restrict__ dur,
+                                                                    const int32_t *__restrict__ t_x,
+                                                                    float *__restrict__ logw_target,
+                                                                    float *__restrict__ grad_unit,
+                                                                    double *__restrict__ partials, int B, int T_x)
 {
-    __shared__ double red[32];
+    __shared__ double red[kDurThreads / 32];
+    __shared__ float s_den;
     const int tid = threadIdx.x;
-    double lsum = 0.0;
-    for (int b = tid; b < B; b += 1024) lsum += (double)min(max(t_x[b], 0), T_x);
+    double lsum = 0.0;   // every block recomputes sum(x_lengths): B integers
+    for (int b = tid; b < B; b += kDurThreads) lsum += (double)min(max(t_x[b], 0), T_x);
     const double total_len = block_sum_f64(lsum, red);
-    __shared__ float s_inv;
-    if (tid == 0) s_inv = (float)total_len;  // torch.sum(lengths) used as an fp32 divisor
+    if (tid == 0) s_den = (float)total_len;  // torch.sum(lengths) used as an fp32 divisor
     __syncthreads();
-    const float denom = s_inv;
+    const float denom = s_den;
     double acc = 0.0;
     const int64_t n = (int64_t)B * T_x;
-    for (int64_t i = tid; i < n; i += 1024) {
+    for (int64_t i = (int64_t)blockIdx.x * kDurThreads + tid; i < n; i += (int64_t)gridDim.x * kDurThreads) {
         const int b = (int)(i / T_x), x = (int)(i - (int64_t)b * T_x);
         const float m = (x < t_x[b]) ? 1.0f : 0.0f;
         const float target = logf(1e-8f + (float)dur[i]) * m;  // tts.py:503-505
@@ -135,7 +139,19 @@ __global__ void __launch_bounds__(1024) duration_loss_kernel(const float *__rest
         if (grad_unit) grad_unit[i] = (2.0f * d) / denom;
     }
     const double s = block_sum_f64(acc, red);
-    if (tid == 0 && loss) loss[0] = (float)s / denom;
+    if (tid == 0 && partials) {
+        partials[blockIdx.x] = s;
+        if (blockIdx.x == 0) partials[gridDim.x] = (double)denom;
+    }
+}
+
+__global__ void __launch_bounds__(32) duration_loss_finalize_kernel(const double *__restrict__ partials, int n,
+                                                                    float *__restrict__ loss)
+{
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n; i += 32) s += partials[i];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(kFull, s, o);
+    if (threadIdx.x == 0) loss[0] = (float)s / (float)partials[n];
 }
 
 // ------------------------------------------------------------------------------------
@@ -252,7 +268,9 @@ __global__ void __launch_bounds__(256) prior_loss_finalize_kernel(const float *_
 // backward of the gather (+ of prior_loss): the frames of a token are contiguous, so
 //   grad_mu_x[b,f,x] = sum_{j in seg(x)} ( g_mu_y[b,f,j] + c * (mu_x[b,f,x] - y_seg[b,f,j]) )
 // with c = g_loss / (sum(y_mask) * F) is a plain segmented sum: no atomics, deterministic.
-// grid (ceil(F/fchunk), B).  Requires a non-decreasing frame index (what MAS produces).
+// grid (ceil(F/fchunk), B).  Each feature row of the gradient is read ONCE, coalesced, into shared
+// memory (already combined: g - c*y); the token threads then add up their runs from there and
+// write grad_mu_x coalesced along x.  Requires a non-decreasing frame index (what MAS produces).
 // ------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kAlignThreads) align_gather_bwd_kernel(
     const float *__restrict__ g_mu_y, const float *__restrict__ y_seg, const float *__restrict__ mu_x,
@@ -264,6 +282,7 @@ __global__ void __launch_bounds__(kAlignThreads) align_gather_bwd_kernel(
     extern __shared__ __align__(16) unsigned char smem[];
     int *s_start = reinterpret_cast<int *>(smem);  // [T_x] first output column of the token, -1 = none
     int *s_end = s_start + T_x;                    // [T_x] one past its last column
+    float *rowbuf = reinterpret_cast<float *>(s_end + T_x);   // [2][T_out] combined gradient rows
     const int b = blockIdx.y, tid = threadIdx.x;
     int off, len;
     segment_of(offset, seg_len, b, T_y, T_out, off, len);
@@ -282,25 +301,33 @@ __global__ void __launch_bounds__(kAlignThreads) align_gather_bwd_kernel(
         }
         if (j == len - 1 && x >= 0 && x < T_x) s_end[x] = len;
     }
-    __syncthreads();
     const bool with_loss = (y_seg != nullptr) && (g_loss != nullptr);
     const float c = with_loss ? g_loss[0] / loss_norm[0] : 0.0f;
     const int f0 = blockIdx.x * fchunk, f1 = min(F, f0 + fchunk);
+    auto load_row = [&](int f, float *dst) {
+        const int64_t row = (int64_t)b * F + f;
+        for (int j = tid; j < len; j += kAlignThreads) {
+            float t = g_mu_y ? __ldg(g_mu_y + row * T_out + j) : 0.0f;
+            if (with_loss) t -= c * __ldg(y_seg + row * T_out + j);
+            dst[j] = t;
+        }
+    };
+    if (f0 < f1) load_row(f0, rowbuf);
+    __syncthreads();
     for (int f = f0; f < f1; ++f) {
+        float *cur = rowbuf + ((f - f0) & 1) * T_out, *nxt = rowbuf + (((f - f0) & 1) ^ 1) * T_out;
+        if (f + 1 < f1) load_row(f + 1, nxt);          // next row in flight while this one is reduced
         const int64_t row = (int64_t)b * F + f;
         for (int x = tid; x < T_x; x += kAlignThreads) {
             const int s = s_start[x], e = s_end[x];
             float sum = 0.0f;
             if (s >= 0) {
-                const float m = with_loss ? __ldg(mu_x + row * T_x + x) : 0.0f;
-                for (int j = s; j < e; ++j) {
-                    float t = g_mu_y ? __ldg(g_mu_y + row * T_out + j) : 0.0f;
-                    if (with_loss) t += c * (m - __ldg(y_seg + row * T_out + j));
-                    sum += t;
-                }
+                for (int j = s; j < e; ++j) sum += cur[j];
+                if (with_loss) sum += c * __ldg(mu_x + row * T_x + x) * (float)(e - s);
             }
             g_mu_x[row * T_x + x] = sum;
         }
+        __syncthreads();
     }
 }
 
@@ -330,12 +357,21 @@ cudaError_t launch_frame_index(const int32_t *dur, const int32_t *t_x, const int
     return cudaGetLastError();
 }
 
+size_t duration_loss_scratch_bytes() { return (size_t)(kDurBlocks + 1) * sizeof(double); }
+
 cudaError_t launch_duration_loss(const float *logw, const int32_t *dur, const int32_t *t_x,
-                                 float *logw_target, float *grad_unit, float *loss, int B, int T_x,
-                                 cudaStream_t st)
+                                 float *logw_target, float *grad_unit, float *loss, double *partials,
+                                 int B, int T_x, cudaStream_t st)
 {
-    duration_loss_kernel<<<1, 1024, 0, st>>>(logw, dur, t_x, logw_target, grad_unit, loss, B, T_x);
+    const int64_t n = (int64_t)B * T_x;
+    const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(kDurBlocks, (n + kDurThreads - 1) / kDurThreads));
+    duration_loss_kernel<<<blocks, kDurThreads, 0, st>>>(logw, dur, t_x, logw_target, grad_unit,
+                                                         loss ? partials : nullptr, B, T_x);
     count_launch();
+    if (loss) {
+        duration_loss_finalize_kernel<<<1, 32, 0, st>>>(partials, blocks, loss);
+        count_launch();
+    }
     return cudaGetLastError();
 }
 
@@ -396,7 +432,7 @@ cudaError_t launch_align_gather_bwd(const float *g_mu_y, const float *y_seg, con
                                     const int32_t *seg_len, float *g_mu_x, int B, int F, int T_x,
                                     int T_y, int T_out, cudaStream_t st)
 {
-    const size_t smem = (size_t)T_x * 2 * sizeof(int);
+    const size_t smem = (size_t)T_x * 2 * sizeof(int) + (size_t)T_out * 2 * sizeof(float);
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(align_gather_bwd_kernel,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

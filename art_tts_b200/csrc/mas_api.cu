@@ -1,6 +1,7 @@
 // mas_api.cu -- the C ABI of libmas_sm100.so (see include/mas_b200.h for the contract and the
 // reference interfaces each entry point replaces).  Host-side only: argument validation,
 // plan selection, launches.  No allocation, no host synchronisation, no CPU fallback.
+#include <algorithm>
 #include <atomic>
 #include <cstdlib>
 #include <initializer_list>
@@ -389,14 +390,18 @@ int mas_frame_index(const int32_t *durations, const int32_t *t_x, const int32_t 
 
 int mas_duration_loss_f32(const float *logw, const int32_t *durations, const int32_t *t_x,
                           float *logw_target, float *grad_unit, float *loss, int B, int T_x,
-                          void *stream)
+                          void *workspace, size_t workspace_bytes, void *stream)
 {
     if (!durations || !t_x) return MAS_ERR_NULL;
     if (!logw_target && !grad_unit && !loss) return MAS_ERR_NULL;
     if ((loss || grad_unit) && !logw) return MAS_ERR_NULL;
     if (B < 0 || T_x < 1) return MAS_ERR_SHAPE;
     if (misaligned4({logw, durations, t_x, logw_target, grad_unit, loss})) return MAS_ERR_ALIGN;
-    return (int)launch_duration_loss(logw, durations, t_x, logw_target, grad_unit, loss, B, T_x,
+    if (loss && (!workspace || workspace_bytes < duration_loss_scratch_bytes())) return MAS_ERR_WORKSPACE;
+    if ((uintptr_t)workspace % 8) return MAS_ERR_ALIGN;
+    if (B == 0) return MAS_OK;
+    return (int)launch_duration_loss(logw, durations, t_x, logw_target, grad_unit, loss,
+                                     static_cast<double *>(workspace), B, T_x,
                                      static_cast<cudaStream_t>(stream));
 }
 
@@ -432,8 +437,8 @@ int mas_path_segment(const int32_t *frame_idx, const int32_t *offset, const int3
 
 size_t mas_align_workspace_bytes(int B, int F, int T_out)
 {
-    if (B < 1 || F < 1 || T_out < 1) return 256;
-    return align_partials(B, F, T_out) * sizeof(float) + 256;
+    if (B < 1 || F < 1 || T_out < 1) return 2048;
+    return std::max(align_partials(B, F, T_out) * sizeof(float), duration_loss_scratch_bytes()) + 256;
 }
 
 int mas_align_gather_f32(const float *mu_x, const int32_t *frame_idx, const int32_t *offset,
@@ -462,7 +467,8 @@ int mas_align_gather_bwd_f32(const float *grad_mu_y, const float *y_seg, const f
                              void *stream)
 {
     if (!frame_idx || !grad_mu_x) return MAS_ERR_NULL;
-    if (!segment_shape_ok(B, F, T_y, T_out) || T_x < 1 || (size_t)T_x * 8 > (size_t)kSmemBudget)
+    if (!segment_shape_ok(B, F, T_y, T_out) || T_x < 1 ||
+        (size_t)T_x * 8 + (size_t)T_out * 8 > (size_t)kSmemBudget)
         return MAS_ERR_SHAPE;
     if (misaligned4({grad_mu_y, y_seg, mu_x, grad_loss, loss_norm, frame_idx, offset, seg_len,
                      grad_mu_x}))

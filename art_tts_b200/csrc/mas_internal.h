@@ -83,9 +83,10 @@ cudaError_t launch_log_prior(const float *mu_x, const float *y, float *lp, int B
 // mas_align.cu: consumers of the alignment (durations / frame index)
 cudaError_t launch_frame_index(const int32_t *dur, const int32_t *t_x, const int32_t *t_y,
                                int32_t *fidx, int B, int T_x, int T_y, cudaStream_t st);
+size_t duration_loss_scratch_bytes();
 cudaError_t launch_duration_loss(const float *logw, const int32_t *dur, const int32_t *t_x,
-                                 float *logw_target, float *grad_unit, float *loss, int B, int T_x,
-                                 cudaStream_t st);
+                                 float *logw_target, float *grad_unit, float *loss, double *partials,
+                                 int B, int T_x, cudaStream_t st);
 cudaError_t launch_crop_rows(const float *src, const int32_t *offset, const int32_t *seg_len,
                              float *dst, int B, int R, int T_y, int T_out, cudaStream_t st);
 cudaError_t launch_path_segment(const int32_t *fidx, const int32_t *offset, const int32_t *seg_len,

@@ -193,11 +193,12 @@ int mas_frame_index(const int32_t *durations, const int32_t *t_x, const int32_t 
  *   logw         NULL or [B,T_x] fp32 (the duration predictor's output)
  *   logw_target  NULL or [B,T_x] fp32: receives logw_
  *   grad_unit    NULL or [B,T_x] fp32: d loss / d logw = 2 (logw - logw_) / sum(x_lengths)
- *   loss         NULL or [1] fp32
+ *   loss         NULL or [1] fp32; needs `workspace` of >= mas_align_workspace_bytes(B, 1, 1)
+ *                bytes (8-byte aligned): per-block partial sums, reduced in a fixed order
  */
 int mas_duration_loss_f32(const float *logw, const int32_t *durations, const int32_t *t_x,
                           float *logw_target, float *grad_unit, float *loss, int B, int T_x,
-                          void *stream);
+                          void *workspace, size_t workspace_bytes, void *stream);
 
 /* out_size crop of a [B,R,T_y] fp32 tensor (y: R = n_feats) -- replaces the per-item slicing
  * loop of tts.py:524-544: dst[b,r,j] = src[b,r,offset[b]+j] for j < seg_len[b], else 0. */
@@ -209,7 +210,7 @@ int mas_crop_f32(const float *src, const int32_t *offset, const int32_t *seg_len
 int mas_path_segment(const int32_t *frame_idx, const int32_t *offset, const int32_t *seg_len,
                      void *path, int path_dtype, int B, int T_x, int T_y, int T_out, void *stream);
 
-/* scratch bytes of mas_align_gather_f32 when prior_loss != NULL (never 0) */
+/* scratch bytes of mas_align_gather_f32 (prior_loss != NULL) and mas_duration_loss_f32 (loss != NULL); never 0 */
 size_t mas_align_workspace_bytes(int B, int F, int T_out);
 
 /*

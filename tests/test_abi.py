@@ -71,8 +71,9 @@ def test_argument_validation_without_gpu(maslib):
     # consumers of the alignment
     assert maslib.mas_frame_index(null, one, one, one, 1, 4, 8, null) == -1
     assert maslib.mas_frame_index(one, one, one, odd, 1, 4, 8, null) == -5
-    assert maslib.mas_duration_loss_f32(null, one, one, null, null, one, 1, 4, null) == -1  # loss needs logw
-    assert maslib.mas_duration_loss_f32(one, one, one, null, null, null, 1, 4, null) == -1  # nothing to do
+    assert maslib.mas_duration_loss_f32(null, one, one, null, null, one, 1, 4, null, 0, null) == -1  # loss needs logw
+    assert maslib.mas_duration_loss_f32(one, one, one, null, null, null, 1, 4, null, 0, null) == -1  # nothing to do
+    assert maslib.mas_duration_loss_f32(one, one, one, null, null, one, 1, 4, null, 0, null) == -4   # loss needs scratch
     assert maslib.mas_crop_f32(one, null, null, null, 1, 80, 8, 4, null) == -1
     assert maslib.mas_crop_f32(one, null, null, one, 1, 80, 8, 0, null) == -2
     assert maslib.mas_path_segment(one, null, null, one, 6, 1, 4, 8, 8, null) == -3
