@@ -58,10 +58,10 @@ static int env_int(const char *name, int dflt)
 
 // Shared-memory carve-up of the fast kernels and the plan that follows from it.
 // `extra_smem` = bytes the caller needs besides ring + bits (the fused kernel's operands).
-Plan choose_plan(int T_x, int T_y, int flags, FastLayout *lay, size_t extra_smem, int max_stages)
+Plan choose_plan(int T_x, int T_y, int flags, FastLayout *lay, size_t extra_smem, int max_stages, int row_align)
 {
     FastLayout L{};
-    L.xrows = ((T_x + 31) / 32) * 32;
+    L.xrows = ((T_x + row_align - 1) / row_align) * row_align;
     L.nch = (T_y + 31) / 32;
     const size_t stage_bytes = (size_t)L.xrows * 128;
     const size_t bits_bytes = (size_t)L.nch * L.xrows * 4;
@@ -102,7 +102,7 @@ Plan choose_plan(int T_x, int T_y, int flags, FastLayout *lay, size_t extra_smem
 
 static size_t bits_workspace_bytes(int B, int T_x, int T_y)
 {
-    const size_t xrows = (size_t)((T_x + 31) / 32) * 32, nch = (size_t)(T_y + 31) / 32;
+    const size_t xrows = (size_t)((T_x + 63) / 64) * 64, nch = (size_t)(T_y + 31) / 32;   // 64: two-DP-warp layout
     return (size_t)B * nch * xrows * 4;
 }
 
@@ -145,12 +145,33 @@ size_t mas_workspace_bytes(int B, int T_x, int T_y)
     return bits_workspace_bytes(B, T_x, T_y) + 256;
 }
 
+static Plan plan_fast(int T_x, int T_y, int flags, MasArgs *a);
+
 int mas_plan(int B, int T_x, int T_y, int flags)
 {
     (void)B;
     if (T_x < 1 || T_y < 1) return MAS_ERR_SHAPE;
-    FastLayout lay;
-    return (int)choose_plan(T_x, T_y, flags, &lay);
+    MasArgs a{};
+    return (int)plan_fast(T_x, T_y, flags, &a);
+}
+
+// Layout + DP-warp count of the drop-in kernel.  Long token axis (config 4: 512 x 4096): the
+// frame-sequential recurrence is the whole run time, so two DP warps split the tokens (mas_dp.cuh
+// dp_forward2); that needs a third ring stage and 64-row alignment of the tiles.
+static Plan plan_fast(int T_x, int T_y, int flags, MasArgs *a)
+{
+    Plan plan = choose_plan(T_x, T_y, flags, &a->lay);
+    a->dp_warps = 1;
+    if (plan != kPlanGeneral && T_x > env_int("MAS_DP2_MIN_TX", 256)) {
+        FastLayout l2;
+        const Plan p2 = choose_plan(T_x, T_y, flags, &l2, 512, 3, 64);
+        if (p2 != kPlanGeneral && l2.nstages >= 3) {
+            a->lay = l2;
+            plan = p2;
+            a->dp_warps = 2;
+        }
+    }
+    return plan;
 }
 
 static bool shape_ok(int B, int T_x, int T_y)
@@ -192,7 +213,7 @@ int mas_maximum_path(const void *value, int value_dtype, const float *cell_mask,
     if (B == 0) return MAS_OK;
 
     MasArgs a{};
-    const Plan plan = choose_plan(T_x, T_y, flags, &a.lay);
+    const Plan plan = plan_fast(T_x, T_y, flags, &a);
     if (plan != kPlanFastSmemBits) {
         if (!workspace || workspace_bytes < mas_workspace_bytes(B, T_x, T_y)) return MAS_ERR_WORKSPACE;
         if ((uintptr_t)workspace % 16) return MAS_ERR_ALIGN;
@@ -305,7 +326,7 @@ int mas_from_prior_f32(const float *mu_x, const float *logs, const float *y, con
     if (!fused) {
         // operands do not fit next to the tile ring: prior to HBM once, then the drop-in kernel
         MasArgs m{};
-        const Plan p2 = choose_plan(T_x, T_y, flags, &m.lay);
+        const Plan p2 = plan_fast(T_x, T_y, flags, &m);
         if (p2 == kPlanGeneral && (size_t)T_x * 16 > (size_t)kSmemBudget) return MAS_ERR_SHAPE;
         m.value = log_prior_out;
         m.t_x = t_x;

@@ -495,7 +495,7 @@ __device__ __forceinline__ float prior_forward2_dispatch(const TileRing &ring, u
             return dp_forward2<N>(ring, bits, xrows, tx, ty, lane, w, g0, edge, edge_full, owns, wacc);    \
         break;
     switch (xpl) {
-        MAS_CASE2(1) MAS_CASE2(2) MAS_CASE2(3) MAS_CASE2(4)
+        MAS_CASE2(1) MAS_CASE2(2) MAS_CASE2(3) MAS_CASE2(4) MAS_CASE2(5) MAS_CASE2(6) MAS_CASE2(7) MAS_CASE2(8)
     default: break;
     }
 #undef MAS_CASE2

@@ -12,6 +12,7 @@ namespace mas {
 constexpr int kMaxFastTx = 512;            // single-warp DP: 16 tokens per lane
 constexpr int kSmemBudget = 227 * 1024;    // opt-in dynamic shared memory per CTA on sm_100
 constexpr int kFastThreads = 160;          // 1 DP warp + 4 staging warps
+constexpr int kFast2Threads = 192;         // 2 DP warps + 4 staging warps (long utterances)
 constexpr int kGeneralThreads = 256;
 
 enum Plan { kPlanFastSmemBits = 0, kPlanFastSpillBits = 1, kPlanGeneral = 2 };
@@ -36,6 +37,7 @@ struct MasArgs {
     uint32_t *bits_ws;     // workspace: [B][nch][xrows] (fast, spilled) or [B][32*nch][xw] (general)
     int B, T_x, T_y;
     int path_esize;
+    int dp_warps;          // 1, or 2 for long utterances (mas_fast2_kernel: two DP warps split the tokens)
     int load_mode;         // fast kernel staging: 0 = LDG/STS (any dtype, cell mask), 1 = cp.async 4 B,
                            // 2 = cp.async 16 B (fp32, rows 16-byte aligned)
     unsigned long long one;
@@ -45,7 +47,7 @@ struct MasArgs {
 int element_size(int dtype);
 unsigned long long one_pattern(int dtype);
 Plan choose_plan(int T_x, int T_y, int flags, FastLayout *lay, size_t extra_smem = 0,
-                 int max_stages = 3);
+                 int max_stages = 3, int row_align = 32);
 
 cudaError_t launch_lengths_from_mask(const void *mask, int mask_dtype, int B, int T_x, int T_y,
                                      int64_t sb, int64_t sx, int64_t sy, int32_t *t_x, int32_t *t_y,

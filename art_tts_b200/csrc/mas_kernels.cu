@@ -276,6 +276,168 @@ __global__ void __launch_bounds__(kFastThreads) mas_fast_kernel(const MasArgs a)
                     a.T_y, tid, kFastThreads);
 }
 
+// ------------------------------------------------------------------------------------
+// fast kernel, long token axis: two DP warps split the tokens (dp_forward2), same staging
+// ------------------------------------------------------------------------------------
+template <typename InT>
+__device__ __forceinline__ void stage_value_tile2(const InT *__restrict__ vb, const float *__restrict__ mb,
+                                                  float *stage, int t, int tx, int ty, int64_t T_y, int hw,
+                                                  int nhw, int lane, bool async, bool vec16)
+{
+    // as stage_value_tile / stage_value_tile_async, with the 64-lane row map
+    const RowMap rm(tx, 6);
+    const int y0 = t * kTileY;
+    const int lo = max(0, tx + y0 - ty);
+    const int hi = min(tx - 1, y0 + kTileY - 1);
+    if (async && vec16) {
+        const int c = lane & 7, r = lane >> 3;
+        const int left = ty - (y0 + 4 * c);
+        const uint32_t bytes = left >= 4 ? 16u : (left > 0 ? 4u * left : 0u);
+        const int yo = bytes ? y0 + 4 * c : 0;
+        for (int x = lo + 4 * hw + r; x <= hi; x += 4 * nhw) {
+            const int row = rm.row(x);
+            cp_async16(stage + (row << 5) + ((c ^ (row & 7)) << 2),
+                       reinterpret_cast<const float *>(vb) + (int64_t)x * T_y + yo, bytes);
+        }
+    } else if (async) {
+        const int y = y0 + lane;
+        const uint32_t bytes = y < ty ? 4u : 0u;
+        const float *src = reinterpret_cast<const float *>(vb) + (y < ty ? y : 0);
+        for (int x = lo + hw; x <= hi; x += nhw)
+            cp_async4(stage + tile_index(rm.row(x), lane), src + (int64_t)x * T_y, bytes);
+    } else {
+        const int y = y0 + lane;
+        const bool in = y < ty;
+        for (int x = lo + hw; x <= hi; x += nhw) {
+            float v = 0.0f;
+            if (in) {
+                const int64_t e = (int64_t)x * T_y + y;
+                v = load_as_f32(vb + e);
+                if (mb) v *= __ldg(mb + e);
+            }
+            stage[tile_index(rm.row(x), lane)] = v;
+        }
+    }
+}
+
+template <typename InT, int XPLMAX>
+__global__ void __launch_bounds__(kFast2Threads) mas_fast2_kernel(const MasArgs a)
+{
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const FastLayout &L = a.lay;
+    float *stages = reinterpret_cast<float *>(smem + L.off_stages);
+    int *first = reinterpret_cast<int *>(smem + L.off_first);
+    int *dur = reinterpret_cast<int *>(smem + L.off_dur);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + L.off_bars);
+    uint64_t *edge_full = bars + 12;                                     // [4], after full[<=6] + empty[<=6]
+    float *edge = reinterpret_cast<float *>(smem + L.off_bars + 128);    // [4 tiles][32 frames]
+
+    const int b = blockIdx.x;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int T_x = a.T_x;
+    const int64_t T_y = a.T_y;
+    const int tx = min(max(a.t_x[b], 0), T_x);
+    const int ty = min(max(a.t_y[b], 0), a.T_y);
+    const bool degenerate = tx > ty && ty >= 1;
+    const bool active = tx >= 1 && ty >= 1 && !degenerate;
+    const int ntiles = active ? (ty + kTileY - 1) / kTileY : 0;
+    constexpr int kHelperWarps = 4;
+
+    uint32_t *bits = L.bits_in_smem ? reinterpret_cast<uint32_t *>(smem + L.off_bits)
+                                    : a.bits_ws + (size_t)b * L.nch * L.xrows;
+    TileRing ring;
+    ring.stages = stages;
+    ring.full = bars;
+    ring.empty = bars + L.nstages;
+    ring.nstages = L.nstages;
+    ring.stage_floats = L.xrows * kTileY;
+    if (tid == 0) {
+        for (int s = 0; s < L.nstages; ++s) {
+            mbar_init(&ring.full[s], kHelperWarps * 32);
+            mbar_init(&ring.empty[s], 2);   // both DP warps
+        }
+        for (int s = 0; s < 4; ++s) mbar_init(&edge_full[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    const InT *vb = static_cast<const InT *>(a.value) + (int64_t)b * T_x * T_y;
+    const float *mb = a.cell_mask ? a.cell_mask + (int64_t)b * T_x * T_y : nullptr;
+
+    if (warp >= kHelperWarps) {
+        // ---------------- the two DP warps ----------------
+        const int w = warp - kHelperWarps;
+        if (w == 0)
+            for (int x = lane; x < T_x; x += 32) dur[x] = 0;
+        __syncwarp();
+        float score = 0.0f;
+        int owns = 0;
+        if (active) {
+            score = prior_forward2_dispatch<XPLMAX>(ring, bits, L.xrows, tx, ty, lane, w, 0, edge, edge_full,
+                                                    &owns, nullptr);
+            if (owns && lane == 0 && a.score) a.score[b] = score;
+            __threadfence_block();
+            asm volatile("bar.sync 1, 64;" ::: "memory");   // both halves of the direction bits are written
+            if (w == 0 && lane == 0) backtrack_bits(bits, L.xrows, tx, ty, first, dur, L.bits_in_smem != 0, 6);
+        } else if (w == 0) {
+            if (degenerate) {
+                if (lane == 0) {
+                    auto val = [&](int x, int y) {
+                        const int64_t e = (int64_t)x * T_y + y;
+                        float v = load_as_f32(vb + e);
+                        if (mb) v *= mb[e];
+                        return v;
+                    };
+                    backtrack_degenerate(val, tx, ty, first, dur);
+                    score = val(tx - 1, ty - 1);
+                }
+                score = __shfl_sync(kFull, score, 0);
+            }
+            if (lane == 0 && a.score) a.score[b] = score;
+        }
+    } else {
+        // ---------------- staging warps ----------------
+        const int hw = warp;
+        constexpr int nht = kHelperWarps * 32;
+        char *pb = a.path ? static_cast<char *>(a.path) + (int64_t)b * T_x * T_y * a.path_esize : nullptr;
+        const int64_t pbytes = a.path ? (int64_t)T_x * T_y * a.path_esize : 0;
+        const bool async = sizeof(InT) == 4 && a.load_mode != 0;
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int t = 0; t < ntiles; ++t) {
+            if (t >= L.nstages) mbar_wait(&ring.empty[stage], phase ^ 1u);
+            float *dst = stages + stage * ring.stage_floats;
+            stage_value_tile2<InT>(vb, mb, dst, t, tx, ty, T_y, hw, kHelperWarps, lane, async, a.load_mode == 2);
+            if (async) cp_async_arrive(&ring.full[stage]);
+            else mbar_arrive(&ring.full[stage]);
+            if (++stage == L.nstages) {
+                stage = 0;
+                phase ^= 1u;
+            }
+            zero_fill_part(pb, pbytes, t, ntiles, tid, nht);
+        }
+        if (ntiles == 0) zero_fill_part(pb, pbytes, 0, 1, tid, nht);
+    }
+    __syncthreads();
+    write_path_ones(a.path ? static_cast<char *>(a.path) + (int64_t)b * T_x * T_y * a.path_esize : nullptr,
+                    a.durations ? a.durations + (int64_t)b * T_x : nullptr, first, dur, T_x, T_y, a.path_esize,
+                    a.one, tid, kFast2Threads);
+    write_frame_idx(a.frame_idx ? a.frame_idx + (int64_t)b * T_y : nullptr, first, dur, T_x, ty, a.T_y, tid,
+                    kFast2Threads);
+}
+
+template <typename InT>
+static cudaError_t launch_fast2_typed(const MasArgs &a, cudaStream_t st)
+{
+    const int xplmax = (a.T_x + 63) / 64;
+    void (*k)(const MasArgs) = (xplmax <= 6) ? mas_fast2_kernel<InT, 6> : mas_fast2_kernel<InT, 8>;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a.lay.total);
+    if (e != cudaSuccess) return e;
+    k<<<a.B, kFast2Threads, a.lay.total, st>>>(a);
+    count_launch();
+    return cudaGetLastError();
+}
+
 template <typename InT>
 static cudaError_t launch_fast_typed(const MasArgs &a, cudaStream_t st)
 {
@@ -302,6 +464,15 @@ static cudaError_t launch_fast_typed(const MasArgs &a, cudaStream_t st)
 
 cudaError_t launch_fast(const MasArgs &a, int value_dtype, cudaStream_t st)
 {
+    if (a.dp_warps == 2) {
+        switch (value_dtype) {
+        case MAS_F32: return launch_fast2_typed<float>(a, st);
+        case MAS_F16: return launch_fast2_typed<__half>(a, st);
+        case MAS_BF16: return launch_fast2_typed<__nv_bfloat16>(a, st);
+        case MAS_F64: return launch_fast2_typed<double>(a, st);
+        default: return cudaErrorInvalidValue;
+        }
+    }
     switch (value_dtype) {
     case MAS_F32: return launch_fast_typed<float>(a, st);
     case MAS_F16: return launch_fast_typed<__half>(a, st);
