@@ -754,8 +754,10 @@ cudaError_t launch_from_prior_tc(const PriorTcArgs &a, cudaStream_t st)
     else k = mas_prior_tc_kernel<4>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a.lay.total);
     if (e != cudaSuccess) return e;
-    if (a.lp_out) {   // parity tap: cells the kernel does not produce (padding) read as zero
-        e = cudaMemsetAsync(a.lp_out, 0, (size_t)a.B * a.T_x * a.T_y * sizeof(float), st);
+    if (a.lp_out) {
+        // parity tap: the kernel below writes every cell it produces (= what the DP consumed); the
+        // cells it never forms (padding, empty and degenerate utterances) come from the plain kernel
+        e = launch_log_prior(a.mu_x, a.y, a.lp_out, a.B, a.F, a.T_x, a.T_y, st);
         if (e != cudaSuccess) return e;
     }
     // persistent: one CTA per SM; `sm_limit` (mas_set_sm_limit) leaves SMs free for a concurrent kernel,

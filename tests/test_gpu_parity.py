@@ -460,3 +460,33 @@ def test_entry_points_are_cuda_graph_capturable_and_stream_ordered(cuda):
     torch.cuda.synchronize()
     for a, b in zip(outs, want):
         assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("engine", ["cuda_core", "tensor_core"])
+def test_fused_degenerate_and_empty_utterances(cuda, engine):
+    """Empty utterances (t_x == 0 or t_y == 0: all-zero path, like the reference's all-zero mask),
+    t_x == t_y (pure diagonal), t_x == 1, and the reference's degenerate t_x > t_y case (backtrack
+    over raw prior values) in the middle of a batch of normal ones."""
+    rng = np.random.default_rng(31)
+    B, F, T_x, T_y = 8, 40, 20, 64
+    x_len = np.array([0, 5, 9, 1, 7, 3, 20, 12], np.int32)
+    y_len = np.array([10, 0, 5, 1, 7, 50, 64, 12], np.int32)
+    mu_x = rng.standard_normal((B, F, T_x)).astype(np.float32)
+    y = rng.standard_normal((B, F, T_y)).astype(np.float32)
+    mask = rect_mask(x_len, y_len, T_x, T_y)
+    path, dur, score, lp = fused(mu_x, y, x_len, y_len, cuda, return_score=True, return_log_prior=True,
+                                 flags=ENGINES[engine])
+    lp_np, path_np = lp.cpu().numpy(), path.cpu().numpy()
+    # the degenerate utterance (b = 2) is decided by raw values both kernels compute with the
+    # CUDA-core formula; the tap of the tensor-core engine differs from it by rounding only, so
+    # feed the oracle the fp32 FMA prior there
+    ref_lp = oracle.log_prior(mu_x, y, method="c")
+    lp_for_oracle = lp_np.copy()
+    lp_for_oracle[2] = ref_lp[2]
+    want = oracle.maximum_path(lp_for_oracle, mask)
+    assert np.array_equal(path_np, want)
+    assert np.array_equal(dur.cpu().numpy(), want.sum(-1).astype(np.int32))
+    assert path_np[0].sum() == 0 and path_np[1].sum() == 0
+    assert np.array_equal(path_np[4, :7, :7], np.eye(7, dtype=np.float32))
+    m = mask.astype(bool)
+    assert np.allclose(lp_np[m], ref_lp[m], rtol=1e-5, atol=1e-4)
