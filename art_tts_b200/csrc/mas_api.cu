@@ -272,7 +272,8 @@ int mas_from_prior_f32(const float *mu_x, const float *logs, const float *y, con
     // CUDA-core kernel (A/B measurements, and the shapes beyond 256 tokens / 96 features)
     if (env_int("MAS_PRIOR_TC", 1) && !(flags & (MAS_FLAG_FORCE_GENERAL | MAS_FLAG_SPILL_BITS | MAS_FLAG_NO_TENSOR))) {
         PriorTcArgs t{};
-        t.lay = tc_layout(F, T_x, T_y);
+        const bool tc2 = env_int("MAS_PRIOR_TC2", 0) != 0;   // experimental engine of mas_prior_tc2.cu (measured slower)
+        t.lay = tc2 ? tc2_layout(F, T_x, T_y) : tc_layout(F, T_x, T_y);
         // measured (profiles/config_sweep.py): below ~32 features the FMA work is so small that the
         // CUDA-core kernel is as fast or faster (F=16: 0.157 vs 0.166 ms at B=1024, 160x512)
         if (t.lay.ok && (F >= env_int("MAS_PRIOR_TC_MIN_F", 32) || (flags & MAS_FLAG_FORCE_TENSOR))) {
@@ -298,7 +299,7 @@ int mas_from_prior_f32(const float *mu_x, const float *logs, const float *y, con
             t.T_y = T_y;
             t.path_esize = path ? esize : 4;
             t.one = one_pattern(path_dtype);
-            return (int)launch_from_prior_tc(t, st);
+            return (int)(tc2 ? launch_from_prior_tc2(t, st) : launch_from_prior_tc(t, st));
         }
     }
 

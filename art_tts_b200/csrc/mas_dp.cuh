@@ -341,7 +341,19 @@ __device__ __forceinline__ void write_frame_idx(int32_t *fi, const int *first, c
 // Warp 0 cannot lap warp 1 by more than the tile ring's depth (<= 3), so the 4-tile edge ring
 // needs no back-pressure of its own.  Tiles use the row map RowMap(tx, 6).
 // ------------------------------------------------------------------------------------
-template <int XPL, bool DIAG>
+// direction bit of one cell: acc |= bit when up > cur (the comparison of core.pyx:30), as FSETP +
+// a predicated integer op that sit beside the value chain, not in it
+__device__ __forceinline__ void dir_bit(float up, float cur, uint32_t &acc, uint32_t bit)
+{
+    asm("{\n\t.reg .pred p;\n\tsetp.gt.f32 p, %1, %2;\n\t@p or.b32 %0, %0, %3;\n\t}" : "+r"(acc) : "f"(up), "f"(cur), "r"(bit));
+}
+
+// FMAX = the formulation of the fused kernels: the value chain is FMNMX + FADD (10 cycles per
+// token instead of 14 for FSETP + FSEL + FADD, profiles/microbench/dp_chain.cu) and the direction
+// bit comes from the same comparison beside the chain.  max(up, cur) is the reference's
+// `up > cur ? up : cur` on finite values (a NaN or a +0/-0 tie could differ), so the drop-in
+// kernel, whose contract is bit-exactness on any input, keeps the select.
+template <int XPL, bool DIAG, bool FMAX = false>
 __device__ __forceinline__ float dp_step2(float (&V)[XPL], uint32_t (&acc)[XPL], const float (&v)[XPL],
                                           float &left, int lane, int x0, int y, uint32_t bit,
                                           float lane0_left)
@@ -350,11 +362,17 @@ __device__ __forceinline__ float dp_step2(float (&V)[XPL], uint32_t (&acc)[XPL],
 #pragma unroll
     for (int j = XPL - 1; j >= 0; --j) {
         const float up = (j == 0) ? left : V[j > 0 ? j - 1 : 0];   // V[x-1, y-1]
-        const bool take_prev = up > V[j];                          // core.pyx:30 max()
-        const float m = take_prev ? up : V[j];
+        float m;
+        if (FMAX) {
+            dir_bit(up, V[j], acc[j], bit);
+            m = fmaxf(up, V[j]);
+        } else {
+            const bool take_prev = up > V[j];                      // core.pyx:30 max()
+            m = take_prev ? up : V[j];
+            if (take_prev) acc[j] |= bit;
+        }
         float nv = __fadd_rn(m, v[j]);
         if (DIAG) nv = (x0 + j <= y) ? nv : kNeg;                  // x > y: not reachable yet
-        if (take_prev) acc[j] |= bit;
         V[j] = nv;
         if (j == XPL - 1) {
             last = nv;
@@ -365,7 +383,7 @@ __device__ __forceinline__ float dp_step2(float (&V)[XPL], uint32_t (&acc)[XPL],
     return last;
 }
 
-template <int XPL, bool DIAG, bool FULL>
+template <int XPL, bool DIAG, bool FULL, bool FMAX = false>
 __device__ __forceinline__ void dp_tile2(float (&V)[XPL], uint32_t (&acc)[XPL], float &left,
                                          const float *__restrict__ stage, float *__restrict__ edge_tile,
                                          int w, int lane, int x0, int y0, int nsteps)
@@ -386,22 +404,22 @@ __device__ __forceinline__ void dp_tile2(float (&V)[XPL], uint32_t (&acc)[XPL], 
         float v[XPL];
 #pragma unroll
         for (int j = 0; j < XPL; ++j) v[j] = f4_get<0>(vv[j]);
-        out.x = dp_step2<XPL, DIAG>(V, acc, v, left, lane, x0, y0 + s0, 1u << s0, ev.x);
+        out.x = dp_step2<XPL, DIAG, FMAX>(V, acc, v, left, lane, x0, y0 + s0, 1u << s0, ev.x);
         out.y = out.z = out.w = 0.0f;
         if (FULL || s0 + 1 < nsteps) {
 #pragma unroll
             for (int j = 0; j < XPL; ++j) v[j] = f4_get<1>(vv[j]);
-            out.y = dp_step2<XPL, DIAG>(V, acc, v, left, lane, x0, y0 + s0 + 1, 2u << s0, ev.y);
+            out.y = dp_step2<XPL, DIAG, FMAX>(V, acc, v, left, lane, x0, y0 + s0 + 1, 2u << s0, ev.y);
         }
         if (FULL || s0 + 2 < nsteps) {
 #pragma unroll
             for (int j = 0; j < XPL; ++j) v[j] = f4_get<2>(vv[j]);
-            out.z = dp_step2<XPL, DIAG>(V, acc, v, left, lane, x0, y0 + s0 + 2, 4u << s0, ev.z);
+            out.z = dp_step2<XPL, DIAG, FMAX>(V, acc, v, left, lane, x0, y0 + s0 + 2, 4u << s0, ev.z);
         }
         if (FULL || s0 + 3 < nsteps) {
 #pragma unroll
             for (int j = 0; j < XPL; ++j) v[j] = f4_get<3>(vv[j]);
-            out.w = dp_step2<XPL, DIAG>(V, acc, v, left, lane, x0, y0 + s0 + 3, 8u << s0, ev.w);
+            out.w = dp_step2<XPL, DIAG, FMAX>(V, acc, v, left, lane, x0, y0 + s0 + 3, 8u << s0, ev.w);
         }
         if (w == 0 && lane == 31)   // publish my last token (token 32*XPL - 1) for warp 1
             asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(edgebase + (g << 4)), "f"(out.x),
@@ -413,7 +431,7 @@ __device__ __forceinline__ void dp_tile2(float (&V)[XPL], uint32_t (&acc)[XPL], 
 // Forward pass of one utterance by DP warp `w` of two.  `edge` = 4 x 32 floats, `edge_full` = 4
 // mbarriers (count 1); ring.empty barriers must expect TWO arrivals per tile.  Returns
 // V[t_x-1, t_y-1] in every lane of the warp that owns token t_x-1 (`*owns` = 1), else *owns = 0.
-template <int XPL>
+template <int XPL, bool FMAX = false>
 __device__ __noinline__ float dp_forward2(const TileRing ring, uint32_t *bits, int xrows, int tx, int ty,
                                           int lane, int w, int g0, float *edge, uint64_t *edge_full,
                                           int *owns, long long *wait_acc = nullptr)
@@ -444,10 +462,10 @@ __device__ __noinline__ float dp_forward2(const TileRing ring, uint32_t *bits, i
         const int nsteps = min(kTileY, ty - y0);
         const bool diag = y0 < tx;  // some token x > y still exists in this tile
         if (nsteps == kTileY) {
-            if (diag) dp_tile2<XPL, true, true>(V, acc, left, tile, etile, w, lane, x0, y0, nsteps);
-            else dp_tile2<XPL, false, true>(V, acc, left, tile, etile, w, lane, x0, y0, nsteps);
+            if (diag) dp_tile2<XPL, true, true, FMAX>(V, acc, left, tile, etile, w, lane, x0, y0, nsteps);
+            else dp_tile2<XPL, false, true, FMAX>(V, acc, left, tile, etile, w, lane, x0, y0, nsteps);
         } else {
-            dp_tile2<XPL, true, false>(V, acc, left, tile, etile, w, lane, x0, y0, nsteps);
+            dp_tile2<XPL, true, false, FMAX>(V, acc, left, tile, etile, w, lane, x0, y0, nsteps);
         }
         __syncwarp();
         if (lane == 0) {
@@ -482,7 +500,7 @@ __device__ __noinline__ float dp_forward2(const TileRing ring, uint32_t *bits, i
     return __shfl_sync(kFull, s, ql & 31);
 }
 
-template <int XPLMAX>
+template <int XPLMAX, bool FMAX = false>
 __device__ __forceinline__ float prior_forward2_dispatch(const TileRing &ring, uint32_t *bits, int xrows,
                                                          int tx, int ty, int lane, int w, int g0,
                                                          float *edge, uint64_t *edge_full, int *owns,
@@ -492,7 +510,7 @@ __device__ __forceinline__ float prior_forward2_dispatch(const TileRing &ring, u
 #define MAS_CASE2(N)                                                                                       \
     case N:                                                                                                \
         if constexpr (N <= XPLMAX)                                                                         \
-            return dp_forward2<N>(ring, bits, xrows, tx, ty, lane, w, g0, edge, edge_full, owns, wacc);    \
+            return dp_forward2<N, FMAX>(ring, bits, xrows, tx, ty, lane, w, g0, edge, edge_full, owns, wacc);    \
         break;
     switch (xpl) {
         MAS_CASE2(1) MAS_CASE2(2) MAS_CASE2(3) MAS_CASE2(4) MAS_CASE2(5) MAS_CASE2(6) MAS_CASE2(7) MAS_CASE2(8)

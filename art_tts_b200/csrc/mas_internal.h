@@ -132,6 +132,8 @@ struct PriorTcArgs {
 };
 TcLayout tc_layout(int F, int T_x, int T_y);
 cudaError_t launch_from_prior_tc(const PriorTcArgs &a, cudaStream_t st);
+TcLayout tc2_layout(int F, int T_x, int T_y);   // mas_prior_tc2.cu: DP straight from tensor memory
+cudaError_t launch_from_prior_tc2(const PriorTcArgs &a, cudaStream_t st);
 
 int sm_count();
 int sm_reserve();   // SMs the persistent kernels leave free (mas_set_sm_reserve)

@@ -1,36 +1,14 @@
-// mas_prior_tc.cu -- fused Gaussian log-prior + MAS with the prior on the 5th-gen tensor cores.
+// mas_prior_tc2.cu -- fused Gaussian log-prior + MAS, tensor-core prior, DP STRAIGHT FROM TENSOR MEMORY.
 //
-// Same contract as mas_prior_kernel (mas_prior.cu; replaces tts.py:483-505), different engine
-// for the cross term sum_f mu[f,x]*y[f,j]: the reference computes it with an fp32 GEMM
-// (torch.matmul, tts.py:491-493), and so does this kernel -- tcgen05.mma kind::tf32 with the
-// 3xTF32 split, which restores fp32-level accuracy from tf32 products:
-//
-//     a = a_hi + a_lo,  b = b_hi + b_lo   (a_hi = tf32(a), a_lo = tf32(a - a_hi), same for b)
-//     a*b ~= a_lo*b_hi + a_hi*b_lo + a_hi*b_hi          (dropped a_lo*b_lo ~ 2^-22 |a*b|)
-//
-// accumulated in fp32 in tensor memory (measured on B200, profiles/microbench/tc_prior.cu:
-// max error 3e-5 on sums of magnitude 35, vs 1e-5 for a sequential fp32 FMA chain and 1e-2 for
-// plain tf32).  The FMA pipe was the binding resource of the CUDA-core kernel (80 FMA per
-// cell); here one utterance's mu_x lives in TENSOR MEMORY as the A operand (hi and lo parts,
-// one column per feature, one lane per token) and each 32-frame slab of y is the B operand
-// in shared memory, so a tile costs 60 MMAs of 128x32x8 and no CUDA-core arithmetic beyond
-// the three adds of tts.py:495.
-//
-// Persistent CTA per SM, 12 warps, all hand-offs are mbarriers:
-//   warps 0-3  epilogue (TMEM lane quarter = warp id): per tile tcgen05.ld the accumulator,
-//              add the y / mu / const terms and write the swizzled tile the DP warp consumes
-//              (same ring layout as the other kernels)
-//   warps 8-11 mu_x movers (TMEM lane quarter = warp id - 8): run one utterance AHEAD -- hold
-//              the next utterance's mu_x in registers (global loads issued while the current
-//              one is still being multiplied) and, the moment its last MMA has retired, split
-//              it into tf32 hi/lo and tcgen05.st it into TMEM; also produce -0.5|mu|^2
-//   warp 4     DP warp        (mas_dp.cuh dp_forward, unchanged)
-//   warp 5     MMA issuer     (one lane): tiles are issued in PAIRS, interleaving the MMAs of
-//              their (up to four) independent accumulators -- back-to-back MMAs into the same
-//              accumulator serialise at ~100 cycles each (measured), independent ones overlap
-//   warp 6     slab loader    (cp.async y slabs in the MN-major SWIZZLE_128B_BASE32B layout,
-//              tf32 hi/lo split in place, -0.5|y|^2 per frame, bulk zero-fill of the path)
-//   warp 7     backtrack warp (unchanged: one utterance behind, second direction-bit buffer)
+// Same contract and the same front half as mas_prior_tc.cu (3xTF32 tcgen05.mma, mu_x resident in
+// TMEM as the A operand, K-major y slabs as B), but the accumulator never goes through shared
+// memory: the four warps that may read TMEM (one per 32-lane quarter) ARE the DP warps.  Token x
+// lives in TMEM lane L = x / P of M tile j = x % P (P = 1 or 2 tokens per lane), so lane L of
+// quarter-warp q owns consecutive tokens and reads its own accumulator rows with tcgen05.ld: a
+// row is 32 frames of one token, exactly what the frame-sequential recurrence consumes.  The
+// x-1 neighbour is a register or one shuffle; the value that crosses a warp boundary goes
+// through a small ring in shared memory, each warp running 8 frames behind its left neighbour
+// (one mbarrier hand-off per 8 frames).  No epilogue warps, no tile ring, no transposition.
 #include <algorithm>
 #include <type_traits>
 
@@ -41,11 +19,11 @@ namespace mas {
 
 namespace {
 
-constexpr int kTcThreads = 448;
+constexpr int kTcThreads = 384;
 // warps 0-3 epilogue, 8-11 mu_x movers (TMEM lane quarter = warp % 4 is a hardware rule); the rest is
 // placed by scheduler (warp % 4): the DP warp shares its scheduler with the latency-bound backtrack
 // warp, not with a loader
-constexpr int kTcDp = 4, kTcMma = 5, kTcLoader = 6, kTcLoader2 = 7, kTcBack = 12, kTcDp2 = 13;
+constexpr int kTcMma = 5, kTcLoader = 6, kTcLoader2 = 7, kTcBack = 4;   // warps 0-3: DP (TMEM quarters), 8-11: movers
 constexpr int kTcSlabs = 4;       // y slabs (hi+lo) in flight
 constexpr int kTcLag = 1;         // a slab is finished one loader iteration after its copy was issued
 constexpr int kTcYsq = 8;         // ring of per-slab -0.5|y|^2 vectors (> kTcSlabs + D buffers)
@@ -53,6 +31,16 @@ constexpr int kTcStage = 2;        // staging buffers [F][32 frames] behind the 
 constexpr int kTcMsq = 4;         // ring of per-utterance -0.5|mu|^2 vectors (> utterances an accumulator lags)
 constexpr int kTcZeroBytes = 4096;
 constexpr int kTcTmemCols = 512;
+#ifndef MAS_EXP_PASS0
+#define MAS_EXP_PASS0 0
+#endif
+constexpr int kExpPass0 = MAS_EXP_PASS0;
+#ifdef MAS_TC2_DPSTATS   // instrumented build (profiles/prior_tc_stats.py --dp): where the DP warps wait
+#define DPSTAT(x) x
+#else
+#define DPSTAT(x)
+#endif   // experiment: skip the first passes (wrong results, timing only)
+constexpr int kTc2BarBytes = 3072;   // barriers (1 KB) + DP edge rings (3 x 16 x 8 floats) + their barriers
 
 // ---------------------------------------------------------------- tcgen05 wrappers
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -133,12 +121,12 @@ struct TcStat {
 // Shared-memory carve-up and TMEM column map of the tensor-core kernel, or ok == 0 when the
 // shape does not qualify (T_x > 256, F > 96, or the buffers do not fit): the CUDA-core kernel
 // of mas_prior.cu takes those.
-TcLayout tc_layout(int F, int T_x, int T_y)
+TcLayout tc2_layout(int F, int T_x, int T_y)
 {
     TcLayout L{};
     L.ok = 0;
     L.Fp = (F + 7) / 8 * 8;
-    L.xrows = (T_x + 63) / 64 * 64;            // two DP warps: 64 lanes share the token axis
+    L.xrows = 256;                             // direction-bit rows: token x -> row (x % P) * 128 + x / P
     L.nch = (T_y + 31) / 32;
     if (T_x > 256 || L.Fp > 96) return L;
     const int mt = (T_x + 127) / 128;          // M tiles of 128 tokens
@@ -147,21 +135,19 @@ TcLayout tc_layout(int F, int T_x, int T_y)
     L.col_d = 2 * mt * L.Fp;
     L.nb = std::min(4, (kTcTmemCols - L.col_d) / 64);   // accumulator buffers of 2 x 32 columns
     if (L.nb < 2) return L;
-    const size_t stage = (size_t)L.xrows * 128, bits = (size_t)L.nch * L.xrows * 4;
+    const size_t bits = (size_t)L.nch * L.xrows * 4;
     const size_t slabs = (size_t)kTcSlabs * 2 * L.Fp * 128;   // hi + lo, K-major: 1 KB per k step of 8 features
     const size_t misc = (size_t)kTcYsq * 128 + (size_t)kTcMsq * 256 * 4 + (((size_t)T_x * 8 + 15) & ~(size_t)15) + 16 +
-                        kTcZeroBytes + 1024 + (size_t)kTcStage * L.Fp * 128;
+                        kTcZeroBytes + kTc2BarBytes + (size_t)kTcStage * L.Fp * 128;
+    L.nstages = 0;                             // no tile ring: the DP reads the accumulators in TMEM
     for (int slots = 2; slots >= 1 && !L.ok; --slots)
-        for (int ns = 4; ns >= 2; --ns)
-            if ((size_t)ns * stage + slots * bits + slabs + misc <= (size_t)kSmemBudget) {
-                L.nstages = ns;
-                L.bits_slots = slots;
-                L.ok = 1;
-                break;
-            }
+        if (slots * bits + slabs + misc <= (size_t)kSmemBudget) {
+            L.bits_slots = slots;
+            L.ok = 1;
+        }
     if (!L.ok) return L;
     L.off_stages = 0;
-    L.off_slabs = (size_t)L.nstages * stage;                  // both multiples of 1024
+    L.off_slabs = 0;
     L.off_staging = L.off_slabs + slabs;
     L.off_bits = L.off_staging + (size_t)kTcStage * L.Fp * 128;
     L.off_ysq = L.off_bits + (size_t)L.bits_slots * bits;
@@ -169,21 +155,187 @@ TcLayout tc_layout(int F, int T_x, int T_y)
     L.off_first = L.off_musq + (size_t)kTcMsq * 256 * 4;
     L.off_dur = L.off_first + (size_t)T_x * 4;
     L.off_zero = (L.off_dur + (size_t)T_x * 4 + 15) & ~(size_t)15;
-    L.off_bars = L.off_zero + kTcZeroBytes;
-    L.total = L.off_bars + 1024;
+    L.off_bars = (L.off_zero + kTcZeroBytes + 127) & ~(size_t)127;
+    L.total = L.off_bars + kTc2BarBytes;
     // one CTA per SM: each CTA allocates all 512 TMEM columns
     L.total = std::max(L.total, (size_t)(kSmemBudget / 2 + 1024));
     return L;
 }
 
-template <int XPLMAX>
-__global__ void __launch_bounds__(kTcThreads, 1) mas_prior_tc_kernel(const PriorTcArgs a)
+// ------------------------------------------------------------------------------------
+// The recurrence of mas_dp.cuh on accumulator rows read from TMEM.  One tile = 32 frames in four
+// groups of 8: tcgen05.ld 8 columns per owned token, wait for the left neighbour warp's boundary
+// values of the same 8 frames, run dp_step2 on them, publish this warp's own boundary values.
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+
+struct EdgeLink {            // hand-off between neighbouring DP warps, 16 groups of 8 frames deep
+    uint32_t in, out;        // shared addresses of [16][8] boundary values: read / written by this warp
+    uint32_t bar_in, bar_out;   // [16] mbarriers, count 1
+};
+
+__device__ __forceinline__ void mbar_wait_s(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "W: mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@!p bra W;\n\t}" ::"r"(bar), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_s(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void sts128(uint32_t addr, float a, float b, float c, float d)
+{
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+// One group of 8 frames on the accumulator columns `c` (already in registers).
+// The DP warps are the latency-bound agents of this kernel (one dependent chain per warp), so the
+// step is written for a short chain and few instructions.  Per frame and token: two FADDs for the
+// prior (independent filler), FMNMX + FADD for the value (max(up, cur) equals the reference's
+// `up > cur ? up : cur` on finite values), FSETP + predicated LOP3 for the direction bit; one
+// SHFL + FSEL per frame for the left neighbour.
+template <int P, bool DIAG, bool FULL, bool TAP>
+__device__ __forceinline__ void tdp_group(float (&V)[P], uint32_t (&acc)[P], float &left, const uint32_t (&c)[P][8],
+                                          int gi, uint32_t qs, const float (&mc)[P], int q, int lane, int x0, int y0,
+                                          int nsteps, const EdgeLink &el, int &gc, float *tap0, float *tap1,
+                                          long long *dst)
+{
+    (void)dst;
+    const float4 q0 = lds128(qs + 32 * gi), q1 = lds128(qs + 32 * gi + 16);
+    const float qv[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+    float v[P][8];
+#pragma unroll
+    for (int j = 0; j < P; ++j)
+#pragma unroll
+        for (int s = 0; s < 8; ++s)   // tts.py:495: y_square - y_mu_double + (mu_square + const)
+            v[j][s] = __fadd_rn(__fadd_rn(qv[s], __uint_as_float(c[j][s])), mc[j]);
+    if (TAP) {
+#pragma unroll
+        for (int s = 0; s < 8; ++s)
+            if (8 * gi + s < nsteps) {
+                if (tap0) tap0[8 * gi + s] = v[0][s];
+                if (P > 1 && tap1) tap1[8 * gi + s] = v[P - 1][s];
+            }
+    }
+    // my left neighbour's last token at these 8 frames (warp 0: a constant block of -1e9)
+    const uint32_t slot = (uint32_t)gc & 15u;
+    DPSTAT(long long c0 = clock64();)
+    if (q > 0) mbar_wait_s(el.bar_in + slot * 8, (uint32_t)(gc >> 4) & 1u);
+    DPSTAT(dst[1] += clock64() - c0;)
+    const uint32_t ein = el.in + (q > 0 ? slot * 32 : 0);
+    const float4 e0 = lds128(ein), e1 = lds128(ein + 16);
+    const float ev[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
+    uint32_t ga[P];
+#pragma unroll
+    for (int j = 0; j < P; ++j) ga[j] = 0u;
+    float out[8];
+#pragma unroll
+    for (int s = 0; s < 8; ++s) {
+        out[s] = 0.0f;
+        if (FULL || 8 * gi + s < nsteps) {
+            float nxt = 0.0f;
+#pragma unroll
+            for (int j = P - 1; j >= 0; --j) {
+                const float up = (j == 0) ? left : V[j > 0 ? j - 1 : 0];   // V[x-1, y-1]
+                dir_bit(up, V[j], ga[j], 1u << s);
+                float nv = __fadd_rn(fmaxf(up, V[j]), v[j][s]);
+                if (DIAG) nv = (x0 + j <= y0 + 8 * gi + s) ? nv : kNeg;   // x > y: not reachable yet
+                V[j] = nv;
+#ifdef MAS_EXP_NOSHFL   // timing experiment only (wrong results): the recurrence without its cross-lane hop
+                if (j == P - 1) nxt = nv;
+#else
+                if (j == P - 1) nxt = __shfl_up_sync(kFull, nv, 1);        // in flight during the rest
+#endif
+            }
+            left = (lane == 0) ? ev[s] : nxt;
+            out[s] = V[P - 1];
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < P; ++j) acc[j] |= ga[j] << (8 * gi);
+    if (q < 3) {   // publish my last token (lane 31) for the warp on my right
+        if (lane == 31) {
+            sts128(el.out + slot * 32, out[0], out[1], out[2], out[3]);
+            sts128(el.out + slot * 32 + 16, out[4], out[5], out[6], out[7]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive_s(el.bar_out + slot * 8);
+    }
+    ++gc;
+}
+
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// One tile = 32 frames in four groups of 8: the accumulator columns of the next group are in
+// flight (tcgen05.ld into the other register buffer) while a group is processed; the accumulator
+// buffer is released as soon as its last columns are in registers.
+template <int P, bool DIAG, bool FULL, bool TAP>
+__device__ __forceinline__ void tdp_tile(float (&V)[P], uint32_t (&acc)[P], float &left, uint32_t dtm, uint32_t qs,
+                                         const float (&mc)[P], int q, int lane, int x0, int y0, int nsteps,
+                                         const EdgeLink &el, int &gc, uint64_t *d_empty_bar, float *tap0, float *tap1,
+                                         long long *dst)
+{
+    uint32_t ca[P][8], cb[P][8];
+    auto load = [&](uint32_t (&c)[P][8], int gi) {
+#pragma unroll
+        for (int j = 0; j < P; ++j) tmem_ld8(dtm + 32 * j + 8 * gi, c[j]);
+    };
+    auto release = [&]() {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(d_empty_bar);
+    };
+#define TDP_GROUP(c, gi) tdp_group<P, DIAG, FULL, TAP>(V, acc, left, c, gi, qs, mc, q, lane, x0, y0, nsteps, el, gc, tap0, tap1, dst)
+    DPSTAT(long long c0 = clock64();)
+    load(ca, 0);
+    tmem_wait_ld();
+    DPSTAT(dst[0] += clock64() - c0;)
+    if (FULL) {
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {   // two groups per trip: the register buffers alternate without copies
+            load(cb, 2 * h + 1);
+            TDP_GROUP(ca, 2 * h);
+            DPSTAT(c0 = clock64();)
+            tmem_wait_ld();
+            DPSTAT(dst[2] += clock64() - c0;)
+            if (h == 0) load(ca, 2);
+            else release();
+            TDP_GROUP(cb, 2 * h + 1);
+            if (h == 0) tmem_wait_ld();
+        }
+    } else {
+        const int ng = (nsteps + 7) >> 3;
+#pragma unroll 1
+        for (int gi = 0; gi < ng; ++gi) {
+            if (gi + 1 < ng) load(cb, gi + 1);
+            else release();
+            TDP_GROUP(ca, gi);
+            if (gi + 1 < ng) {
+                tmem_wait_ld();
+#pragma unroll
+                for (int j = 0; j < P; ++j)
+#pragma unroll
+                    for (int s = 0; s < 8; ++s) ca[j][s] = cb[j][s];
+            }
+        }
+    }
+#undef TDP_GROUP
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1) mas_prior_tc2_kernel(const PriorTcArgs a)
 {
     extern __shared__ __align__(1024) unsigned char smem[];
     const TcLayout &L = a.lay;
-    const int F = a.F, Fp = L.Fp, T_x = a.T_x, NS = L.nstages, NB = L.nb;
+    const int F = a.F, Fp = L.Fp, T_x = a.T_x, NB = L.nb;
     const int64_t T_y = a.T_y;
-    float *stages = reinterpret_cast<float *>(smem + L.off_stages);
     float *slabs = reinterpret_cast<float *>(smem + L.off_slabs);
     float *staging = reinterpret_cast<float *>(smem + L.off_staging);   // [kTcStage][Fp][32]
     uint32_t *bits_a = reinterpret_cast<uint32_t *>(smem + L.off_bits);
@@ -195,44 +347,33 @@ __global__ void __launch_bounds__(kTcThreads, 1) mas_prior_tc_kernel(const Prior
     uint32_t *zbuf = reinterpret_cast<uint32_t *>(smem + L.off_zero);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + L.off_bars);
     // barrier map
-    uint64_t *ring_full = bars, *ring_empty = bars + 4;
     uint64_t *slab_full = bars + 8, *slab_free = bars + 12;
     uint64_t *d_full = bars + 16, *d_empty = bars + 20;
     uint64_t *a_ready = bars + 24, *a_free = bars + 30;   // [2] each: one pair per 128-token M tile
-    volatile int *ctrl = reinterpret_cast<volatile int *>(bars + 32);   // [0] zdone [1] fwd_done [2] bt_done
+    volatile int *ctrl = reinterpret_cast<volatile int *>(bars + 32);   // [0] zdone [2] bt_done [4..7] fwd_done per DP warp
     uint32_t *tslot = reinterpret_cast<uint32_t *>(bars + 40);
-    uint64_t *edge_full = bars + 26;                            // [4] DP warp 0 -> DP warp 1, per tile
-    float *edge = reinterpret_cast<float *>(bars + 64);         // [4 tiles][32 frames] boundary values
+    uint64_t *edge_bar = bars + 64;                             // [3 links][16 groups]
+    float *edge = reinterpret_cast<float *>(bars + 128);        // [3 links][16 groups][8 frames]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int part_floats = Fp * kTileY;              // one K-major part: [Fp/8 k steps][32 frames][8 features]
     const int slab_floats = 2 * part_floats;          // hi then lo
     const float cst = (float)(-0.5 * 1.8378770664093453 * (double)F);  // -0.5*log(2*pi)*F, tts.py:484
 
-    TileRing ring;
-    ring.stages = stages;
-    ring.full = ring_full;
-    ring.empty = ring_empty;
-    ring.nstages = NS;
-    ring.stage_floats = L.xrows * kTileY;
     if (tid == 0) {
         for (int s = 0; s < 4; ++s) {
-            mbar_init(&ring_full[s], 4);    // the four epilogue warps
-            mbar_init(&ring_empty[s], 2);   // both DP warps
-            mbar_init(&edge_full[s], 1);
             mbar_init(&slab_full[s], 1);
             mbar_init(&slab_free[s], 1);
             mbar_init(&d_full[s], 1);
-            mbar_init(&d_empty[s], 4);
+            mbar_init(&d_empty[s], 4);      // the four DP warps
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&a_ready[i], 4);
             mbar_init(&a_free[i], 1);
         }
-        ctrl[0] = 0;
-        ctrl[1] = 0;
-        ctrl[2] = 0;
-        ctrl[3] = 0;
+        for (int i = 0; i < 48; ++i) mbar_init(&edge_bar[i], 1);
+        for (int i = 0; i < 8; ++i) ctrl[i] = 0;
+        for (int i = 0; i < 8; ++i) edge[384 + i] = kNeg;
         mbar_fence_init();
     }
     for (int i = tid; i < kTcZeroBytes / 4; i += kTcThreads) zbuf[i] = 0u;
@@ -256,63 +397,134 @@ __global__ void __launch_bounds__(kTcThreads, 1) mas_prior_tc_kernel(const Prior
         const bool active = tx >= 1 && ty >= 1 && !degenerate;
         ntiles = active ? (ty + kTileY - 1) / kTileY : 0;
     };
-    // which 128-token M tiles of tile t hold band cells (all of them when the parity tap is on)
+    // tokens per TMEM lane of an utterance, and the M tiles it uses (token x = lane * P + M tile)
+    auto tokens_per_lane = [&](int tx) -> int { return tx > 128 ? 2 : 1; };
     auto tile_mask = [&](int tx, int ty, int t) -> int {
-        const int mt = (tx + 127) >> 7;
-        if (a.lp_out) return (1 << mt) - 1;
-        const int lo = max(0, tx + t * kTileY - ty), hi = min(tx - 1, t * kTileY + kTileY - 1);
-        int m = 0;
-        for (int i = 0; i < mt; ++i)
-            if (128 * i <= hi && 128 * i + 127 >= lo) m |= 1 << i;
-        return m;
+        (void)ty;
+        (void)t;
+        return tokens_per_lane(tx) == 2 ? 3 : 1;
     };
-    volatile int *zdone = ctrl, *fwd_done = ctrl + 1, *bt_done = ctrl + 2, *fwd_done2 = ctrl + 3;
+    volatile int *zdone = ctrl, *bt_done = ctrl + 2, *fwd_done = ctrl + 4;   // fwd_done[4]: one per DP warp
     const bool son = a.stats != nullptr;
     long long *so = son ? a.stats + (size_t)blockIdx.x * 32 : nullptr;
     const int bslots = L.bits_slots;
     auto bits_of = [&](int k) -> uint32_t * { return ((k & 1) && bslots == 2) ? bits_b : bits_a; };
 
-    if (warp == kTcDp || warp == kTcDp2) {
-        // ======================= DP warps: forward recurrence (mas_dp.cuh dp_forward2) =======================
-        const int w = (warp == kTcDp) ? 0 : 1;
-        int g = 0, k = 0;
-        TcStat s_all(son);
-        long long dp_wait = 0;
+    if (warp < 4) {
+        // ======================= DP warps (TMEM lane quarter q = warp) =======================
+        const int q = warp;
+        const int Lg = 32 * q + lane;                       // TMEM lane = global DP lane
+        const uint32_t lane_base = tbase + ((uint32_t)(32 * q) << 16);
+        EdgeLink el;   // [384..391] of `edge`: -1e9, the "left neighbour" of token 0
+        el.in = smem_u32(edge + (q > 0 ? (q - 1) * 128 : 384));
+        el.out = smem_u32(edge + (q < 3 ? q * 128 : 0));
+        el.bar_in = smem_u32(edge_bar + (q > 0 ? (q - 1) * 16 : 0));
+        el.bar_out = smem_u32(edge_bar + (q < 3 ? q * 16 : 0));
+        int g = 0, gc = 0, k = 0, ka = 0;
+        TcStat s_all(son && q == 0), s_w(son && q == 0), s_bt(son && q == 0);
+        long long dpst[3] = {0, 0, 0};   // MAS_TC2_DPSTATS: first ld of a tile, edge waits, later lds
         s_all.begin();
         for (int u = blockIdx.x; u < a.B; u += gridDim.x, ++k) {
             int tx, ty, ntiles;
             bool degenerate;
             geometry(u, tx, ty, ntiles, degenerate);
             if (ntiles > 0) {
+                const int P = tokens_per_lane(tx);
+                const int x0 = Lg * P;
+                s_bt.begin();
                 while (*bt_done < k - bslots + 1) __nanosleep(32);
+                s_bt.end();
                 __threadfence_block();
-                int owns = 0;
-                const float score = prior_forward2_dispatch<XPLMAX, true>(ring, bits_of(k), L.xrows, tx, ty, lane, w, g,
-                                                                    edge, edge_full, &owns,
-                                                                    son ? &dp_wait : nullptr);
-                g += ntiles;
-                if (owns && lane == 0 && a.score) a.score[u] = score;
+                uint32_t *bits = bits_of(k);
+                float V[2] = {kNeg, kNeg}, ms[2] = {0.0f, 0.0f};
+                uint32_t acc[2] = {0u, 0u};
+                float left = (Lg == 0) ? 0.0f : kNeg;       // frame 0: v_prev(x=0) = 0, everything else -1e9
+                const float *msq = musq + (ka % kTcMsq) * 256;
+                for (int t = 0; t < ntiles; ++t, ++g) {
+                    const int b = g % NB;
+                    s_w.begin();
+                    mbar_wait(&d_full[b], (g / NB) & 1);
+                    s_w.end();
+                    tc_fence_after();
+                    if (t == 0) {   // -0.5|mu|^2 + const of my tokens (visible: the movers' arrive precedes the MMAs)
+                        ms[0] = (x0 < tx) ? __fadd_rn(msq[x0], cst) : 0.0f;
+                        ms[1] = (P == 2 && x0 + 1 < tx) ? __fadd_rn(msq[x0 + 1], cst) : 0.0f;
+                    }
+                    const uint32_t dtm = lane_base + L.col_d + b * 64;
+                    const uint32_t qs = smem_u32(ysq + (g % kTcYsq) * kTileY);
+                    const int y0 = t * kTileY;
+                    const int nsteps = min(kTileY, ty - y0);
+                    const bool diag = y0 < tx;
+                    float *tap0 = nullptr, *tap1 = nullptr;
+                    if (a.lp_out) {
+                        if (x0 < tx) tap0 = a.lp_out + ((int64_t)u * T_x + x0) * T_y + y0;
+                        if (P == 2 && x0 + 1 < tx) tap1 = a.lp_out + ((int64_t)u * T_x + x0 + 1) * T_y + y0;
+                    }
+#define TDP_ARGS left, dtm, qs, M, q, lane, x0, y0, nsteps, el, gc, &d_empty[b], tap0, tap1, dpst
+                    if (P == 2) {
+                        float(&W)[2] = V;
+                        uint32_t(&A)[2] = acc;
+                        const float(&M)[2] = ms;
+                        if (a.lp_out) tdp_tile<2, true, false, true>(W, A, TDP_ARGS);
+                        else if (nsteps != kTileY) tdp_tile<2, true, false, false>(W, A, TDP_ARGS);
+                        else if (diag) tdp_tile<2, true, true, false>(W, A, TDP_ARGS);
+                        else tdp_tile<2, false, true, false>(W, A, TDP_ARGS);
+                    } else {
+                        float(&W)[1] = *reinterpret_cast<float(*)[1]>(&V[0]);
+                        uint32_t(&A)[1] = *reinterpret_cast<uint32_t(*)[1]>(&acc[0]);
+                        const float(&M)[1] = *reinterpret_cast<const float(*)[1]>(&ms[0]);
+                        if (a.lp_out) tdp_tile<1, true, false, true>(W, A, TDP_ARGS);
+                        else if (nsteps != kTileY) tdp_tile<1, true, false, false>(W, A, TDP_ARGS);
+                        else if (diag) tdp_tile<1, true, true, false>(W, A, TDP_ARGS);
+                        else tdp_tile<1, false, true, false>(W, A, TDP_ARGS);
+                    }
+#undef TDP_ARGS
+                    // x == y always steps down (core.pyx:34 `index == y`), token 0 never does.
+                    if (diag) {
+#pragma unroll
+                        for (int j = 0; j < 2; ++j)
+                            if (j < P && ((x0 + j) >> 5) == t) acc[j] |= 1u << ((x0 + j) & 31);
+                    }
+                    if (Lg == 0) acc[0] = 0u;
+                    uint32_t *dst = bits + (size_t)t * L.xrows + Lg;
+                    dst[0] = acc[0];
+                    acc[0] = 0u;
+                    if (P == 2) {
+                        dst[128] = acc[1];
+                        acc[1] = 0u;
+                    }
+                }
+                // total alignment score: token tx-1 = lane (tx-1)/P, slot (tx-1)%P
+                const int ql = (tx - 1) / P, qj = (tx - 1) - ql * P;
+                if (Lg == ql && a.score) a.score[u] = V[qj];
+                ++ka;
             }
             __threadfence_block();
             __syncwarp();
-            if (lane == 0) *(w == 0 ? fwd_done : fwd_done2) = k + 1;
+            if (lane == 0) fwd_done[q] = k + 1;
         }
         s_all.end();
-        if (son && lane == 0 && w == 0) { so[0] = s_all.acc; so[1] = dp_wait; so[2] = g; so[3] = k; }
-        if (son && lane == 0 && w == 1) { so[26] = s_all.acc; so[27] = dp_wait; }
+        if (son && lane == 0 && q == 0) { so[0] = s_all.acc; so[1] = s_w.acc; so[2] = g; so[3] = k; so[28] = s_bt.acc; }
+        DPSTAT(if (son && lane == 0 && (q == 0 || q == 3)) { long long *d = so + (q == 0 ? 13 : 16); d[0] = dpst[0]; d[1] = dpst[1]; d[2] = dpst[2]; })
     } else if (warp == kTcBack) {
         // ======================= backtrack warp =======================
         int k = 0;
+        TcStat b_bt(son), b_w(son), b_out(son);
         for (int u = blockIdx.x; u < a.B; u += gridDim.x, ++k) {
             int tx, ty, ntiles;
             bool degenerate;
             geometry(u, tx, ty, ntiles, degenerate);
             for (int x = lane; x < T_x; x += 32) dur[x] = 0;
-            while (*fwd_done <= k || *fwd_done2 <= k) __nanosleep(32);
+            b_w.begin();
+            while (fwd_done[0] <= k || fwd_done[1] <= k || fwd_done[2] <= k || fwd_done[3] <= k) __nanosleep(32);
+            b_w.end();
+            b_bt.begin();
             __threadfence_block();
             __syncwarp();
             if (ntiles > 0) {
-                if (lane == 0) backtrack_bits(bits_of(k), L.xrows, tx, ty, first, dur, true, 6);
+#ifndef MAS_EXP_NOBACK   // (timing experiment only when defined: no path)
+                if (lane == 0) backtrack_bits(bits_of(k), L.xrows, tx, ty, first, dur, true, 7);
+#endif
             } else if (degenerate) {
                 if (lane == 0) {  // reference semantics for t_x > t_y: raw prior values (mas_dp.cuh)
                     const float *mub = a.mu_x + (int64_t)u * F * T_x;
@@ -327,6 +539,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) mas_prior_tc_kernel(const Prior
             __threadfence_block();
             __syncwarp();
             if (lane == 0) *bt_done = k + 1;
+            b_bt.end();
+            b_out.begin();
             if (a.path) {
                 while (*zdone <= k) __nanosleep(64);
                 __threadfence_block();
@@ -337,7 +551,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) mas_prior_tc_kernel(const Prior
             write_frame_idx(a.frame_idx ? a.frame_idx + (int64_t)u * T_y : nullptr, first, dur, T_x, ty, a.T_y,
                             lane, 32);
             __syncwarp();
+            b_out.end();
         }
+        if (son && lane == 0) { so[29] = b_bt.acc; so[30] = b_w.acc; so[31] = b_out.acc; }
     } else if (warp == kTcLoader || warp == kTcLoader2) {
         // ======================= slab loader =======================
         // y[:, 32t..32t+31] -> staging buffer in shared memory (cp.async, 16-byte pieces, the natural
@@ -361,6 +577,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) mas_prior_tc_kernel(const Prior
             const float *st = staging + (size_t)(gg & 1) * Fp * kTileY + 4 * c;   // tile parity == owning loader
             float *hi = slabs + (size_t)(gg % kTcSlabs) * slab_floats, *lo = hi + part_floats;
             float q0 = 0.0f, q1 = 0.0f, q2 = 0.0f, q3 = 0.0f;   // frames 4c .. 4c+3
+#ifdef MAS_EXP_NOLOADERPASS   // timing experiment only (wrong results)
+            if (gg < 0)
+#endif
 #pragma unroll 1
             for (int fg = r; 4 * fg < Fp; fg += 4) {   // feature group: features 4fg .. 4fg+3
                 const float *sp = st + (fg << 7);
@@ -486,7 +705,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mas_prior_tc_kernel(const Prior
                 // refill one half of TMEM while the other is still (or already) being multiplied
                 bool a_ok[2] = {false, false}, a_rel[2] = {false, false};
                 // last tile whose band still reaches into M tile 0 (tokens < 128)
-                const int t0_last = a.lp_out ? ntiles - 1 : min(ntiles - 1, (127 - tx + ty) >> 5);   // tap: every tile
+                const int t0_last = ntiles - 1;   // tokens are interleaved over the M tiles: both live to the end
                 for (int t = 0; t < ntiles;) {
                     // a pair of tiles (g, g+1): up to four independent accumulators in flight
                     // (accumulator c = 2*e + i: tile e of the pair, M tile i); everything the issue
@@ -540,12 +759,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) mas_prior_tc_kernel(const Prior
                         constexpr int KS = decltype(ks_tag)::value;   // 0 = run-time k-step count (rolled loop)
                         const int nk = KS ? KS : ksteps;
 #pragma unroll
-                        for (int pass = 0; pass < 3; ++pass) {
+                        for (int pass = kExpPass0; pass < 3; ++pass) {
                             const uint32_t abase = (pass == 0) ? alo0 : ahi0;
                             const uint64_t b0 = (pass == 1) ? bl[0] : bh[0], b1 = (pass == 1) ? bl[1] : bh[1];
 #pragma unroll
                             for (int j = 0; j < nk; ++j) {
-                                const uint32_t acc = (pass | j) != 0;
+                                const uint32_t acc = ((pass - kExpPass0) | j) != 0;
                                 const uint32_t ac = abase + 8 * j;
                                 const uint32_t bo = (uint32_t)(64 * j);
                                 const uint64_t d0 = b0 + bo, d1 = b1 + bo;
@@ -607,12 +826,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) mas_prior_tc_kernel(const Prior
             bool degenerate;
             geometry(u, tx, ty, ntiles, degenerate);
             if (ntiles == 0) continue;
-            const int mt = (tx + 127) >> 7;
+            const int P = tokens_per_lane(tx);
             const float *mub = a.mu_x + (int64_t)u * F * T_x;
             float *msq = musq + (ka % kTcMsq) * 256;
             for (int i = 0; i < 2; ++i) {
-                const bool any = i < mt && 128 * i + 32 * q < tx;   // some of this warp's tokens exist
-                const int x = 128 * i + 32 * q + lane;
+                const bool any = i < P && (32 * q) * P + i < tx;   // some of this warp's tokens exist
+                const int x = (32 * q + lane) * P + i;         // token of (M tile i, TMEM lane 32q + lane)
                 const bool xv = x < tx;
                 // every feature of "my" token into registers: all loads in flight at once, issued
                 // while the previous utterance is still being multiplied
@@ -658,100 +877,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) mas_prior_tc_kernel(const Prior
         }
         a_all.end();
         if (aon && lane == 0) { so[19] = a_all.acc; so[20] = a_ld.acc; so[21] = a_w.acc; so[22] = a_st.acc; }
-    } else {
-        // ======================= epilogue warps (TMEM lane quarter q = warp) =======================
-        const int q = warp;
-        const uint32_t lane_base = tbase + ((uint32_t)(32 * q) << 16);
-        int g = 0, ka = 0;
-        const bool eon = son && q == 0;
-        TcStat e_all(eon), e_df(eon), e_re(eon), e_w(eon);
-        e_all.begin();
-        for (int u = blockIdx.x; u < a.B; u += gridDim.x) {
-            int tx, ty, ntiles;
-            bool degenerate;
-            geometry(u, tx, ty, ntiles, degenerate);
-            if (ntiles == 0) continue;
-            const RowMap rm(tx, 6);
-            const float *msq = musq + (ka % kTcMsq) * 256;
-            for (int t = 0; t < ntiles; ++t, ++g) {
-                const int b = g % NB, sidx = g % NS;
-                const int mask = tile_mask(tx, ty, t);
-                e_df.begin();
-                mbar_wait_relaxed(&d_full[b], (g / NB) & 1, 32);
-                e_df.end();
-                tc_fence_after();
-                e_w.begin();
-                uint32_t acc[2][32];
-                bool have[2];
-#pragma unroll
-                for (int i = 0; i < 2; ++i) {
-                    have[i] = (mask >> i & 1) && (128 * i + 32 * q < tx);
-                    if (have[i]) tmem_ld32(lane_base + L.col_d + (b * 2 + i) * 32, acc[i]);
-                }
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&d_empty[b]);       // accumulator buffer free again
-                e_w.end();
-                e_re.begin();
-                if (g >= NS) mbar_wait_relaxed(&ring_empty[sidx], ((g / NS) - 1) & 1, 32);  // DP consumed tile g-NS
-                e_re.end();
-                e_w.begin();
-                const float *qs = ysq + (g % kTcYsq) * kTileY;
-                float *tile = stages + (size_t)sidx * ring.stage_floats;
-                const int y0 = t * kTileY;
-#pragma unroll
-                for (int i = 0; i < 2; ++i) {
-                    if (!have[i]) continue;
-                    const int x = 128 * i + 32 * q + lane;
-                    if (x >= tx) continue;
-                    const float ms = msq[x];
-                    const int pr = rm.row(x);
-                    float *row = tile + (pr << 5);
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) {
-                        const float4 qq = *reinterpret_cast<const float4 *>(qs + 4 * c);
-                        float4 o;
-                        // tts.py:495: y_square - y_mu_double + mu_square + const
-                        o.x = ((qq.x + __uint_as_float(acc[i][4 * c + 0])) + ms) + cst;
-                        o.y = ((qq.y + __uint_as_float(acc[i][4 * c + 1])) + ms) + cst;
-                        o.z = ((qq.z + __uint_as_float(acc[i][4 * c + 2])) + ms) + cst;
-                        o.w = ((qq.w + __uint_as_float(acc[i][4 * c + 3])) + ms) + cst;
-                        *reinterpret_cast<float4 *>(row + ((c ^ (pr & 7)) << 2)) = o;
-                    }
-                }
-                if (a.lp_out) {   // parity tap (cold path): copy this warp's rows of the tile to HBM
-                    __syncwarp();
-                    for (int i = 0; i < 2; ++i) {
-                        const int x = 128 * i + 32 * q + lane;
-                        if (!have[i] || x >= tx) continue;
-                        const int pr = rm.row(x);
-                        const float *row = tile + (pr << 5);
-                        float *tap = a.lp_out + ((int64_t)u * T_x + x) * T_y + y0;
-                        for (int e = 0; e < kTileY && y0 + e < ty; ++e) tap[e] = row[(((e >> 2) ^ (pr & 7)) << 2) + (e & 3)];
-                    }
-                }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&ring_full[sidx]);   // this warp's rows of tile g are written
-                e_w.end();
-            }
-            ++ka;
-        }
-        e_all.end();
-        if (eon && lane == 0) { so[13] = e_all.acc; so[16] = e_df.acc; so[17] = e_re.acc; so[18] = e_w.acc; }
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tbase), "r"(kTcTmemCols));
 }
 
-cudaError_t launch_from_prior_tc(const PriorTcArgs &a, cudaStream_t st)
+cudaError_t launch_from_prior_tc2(const PriorTcArgs &a, cudaStream_t st)
 {
-    const int xplmax = (a.T_x + 63) / 64;   // tokens per lane of the two DP warps
-    void (*k)(const PriorTcArgs) = nullptr;
-    if (xplmax <= 2) k = mas_prior_tc_kernel<2>;
-    else if (xplmax <= 3) k = mas_prior_tc_kernel<3>;
-    else k = mas_prior_tc_kernel<4>;
+    void (*k)(const PriorTcArgs) = mas_prior_tc2_kernel;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a.lay.total);
     if (e != cudaSuccess) return e;
     if (a.lp_out) {

@@ -296,15 +296,27 @@ def test_fused_matches_reference_model_capture(cuda, fname):
         assert (fi[b, y_len[b]:] == -1).all()
 
 
-ENGINES = {"auto": 0, "cuda_core": 16, "tensor_core": 32}   # MAS_FLAG_NO_TENSOR / MAS_FLAG_FORCE_TENSOR
+# MAS_FLAG_NO_TENSOR / MAS_FLAG_FORCE_TENSOR; "tensor_core_tmem_dp" = the experimental engine of
+# csrc/mas_prior_tc2.cu (DP warps read the accumulators straight from tensor memory), opt-in by
+# environment (MAS_PRIOR_TC2=1, read on every call)
+ENGINES = {"auto": 0, "cuda_core": 16, "tensor_core": 32, "tensor_core_tmem_dp": 32}
+
+
+def select_engine(monkeypatch, engine):
+    if engine == "tensor_core_tmem_dp":
+        monkeypatch.setenv("MAS_PRIOR_TC2", "1")
+    else:
+        monkeypatch.delenv("MAS_PRIOR_TC2", raising=False)
+    return ENGINES[engine]
 
 
 @pytest.mark.parametrize("engine", list(ENGINES))
 @pytest.mark.parametrize("F,B,T_x,T_y,seed", [(16, 32, 160, 512, 1), (80, 16, 190, 870, 2),
                                               (80, 3, 33, 95, 3), (7, 2, 5, 40, 4)])
-def test_fused_vs_oracle_configs(cuda, F, B, T_x, T_y, seed, engine):
-    """BASELINE config 2 (articulatory, F=16, ragged) and the LJSpeech shape (F=80), through both
+def test_fused_vs_oracle_configs(cuda, F, B, T_x, T_y, seed, engine, monkeypatch):
+    """BASELINE config 2 (articulatory, F=16, ragged) and the LJSpeech shape (F=80), through the
     engines of the fused kernel: fp32 FMA on CUDA cores and 3xTF32 on the tensor cores."""
+    select_engine(monkeypatch, engine)
     rng = np.random.default_rng(seed)
     x_len = rng.integers(max(1, T_x // 8), T_x + 1, B).astype(np.int32)
     y_len = np.minimum(T_y, 3 * x_len + rng.integers(0, 61, B)).astype(np.int32)
@@ -329,10 +341,12 @@ def test_fused_vs_oracle_configs(cuda, F, B, T_x, T_y, seed, engine):
     assert torch.equal(p2, path) and torch.equal(d2, dur)
 
 
+@pytest.mark.parametrize("engine", ["tensor_core", "tensor_core_tmem_dp"])
 @pytest.mark.parametrize("T_x", [1, 31, 32, 33, 63, 64, 65, 127, 128, 129, 191, 192, 255, 256, 257])
-def test_tensor_core_engine_token_axis_edges(cuda, T_x):
+def test_tensor_core_engine_token_axis_edges(cuda, T_x, engine, monkeypatch):
     """Token counts around every ownership boundary of the tensor-core kernel: 32 lanes x 2 DP
     warps (64), the 128-token M tile, and its 256-token limit (257 falls back to CUDA cores)."""
+    select_engine(monkeypatch, engine)
     rng = np.random.default_rng(100 + T_x)
     B, F = 5, 24
     T_y = max(T_x + 40, 3 * T_x // 2)
@@ -462,11 +476,12 @@ def test_entry_points_are_cuda_graph_capturable_and_stream_ordered(cuda):
         assert torch.equal(a, b)
 
 
-@pytest.mark.parametrize("engine", ["cuda_core", "tensor_core"])
-def test_fused_degenerate_and_empty_utterances(cuda, engine):
+@pytest.mark.parametrize("engine", ["cuda_core", "tensor_core", "tensor_core_tmem_dp"])
+def test_fused_degenerate_and_empty_utterances(cuda, engine, monkeypatch):
     """Empty utterances (t_x == 0 or t_y == 0: all-zero path, like the reference's all-zero mask),
     t_x == t_y (pure diagonal), t_x == 1, and the reference's degenerate t_x > t_y case (backtrack
     over raw prior values) in the middle of a batch of normal ones."""
+    select_engine(monkeypatch, engine)
     rng = np.random.default_rng(31)
     B, F, T_x, T_y = 8, 40, 20, 64
     x_len = np.array([0, 5, 9, 1, 7, 3, 20, 12], np.int32)
