@@ -57,11 +57,18 @@ __device__ __forceinline__ float f4_get(const float4 &v)
     return v.w;
 }
 
+// direction bit of one cell: acc |= bit when up > cur (the comparison of core.pyx:30), as FSETP +
+// a predicated integer op that sit beside the value chain, not in it
+__device__ __forceinline__ void dir_bit(float up, float cur, uint32_t &acc, uint32_t bit)
+{
+    asm("{\n\t.reg .pred p;\n\tsetp.gt.f32 p, %1, %2;\n\t@p or.b32 %0, %0, %3;\n\t}" : "+r"(acc) : "f"(up), "f"(cur), "r"(bit));
+}
+
 // One frame.  `v[j]` is value[x_j, y]; `bit` = 1 << (y & 31); `left` is the left lane's last
 // token at frame y-1 (lane 0: the x == 0 boundary of core.pyx:23-27) and is replaced by the
 // value for frame y.  Tokens are updated from the lane's last to its first so that V[j-1]
 // is still the previous frame's value when token j reads it.
-template <int XPL, bool DIAG>
+template <int XPL, bool DIAG, bool FMAX = false>   // FMAX: see dp_step2
 __device__ __forceinline__ void dp_step(float (&V)[XPL], uint32_t (&acc)[XPL],
                                         const float (&v)[XPL], float &left, int lane, int x0,
                                         int y, uint32_t bit)
@@ -70,11 +77,17 @@ __device__ __forceinline__ void dp_step(float (&V)[XPL], uint32_t (&acc)[XPL],
 #pragma unroll
     for (int j = XPL - 1; j >= 0; --j) {
         const float up = (j == 0) ? left : V[j > 0 ? j - 1 : 0];   // V[x-1, y-1]
-        const bool take_prev = up > V[j];                          // core.pyx:30 max()
-        const float m = take_prev ? up : V[j];
+        float m;
+        if (FMAX) {
+            dir_bit(up, V[j], acc[j], bit);
+            m = fmaxf(up, V[j]);
+        } else {
+            const bool take_prev = up > V[j];                      // core.pyx:30 max()
+            m = take_prev ? up : V[j];
+            if (take_prev) acc[j] |= bit;
+        }
         float nv = __fadd_rn(m, v[j]);
         if (DIAG) nv = (x0 + j <= y) ? nv : kNeg;                  // x > y: not reachable yet
-        if (take_prev) acc[j] |= bit;
         V[j] = nv;
         if (j == XPL - 1) nxt = __shfl_up_sync(kFull, nv, 1);      // in flight during the rest
     }
@@ -83,7 +96,7 @@ __device__ __forceinline__ void dp_step(float (&V)[XPL], uint32_t (&acc)[XPL],
 
 // One staged tile of up to 32 frames (frames y0 .. y0+nsteps-1, y0 % 32 == 0).
 // `stage` is the swizzled [row][32 frames] tile in shared memory (see tile_index()).
-template <int XPL, bool DIAG, bool FULL>
+template <int XPL, bool DIAG, bool FULL, bool FMAX = false>
 __device__ __forceinline__ void dp_tile(float (&V)[XPL], uint32_t (&acc)[XPL], float &left,
                                         const float *__restrict__ stage, int lane, int x0, int y0,
                                         int nsteps)
@@ -102,21 +115,21 @@ __device__ __forceinline__ void dp_tile(float (&V)[XPL], uint32_t (&acc)[XPL], f
         float v[XPL];
 #pragma unroll
         for (int j = 0; j < XPL; ++j) v[j] = f4_get<0>(vv[j]);
-        dp_step<XPL, DIAG>(V, acc, v, left, lane, x0, y0 + s0, 1u << s0);
+        dp_step<XPL, DIAG, FMAX>(V, acc, v, left, lane, x0, y0 + s0, 1u << s0);
         if (FULL || s0 + 1 < nsteps) {
 #pragma unroll
             for (int j = 0; j < XPL; ++j) v[j] = f4_get<1>(vv[j]);
-            dp_step<XPL, DIAG>(V, acc, v, left, lane, x0, y0 + s0 + 1, 2u << s0);
+            dp_step<XPL, DIAG, FMAX>(V, acc, v, left, lane, x0, y0 + s0 + 1, 2u << s0);
         }
         if (FULL || s0 + 2 < nsteps) {
 #pragma unroll
             for (int j = 0; j < XPL; ++j) v[j] = f4_get<2>(vv[j]);
-            dp_step<XPL, DIAG>(V, acc, v, left, lane, x0, y0 + s0 + 2, 4u << s0);
+            dp_step<XPL, DIAG, FMAX>(V, acc, v, left, lane, x0, y0 + s0 + 2, 4u << s0);
         }
         if (FULL || s0 + 3 < nsteps) {
 #pragma unroll
             for (int j = 0; j < XPL; ++j) v[j] = f4_get<3>(vv[j]);
-            dp_step<XPL, DIAG>(V, acc, v, left, lane, x0, y0 + s0 + 3, 8u << s0);
+            dp_step<XPL, DIAG, FMAX>(V, acc, v, left, lane, x0, y0 + s0 + 3, 8u << s0);
         }
     }
 }
@@ -136,7 +149,7 @@ struct TileRing {
 // returns V[t_x-1, t_y-1].  Requires 1 <= t_x <= t_y and XPL == ceil(t_x/32).
 // `g0` = index (in the ring's lifetime) of this utterance's first tile: a persistent CTA keeps
 // one ring and its barrier phases running across utterances.
-template <int XPL>
+template <int XPL, bool FMAX = false>
 __device__ __noinline__ float dp_forward(const TileRing ring, uint32_t *bits, int xrows, int tx,
                                          int ty, int lane, int g0 = 0, long long *wait_acc = nullptr)
 {
@@ -165,10 +178,10 @@ __device__ __noinline__ float dp_forward(const TileRing ring, uint32_t *bits, in
         const int nsteps = min(kTileY, ty - y0);
         const bool diag = y0 < tx;  // some token x > y still exists in this tile
         if (nsteps == kTileY) {
-            if (diag) dp_tile<XPL, true, true>(V, acc, left, tile, lane, x0, y0, nsteps);
-            else dp_tile<XPL, false, true>(V, acc, left, tile, lane, x0, y0, nsteps);
+            if (diag) dp_tile<XPL, true, true, FMAX>(V, acc, left, tile, lane, x0, y0, nsteps);
+            else dp_tile<XPL, false, true, FMAX>(V, acc, left, tile, lane, x0, y0, nsteps);
         } else {
-            dp_tile<XPL, true, false>(V, acc, left, tile, lane, x0, y0, nsteps);
+            dp_tile<XPL, true, false, FMAX>(V, acc, left, tile, lane, x0, y0, nsteps);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&ring.empty[stage]);
@@ -341,13 +354,6 @@ __device__ __forceinline__ void write_frame_idx(int32_t *fi, const int *first, c
 // Warp 0 cannot lap warp 1 by more than the tile ring's depth (<= 3), so the 4-tile edge ring
 // needs no back-pressure of its own.  Tiles use the row map RowMap(tx, 6).
 // ------------------------------------------------------------------------------------
-// direction bit of one cell: acc |= bit when up > cur (the comparison of core.pyx:30), as FSETP +
-// a predicated integer op that sit beside the value chain, not in it
-__device__ __forceinline__ void dir_bit(float up, float cur, uint32_t &acc, uint32_t bit)
-{
-    asm("{\n\t.reg .pred p;\n\tsetp.gt.f32 p, %1, %2;\n\t@p or.b32 %0, %0, %3;\n\t}" : "+r"(acc) : "f"(up), "f"(cur), "r"(bit));
-}
-
 // FMAX = the formulation of the fused kernels: the value chain is FMNMX + FADD (10 cycles per
 // token instead of 14 for FSETP + FSEL + FADD, profiles/microbench/dp_chain.cu) and the direction
 // bit comes from the same comparison beside the chain.  max(up, cur) is the reference's
@@ -536,7 +542,7 @@ __device__ __forceinline__ float lp_cell(const float *mub, const float *yb, int 
     return ((-0.5f * ysq + c) + -0.5f * msq) + cst;
 }
 
-template <int XPLMAX>
+template <int XPLMAX, bool FMAX = false>
 __device__ __forceinline__ float prior_forward_dispatch(const TileRing &ring, uint32_t *bits,
                                                         int xrows, int tx, int ty, int lane, int g0,
                                                         long long *wacc)
@@ -544,7 +550,7 @@ __device__ __forceinline__ float prior_forward_dispatch(const TileRing &ring, ui
     const int xpl = (tx + 31) >> 5;
 #define MAS_CASE(N)                                                                           \
     case N:                                                                                   \
-        if constexpr (N <= XPLMAX) return dp_forward<N>(ring, bits, xrows, tx, ty, lane, g0, wacc); \
+        if constexpr (N <= XPLMAX) return dp_forward<N, FMAX>(ring, bits, xrows, tx, ty, lane, g0, wacc); \
         break;
     switch (xpl) {
         MAS_CASE(1) MAS_CASE(2) MAS_CASE(3) MAS_CASE(4) MAS_CASE(5) MAS_CASE(6) MAS_CASE(7)

@@ -270,7 +270,7 @@ __global__ void __launch_bounds__(kPriorThreads) mas_prior_kernel(const PriorArg
                 __threadfence_block();
                 st_w.end();
                 st_fwd.begin();
-                score = prior_forward_dispatch<XPLMAX>(ring, bits_of(u, k), L.xrows, tx, ty, lane, g,
+                score = prior_forward_dispatch<XPLMAX, true>(ring, bits_of(u, k), L.xrows, tx, ty, lane, g,
                                                        a.stats ? &dp_wait : nullptr);
                 g += ntiles;
                 st_fwd.end();
