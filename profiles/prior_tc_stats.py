@@ -55,3 +55,14 @@ print(f"slowest CTA: DP warp 0 total {t[:, 0].max():.0f} cyc (mean {t[:, 0].mean
 for i, n in names.items():
     v = t[:, i]
     print(f"{n:36s} {v.mean():12.0f} cyc  per tile {v.mean() / tiles:8.0f}")
+if os.environ.get("MAS_STATS_PER_CTA"):
+    tot = t[:, 0]
+    print("per-CTA DP warp 0 total, percentiles 0/25/50/75/100:", np.percentile(tot, [0, 25, 50, 75, 100]).astype(int))
+    print("utterances per CTA:", np.bincount(t[:, 3].astype(int)))
+    tl = t[:, 2]
+    print("tiles per CTA, percentiles 0/25/50/75/100:", np.percentile(tl, [0, 25, 50, 75, 100]).astype(int))
+    print("cycles per tile by CTA, percentiles:", np.percentile(tot / tl, [0, 25, 50, 75, 100]).astype(int))
+    print("correlation(total, tiles) =", round(float(np.corrcoef(tot, tl)[0, 1]), 3))
+    order = np.argsort(tot)
+    print("slowest CTAs (index in launch order, tiles, cycles):", [(int(i), int(tl[i]), int(tot[i])) for i in order[-6:]])
+    print("fastest CTAs:", [(int(i), int(tl[i]), int(tot[i])) for i in order[:6]])
