@@ -44,7 +44,7 @@ tiles = t[:, 2].mean()
 print(f"{len(t)} CTAs; utterances/CTA {t[:, 3].mean():.2f}; tiles/CTA {tiles:.1f}")
 names = {0: "DP warp 0 total", 1: "  starved of tiles", 28: "  waiting for a free bit buffer (backtrack)",
          29: "backtrack warp: backtrack", 30: "backtrack warp: waiting for forward", 31: "backtrack warp: outputs (+ wait zero fill)", 26: "DP warp 1 total", 27: "  starved (tiles / warp 0)",
-         4: "loader total", 5: "  wait slab free (MMA done)", 6: "  finish slab (split + ysq)", 7: "  cp.async wait", 23: "    finish: staged -> registers", 24: "    finish: proxy fence + arrive", 25: "  cp.async issue (+ L2 prefetch)", 
+         4: "loader total", 5: "  wait slab free (MMA done)", 6: "  finish slab (split + ysq)", 7: "  cp.async wait", 23: "    finish: staged -> registers", 24: "    finish: proxy fence + arrive", 25: "  cp.async issue", 
          8: "MMA lane total", 9: "  wait A ready (mu_x -> TMEM)", 10: "  wait slab full", 11: "  wait D buffer empty", 12: "  issue + commit",
          13: "epilogue warp0 total", 16: "  wait D full", 17: "  wait ring stage empty", 18: "  ld + adds + store",
          19: "mu_x mover warp0 total", 20: "  global loads (issue)", 21: "  wait A free (prev MMAs done)", 22: "  split + tcgen05.st", 14: "  zero fill of the dense path (a quarter)"}
