@@ -58,8 +58,11 @@ def parse():
     ap.add_argument("--no-dropin", action="store_true")
     ap.add_argument("--e2e-chunk", type=int, default=0, help="utterances per H2D chunk (0 = library default)")
     ap.add_argument("--e2e-no-trim", action="store_true", help="copy whole padded rows")
-    ap.add_argument("--gather", default="overlap", choices=["overlap", "serial"],
-                    help="N>1: all-gather of step i on a side stream under the kernel of step i+1, or in line")
+    # default "serial": measured on 2 GPUs, the overlapped gather is 3 % faster when it works (0.347 vs
+    # 0.357 ms) but the fused kernel is persistent with one CTA per SM, and whenever the collective's CTAs
+    # still hold an SM at the next launch the CTAs that do not fit run as a second wave (0.78-1.6 ms observed)
+    ap.add_argument("--gather", default="serial", choices=["overlap", "serial"],
+                    help="N>1: all-gather of step i in line after its kernel, or on a side stream under the kernel of step i+1")
     ap.add_argument("--reserve-sms", type=int, default=-1,
                     help="SMs the persistent kernel leaves to the overlapped collective (default 0: measured "
                          "at N=8, reserving 8 SMs costs 8%% and the gather overlaps anyway)")
