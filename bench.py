@@ -377,7 +377,8 @@ def run_ours(args):
         pass
     roofline = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
                 "frac": ach / hbm_peak, "traffic": traffic, "peak_source": peak_src,
-                "kernel": kname, "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg_bytes}
+                "kernel": kname, "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg_bytes,
+                "frac_of_nominal_8tbs": ach / 8000.0}   # also quoted against the nominal ~8 TB/s
     if args.op == "fused" and tensor_engine:
         roofline["engine"] = ("tcgen05.mma kind::tf32, 3xTF32 split (fp32-level accuracy), mu_x in TMEM; "
                               "the CUDA-core engine (--engine cuda) is the fp32 FMA variant")
