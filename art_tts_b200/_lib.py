@@ -38,6 +38,7 @@ EXPORTS = (
     "mas_frame_index", "mas_duration_loss_f32", "mas_crop_f32", "mas_path_segment",
     "mas_align_workspace_bytes", "mas_align_gather_f32", "mas_align_gather_bwd_f32",
     "mas_from_prior_host_f32", "mas_set_sm_reserve",
+    "mas_set_peer_durations", "mas_peer_durations_supported",
 )
 
 _lib = None
@@ -104,6 +105,10 @@ def load() -> ctypes.CDLL:
                                             ci, ci, ci, ci, vp, sz, ci, ci, vp, vp]
     lib.mas_set_sm_reserve.restype = ci
     lib.mas_set_sm_reserve.argtypes = [ci]
+    lib.mas_set_peer_durations.restype = ci
+    lib.mas_set_peer_durations.argtypes = [ci, ctypes.POINTER(ctypes.c_uint64), ctypes.c_int64]
+    lib.mas_peer_durations_supported.restype = ci
+    lib.mas_peer_durations_supported.argtypes = [ci, ci, ci, ci, ci]
     if lib.mas_abi_version() != 1:
         raise MasError("libmas_sm100.so ABI version mismatch; rebuild it")
     _lib = lib

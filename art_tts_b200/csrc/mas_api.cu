@@ -3,6 +3,7 @@
 // plan selection, launches.  No allocation, no host synchronisation, no CPU fallback.
 #include <algorithm>
 #include <atomic>
+#include <mutex>
 #include <cstdlib>
 #include <initializer_list>
 
@@ -131,6 +132,35 @@ const char *mas_strerror(int code)
 }
 
 uint64_t mas_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+namespace {
+std::mutex g_peer_mu;
+int g_npeer = 0;
+uint64_t g_peer[mas::kMaxPeers];
+long long g_peer_row0 = 0;
+}  // namespace
+
+int mas_peer_durations_supported(int B, int F, int T_x, int T_y, int flags)
+{
+    (void)B;
+    if (T_x < 1 || T_y < 1 || F < 1) return 0;
+    if (!env_int("MAS_PRIOR_TC", 1) || env_int("MAS_PRIOR_TC2", 0)) return 0;
+    if (flags & (MAS_FLAG_FORCE_GENERAL | MAS_FLAG_SPILL_BITS | MAS_FLAG_NO_TENSOR)) return 0;
+    const mas::TcLayout lay = mas::tc_layout(F, T_x, T_y);
+    return (lay.ok && (F >= env_int("MAS_PRIOR_TC_MIN_F", 32) || (flags & MAS_FLAG_FORCE_TENSOR))) ? 1 : 0;
+}
+
+int mas_set_peer_durations(int n_peers, const uint64_t *peer_ptrs, int64_t row0)
+{
+    if (n_peers < 0 || n_peers > mas::kMaxPeers || (n_peers > 0 && !peer_ptrs) || row0 < 0) return MAS_ERR_SHAPE;
+    for (int i = 0; i < n_peers; ++i)
+        if (!peer_ptrs[i] || peer_ptrs[i] % 4) return MAS_ERR_ALIGN;
+    std::lock_guard<std::mutex> lk(g_peer_mu);
+    g_npeer = n_peers;
+    for (int i = 0; i < n_peers; ++i) g_peer[i] = peer_ptrs[i];
+    g_peer_row0 = row0;
+    return MAS_OK;
+}
 
 int mas_set_sm_reserve(int n_sms)
 {
@@ -299,6 +329,13 @@ int mas_from_prior_f32(const float *mu_x, const float *logs, const float *y, con
             t.T_y = T_y;
             t.path_esize = path ? esize : 4;
             t.one = one_pattern(path_dtype);
+            t.npeer = 0;
+            if (!tc2) {   // fused all-gather of the durations over peer memory (mas_set_peer_durations)
+                std::lock_guard<std::mutex> lk(g_peer_mu);
+                t.npeer = g_npeer;
+                for (int i = 0; i < g_npeer; ++i) t.peer[i] = reinterpret_cast<int32_t *>(g_peer[i]);
+                t.peer_row0 = g_peer_row0 + t_peer_row_extra;
+            }
             return (int)(tc2 ? launch_from_prior_tc2(t, st) : launch_from_prior_tc(t, st));
         }
     }

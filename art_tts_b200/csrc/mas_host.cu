@@ -49,6 +49,9 @@ inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
 }  // namespace
 
+// first utterance of the chunk being launched: added to the peer rows of mas_set_peer_durations (mas_api.cu)
+thread_local long long t_peer_row_extra = 0;
+
 }  // namespace mas
 
 using namespace mas;
@@ -116,12 +119,14 @@ extern "C" int mas_from_prior_host_f32(const float *mu_x_host, const float *y_ho
         MAS_TRY(cudaEventRecord(hs->ready[ci], copy));
         MAS_TRY(cudaStreamWaitEvent(main, hs->ready[ci], 0));
         const size_t esz = (size_t)element_size(path_dtype);
+        t_peer_row_extra = b0;   // peer rows of this chunk (mas_set_peer_durations)
         const int rc = mas_from_prior_f32(
             mu_x_dev + ox, nullptr, y_dev + oy, t_x_dev + b0, t_y_dev + b0,
             path ? static_cast<char *>(path) + (size_t)b0 * T_x * T_y * esz : nullptr, path_dtype,
             durations ? durations + (size_t)b0 * T_x : nullptr,
             frame_idx ? frame_idx + (size_t)b0 * T_y : nullptr, score ? score + b0 : nullptr, nullptr,
             nb, F, T_x, T_y, workspace, workspace_bytes, flags & ~MAS_FLAG_HOST_NO_TRIM, main);
+        t_peer_row_extra = 0;
         if (rc != MAS_OK) return rc;
     }
     if (durations_host)

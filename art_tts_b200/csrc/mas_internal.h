@@ -114,6 +114,7 @@ struct TcLayout {
     int col_ahi, col_alo, col_d;   // TMEM column map
     size_t off_stages, off_slabs, off_staging, off_bits, off_ysq, off_musq, off_first, off_dur, off_zero, off_bars, total;
 };
+constexpr int kMaxPeers = 16;
 struct PriorTcArgs {
     const float *mu_x;
     const float *y;
@@ -125,6 +126,9 @@ struct PriorTcArgs {
     float *score;
     long long *stats;      // optional [grid][32] cycle counters (MAS_PRIOR_STATS=1), else NULL
     float *lp_out;         // optional parity tap [B,T_x,T_y]: the prior exactly as the DP consumed it
+    int32_t *peer[kMaxPeers];   // mas_set_peer_durations: every rank's [world*B, T_x] buffer, or npeer == 0
+    int npeer;
+    long long peer_row0;
     int B, F, T_x, T_y;
     int path_esize;
     unsigned long long one;
@@ -135,6 +139,7 @@ cudaError_t launch_from_prior_tc(const PriorTcArgs &a, cudaStream_t st);
 TcLayout tc2_layout(int F, int T_x, int T_y);   // mas_prior_tc2.cu: DP straight from tensor memory
 cudaError_t launch_from_prior_tc2(const PriorTcArgs &a, cudaStream_t st);
 
+extern thread_local long long t_peer_row_extra;   // mas_api.cu: chunk offset of the host-buffer entry
 int sm_count();
 int sm_reserve();   // SMs the persistent kernels leave free (mas_set_sm_reserve)
 void count_launch(int n = 1);

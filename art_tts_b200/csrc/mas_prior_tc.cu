@@ -353,6 +353,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) mas_prior_tc_kernel(const Prior
                             a.path_esize, a.one, lane, 32);
             write_frame_idx(a.frame_idx ? a.frame_idx + (int64_t)u * T_y : nullptr, first, dur, T_x, ty, a.T_y,
                             lane, 32);
+            // fused all-gather of the durations (mas_set_peer_durations): the row of this utterance goes
+            // straight into row row0 + u of every rank's buffer over NVLink peer memory
+            for (int p = 0; p < a.npeer; ++p) {
+                int32_t *row = a.peer[p] + (a.peer_row0 + u) * (long long)T_x;
+                for (int x = lane; x < T_x; x += 32) row[x] = dur[x];
+            }
             __syncwarp();
         }
     } else if (warp == kTcLoader || warp == kTcLoader2) {

@@ -98,6 +98,54 @@ class DurationGatherer:
         torch.cuda.current_stream().wait_stream(self.stream)
 
 
+class PeerDurationGather:
+    """All-gather of the durations done BY the fused kernel over NVLink peer memory.
+
+    Every rank owns a [world * b_local, t_x] int32 buffer in symmetric memory
+    (torch.distributed._symmetric_memory); the buffers of all ranks are mapped into every process and
+    handed to the library (mas_set_peer_durations), whose backtrack warp stores each utterance's
+    durations into row `rank * b_local + b` of every rank's buffer.  No collective kernel runs: after
+    the MAS kernel the ranks only meet in `finish()` (a symmetric-memory barrier, ~7 us at 2 GPUs against
+    25-44 us for the NCCL all-gather), after which `self.all` holds the durations of the whole batch.
+    Only the tensor-core engine of maximum_path_from_prior does this (`supported()`); everything else
+    must use the NCCL gathers above.  Process-wide library state: one instance at a time, `close()` it."""
+
+    def __init__(self, b_local: int, t_x: int, device, group: Optional[dist.ProcessGroup] = None):
+        import ctypes
+
+        import torch.distributed._symmetric_memory as symm
+
+        from . import _lib
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        if self.world > 16:
+            raise ValueError("PeerDurationGather: at most 16 ranks (one NVLink domain)")
+        self.b_local, self.t_x = b_local, t_x
+        self.all = symm.empty((self.world * b_local, t_x), dtype=torch.int32, device=device)
+        self.all.zero_()
+        self.hdl = symm.rendezvous(self.all, self.group.group_name)
+        ptrs = (ctypes.c_uint64 * self.world)(*[int(p) for p in self.hdl.buffer_ptrs])
+        _lib.check(_lib.load().mas_set_peer_durations(self.world, ptrs, self.rank * b_local),
+                   "mas_set_peer_durations")
+        torch.cuda.synchronize(device)
+        self.hdl.barrier(channel=0)
+
+    @staticmethod
+    def supported(B: int, F: int, T_x: int, T_y: int, flags: int = 0) -> bool:
+        from . import _lib
+        return bool(_lib.load().mas_peer_durations_supported(B, F, T_x, T_y, flags))
+
+    def finish(self) -> torch.Tensor:
+        """Call after maximum_path_from_prior on the same stream: once every rank's kernel of this step
+        has completed (its peer stores are then visible), returns the gathered durations."""
+        self.hdl.barrier(channel=0)
+        return self.all
+
+    def close(self) -> None:
+        from . import _lib
+        _lib.check(_lib.load().mas_set_peer_durations(0, None, 0), "mas_set_peer_durations")
+
+
 def maximum_path_from_prior_sharded(mu_x, y, t_x, t_y, *, group=None, rebuild_path=False):
     """Every rank holds the FULL batch description (or just its shard, see below), computes MAS
     for its contiguous shard and all-gathers durations.  Returns (durations [B,T_x] int32 for

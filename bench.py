@@ -61,8 +61,9 @@ def parse():
     # default "serial": measured on 2 GPUs, the overlapped gather is 3 % faster when it works (0.347 vs
     # 0.357 ms) but the fused kernel is persistent with one CTA per SM, and whenever the collective's CTAs
     # still hold an SM at the next launch the CTAs that do not fit run as a second wave (0.78-1.6 ms observed)
-    ap.add_argument("--gather", default="serial", choices=["overlap", "serial"],
-                    help="N>1: all-gather of step i in line after its kernel, or on a side stream under the kernel of step i+1")
+    ap.add_argument("--gather", default="serial", choices=["overlap", "serial", "p2p"],
+                    help="N>1: all-gather of step i in line after its kernel, on a side stream under the kernel of step "
+                         "i+1, or done by the fused kernel itself over NVLink peer memory (+ a barrier)")
     ap.add_argument("--reserve-sms", type=int, default=-1,
                     help="SMs the persistent kernel leaves to the overlapped collective (default 0: measured "
                          "at N=8, reserving 8 SMs costs 8%% and the gather overlaps anyway)")
@@ -277,6 +278,13 @@ def run_ours(args):
         reserve = 0 if args.reserve_sms < 0 else args.reserve_sms
         _lib.check(_lib.load().mas_set_sm_reserve(reserve), "mas_set_sm_reserve")
 
+    peer = None
+    if world > 1 and args.gather == "p2p":
+        from art_tts_b200.distributed import PeerDurationGather
+        if args.op != "fused" or not PeerDurationGather.supported(B, N_FEATS, T_X, T_Y):
+            raise SystemExit("--gather p2p: only the tensor-core engine of the fused op writes peer memory")
+        peer = PeerDurationGather(B, T_X, dev)
+
     value = None
     if args.op == "dropin" or not args.no_dropin:
         value = -(torch.rand(B, T_X, T_Y, device=dev) * 100 + 50)
@@ -286,7 +294,9 @@ def run_ours(args):
 
     def step_fused():
         path, dur = monotonic_align.maximum_path_from_prior(mu_x, None, y, t_x, t_y, flags=eng_flags)
-        if gatherer is not None:
+        if peer is not None:
+            peer.finish()            # the kernel wrote every rank's buffer; the ranks only meet here
+        elif gatherer is not None:
             gatherer.gather(dur)
         elif world > 1:
             dist.all_gather_into_tensor(dur_all, dur)
@@ -430,7 +440,9 @@ def run_ours(args):
                     h_in[0], h_in[1], h_in[2], h_in[3], dev, chunk=args.e2e_chunk,
                     durations_host=h_dur, score_host=h_score,
                     flags=(_lib.FLAG_HOST_NO_TRIM if args.e2e_no_trim else 0) | eng_flags)
-                if world > 1:
+                if peer is not None:
+                    peer.finish()
+                elif world > 1:
                     dist.all_gather_into_tensor(dur_all, dur)
             else:
                 for h, d in zip(h_in, d_in):
