@@ -61,9 +61,10 @@ def parse():
     # default "serial": measured on 2 GPUs, the overlapped gather is 3 % faster when it works (0.347 vs
     # 0.357 ms) but the fused kernel is persistent with one CTA per SM, and whenever the collective's CTAs
     # still hold an SM at the next launch the CTAs that do not fit run as a second wave (0.78-1.6 ms observed)
-    ap.add_argument("--gather", default="serial", choices=["overlap", "serial", "p2p"],
+    ap.add_argument("--gather", default="auto", choices=["auto", "overlap", "serial", "p2p"],
                     help="N>1: all-gather of step i in line after its kernel, on a side stream under the kernel of step "
-                         "i+1, or done by the fused kernel itself over NVLink peer memory (+ a barrier)")
+                         "i+1, or done by the fused kernel itself over NVLink peer memory (+ a barrier); auto = p2p when "
+                         "every rank can set it up (fused op, tensor-core engine, symmetric memory), else serial")
     ap.add_argument("--reserve-sms", type=int, default=-1,
                     help="SMs the persistent kernel leaves to the overlapped collective (default 0: measured "
                          "at N=8, reserving 8 SMs costs 8%% and the gather overlaps anyway)")
@@ -279,11 +280,28 @@ def run_ours(args):
         _lib.check(_lib.load().mas_set_sm_reserve(reserve), "mas_set_sm_reserve")
 
     peer = None
-    if world > 1 and args.gather == "p2p":
+    if world > 1 and args.gather in ("p2p", "auto"):
         from art_tts_b200.distributed import PeerDurationGather
-        if args.op != "fused" or not PeerDurationGather.supported(B, N_FEATS, T_X, T_Y):
+        can = args.op == "fused" and args.engine != "cuda" and PeerDurationGather.supported(B, N_FEATS, T_X, T_Y)
+        if args.gather == "p2p" and not can:
             raise SystemExit("--gather p2p: only the tensor-core engine of the fused op writes peer memory")
-        peer = PeerDurationGather(B, T_X, dev)
+        # every rank must take the same branch: agree before the (collective) rendezvous and after it
+        flag = torch.tensor([1 if can else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()):
+            try:
+                peer = PeerDurationGather(B, T_X, dev)
+            except Exception as e:   # no symmetric memory on this box: NCCL gather in line
+                if args.gather == "p2p":
+                    raise
+                print(f"[bench] rank {rank}: peer-memory gather unavailable ({type(e).__name__}: {e}); using NCCL",
+                      file=sys.stderr)
+            flag = torch.tensor([1 if peer is not None else 0], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if not int(flag.item()) and peer is not None:
+                peer.close()
+                peer = None
+        args.gather = "p2p" if peer is not None else ("serial" if args.gather == "auto" else args.gather)
 
     value = None
     if args.op == "dropin" or not args.no_dropin:
