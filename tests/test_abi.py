@@ -88,6 +88,26 @@ def test_argument_validation_without_gpu(maslib):
     assert bw(one, null, null, null, null, one, null, null, one, 1, 80, 1 << 20, 8, 8, null) == -2
 
 
+def test_peer_durations_setting_without_gpu(maslib):
+    """mas_set_peer_durations (fused all-gather over peer memory): argument validation and the shape
+    query, neither of which touches a device."""
+    import ctypes
+    lib = maslib
+    two = (ctypes.c_uint64 * 2)(0x7f0000000000, 0x7f0000100000)
+    assert lib.mas_set_peer_durations(2, two, 0) == 0
+    assert lib.mas_set_peer_durations(0, None, 0) == 0             # off
+    assert lib.mas_set_peer_durations(2, None, 0) < 0              # pointers missing
+    assert lib.mas_set_peer_durations(17, two, 0) < 0              # more ranks than one NVLink domain
+    assert lib.mas_set_peer_durations(2, two, -1) < 0
+    odd = (ctypes.c_uint64 * 1)(0x7f0000000002)
+    assert lib.mas_set_peer_durations(1, odd, 0) < 0               # int32 rows need 4-byte alignment
+    assert lib.mas_set_peer_durations(0, None, 0) == 0
+    assert lib.mas_peer_durations_supported(1024, 80, 190, 872, 0) == 1    # tensor-core engine
+    assert lib.mas_peer_durations_supported(1024, 16, 160, 512, 0) == 0    # CUDA-core engine (F < 32)
+    assert lib.mas_peer_durations_supported(32, 80, 512, 4096, 0) == 0     # beyond 256 tokens
+    assert lib.mas_peer_durations_supported(1024, 80, 190, 872, 16) == 0   # MAS_FLAG_NO_TENSOR
+
+
 def test_python_surface_refuses_cpu_tensors(maslib):
     """No CPU fallback: the reference's host path is what this package replaces."""
     from art_tts_b200 import _lib, monotonic_align
