@@ -93,7 +93,9 @@ def config_dict(args, world):
         "T_text": T_X, "T_mel": T_Y, "n_feats": N_FEATS, "ragged": True,
         "cells_definition": "B*T_text*T_mel (padded)",
         "l2_policy": "inputs+outputs per step (>= 1 GB) exceed the 126 MB L2; no explicit flush",
-        "collective": (f"all_gather(durations int32 [B,T_text]), {args.gather}" if world > 1 else "none"),
+        "collective": ("all_gather(durations int32 [B,T_text]), " +
+                       ("auto: fused over NVLink peer memory, else NCCL in line" if args.gather == "auto" else args.gather)
+                       if world > 1 else "none"),
     }
 
 
