@@ -125,6 +125,7 @@ const char *mas_strerror(int code)
     case MAS_ERR_WORKSPACE: return "workspace missing or too small";
     case MAS_ERR_ALIGN: return "pointer not aligned to its element size";
     case MAS_ERR_NO_DEVICE: return "no usable CUDA device";
+    case MAS_ERR_PEER: return "peer durations are set but this shape / engine does not write peer memory";
     default: break;
     }
     if (code > 0) return cudaGetErrorString(static_cast<cudaError_t>(code));
@@ -330,6 +331,10 @@ int mas_from_prior_f32(const float *mu_x, const float *logs, const float *y, con
             t.path_esize = path ? esize : 4;
             t.one = one_pattern(path_dtype);
             t.npeer = 0;
+            if (tc2) {
+                std::lock_guard<std::mutex> lk(g_peer_mu);
+                if (g_npeer > 0) return MAS_ERR_PEER;
+            }
             if (!tc2) {   // fused all-gather of the durations over peer memory (mas_set_peer_durations)
                 std::lock_guard<std::mutex> lk(g_peer_mu);
                 t.npeer = g_npeer;
@@ -340,6 +345,10 @@ int mas_from_prior_f32(const float *mu_x, const float *logs, const float *y, con
         }
     }
 
+    {   // fail loudly rather than leave the peers' buffers unwritten (mas_set_peer_durations)
+        std::lock_guard<std::mutex> lk(g_peer_mu);
+        if (g_npeer > 0) return MAS_ERR_PEER;
+    }
     PriorArgs a{};
     // prefer two direction-bit buffers in shared memory (backtrack of utterance k overlaps the
     // forward pass of k+1); else one; else the bits spill to the workspace

@@ -47,7 +47,9 @@ enum {
     MAS_ERR_DTYPE = -3,     /* unsupported element type for this argument          */
     MAS_ERR_WORKSPACE = -4, /* workspace missing or smaller than *_workspace_bytes */
     MAS_ERR_ALIGN = -5,     /* pointer not aligned to its element size             */
-    MAS_ERR_NO_DEVICE = -6  /* no sm_100 device / driver available                 */
+    MAS_ERR_NO_DEVICE = -6, /* no sm_100 device / driver available                 */
+    MAS_ERR_PEER = -7       /* mas_set_peer_durations is active but this call would run an engine
+                               that does not write peer memory (mas_peer_durations_supported)     */
 };
 
 /* flags for mas_maximum_path / mas_from_prior_f32 */

@@ -102,6 +102,7 @@ def test_peer_durations_setting_without_gpu(maslib):
     odd = (ctypes.c_uint64 * 1)(0x7f0000000002)
     assert lib.mas_set_peer_durations(1, odd, 0) < 0               # int32 rows need 4-byte alignment
     assert lib.mas_set_peer_durations(0, None, 0) == 0
+    assert b"peer" in lib.mas_strerror(-7)
     assert lib.mas_peer_durations_supported(1024, 80, 190, 872, 0) == 1    # tensor-core engine
     assert lib.mas_peer_durations_supported(1024, 16, 160, 512, 0) == 0    # CUDA-core engine (F < 32)
     assert lib.mas_peer_durations_supported(32, 80, 512, 4096, 0) == 0     # beyond 256 tokens

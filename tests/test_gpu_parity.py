@@ -505,3 +505,35 @@ def test_fused_degenerate_and_empty_utterances(cuda, engine, monkeypatch):
     assert np.array_equal(path_np[4, :7, :7], np.eye(7, dtype=np.float32))
     m = mask.astype(bool)
     assert np.allclose(lp_np[m], ref_lp[m], rtol=1e-5, atol=1e-4)
+
+
+def test_peer_durations_single_rank_and_refusal(cuda):
+    """mas_set_peer_durations with this GPU's own buffer as the only peer (the multi-GPU form is
+    tests/multi_gpu_peer_gather.py under torchrun): the tensor-core engine writes the rows at row0 + b, the
+    CUDA-core engine refuses the call instead of leaving the buffer unwritten."""
+    import ctypes
+    from art_tts_b200 import _lib
+    rng = np.random.default_rng(5)
+    B, F, T_x, T_y = 40, 80, 70, 300
+    x_len = rng.integers(5, T_x + 1, B).astype(np.int32)
+    y_len = np.minimum(T_y, 4 * x_len + rng.integers(0, 20, B)).astype(np.int32)
+    mu_x = rng.standard_normal((B, F, T_x)).astype(np.float32)
+    y = rng.standard_normal((B, F, T_y)).astype(np.float32)
+    row0 = 3
+    buf = torch.full((row0 + B + 2, T_x), -7, dtype=torch.int32, device=cuda)
+    lib = _lib.load()
+    ptrs = (ctypes.c_uint64 * 1)(buf.data_ptr())
+    _lib.check(lib.mas_set_peer_durations(1, ptrs, row0), "mas_set_peer_durations")
+    try:
+        path, dur = fused(mu_x, y, x_len, y_len, cuda)
+        torch.cuda.synchronize()
+        assert torch.equal(buf[row0:row0 + B], dur)
+        assert (buf[:row0] == -7).all() and (buf[row0 + B:] == -7).all()
+        with pytest.raises(ValueError):
+            fused(mu_x, y, x_len, y_len, cuda, flags=ENGINES["cuda_core"])
+    finally:
+        _lib.check(lib.mas_set_peer_durations(0, None, 0), "mas_set_peer_durations")
+    buf.fill_(-7)
+    fused(mu_x, y, x_len, y_len, cuda)
+    torch.cuda.synchronize()
+    assert (buf == -7).all()
