@@ -106,7 +106,7 @@ def load() -> ctypes.CDLL:
     lib.mas_set_sm_reserve.restype = ci
     lib.mas_set_sm_reserve.argtypes = [ci]
     lib.mas_set_peer_durations.restype = ci
-    lib.mas_set_peer_durations.argtypes = [ci, ctypes.POINTER(ctypes.c_uint64), ctypes.c_int64]
+    lib.mas_set_peer_durations.argtypes = [ci, ctypes.POINTER(ctypes.c_uint64), ctypes.c_int64, ctypes.c_int64, ci]
     lib.mas_peer_durations_supported.restype = ci
     lib.mas_peer_durations_supported.argtypes = [ci, ci, ci, ci, ci]
     if lib.mas_abi_version() != 1:

@@ -125,7 +125,7 @@ const char *mas_strerror(int code)
     case MAS_ERR_WORKSPACE: return "workspace missing or too small";
     case MAS_ERR_ALIGN: return "pointer not aligned to its element size";
     case MAS_ERR_NO_DEVICE: return "no usable CUDA device";
-    case MAS_ERR_PEER: return "peer durations are set but this shape / engine does not write peer memory";
+    case MAS_ERR_PEER: return "peer durations are set but this engine does not write peer memory, or the call does not fit the peer buffers";
     default: break;
     }
     if (code > 0) return cudaGetErrorString(static_cast<cudaError_t>(code));
@@ -138,7 +138,8 @@ namespace {
 std::mutex g_peer_mu;
 int g_npeer = 0;
 uint64_t g_peer[mas::kMaxPeers];
-long long g_peer_row0 = 0;
+long long g_peer_row0 = 0, g_peer_rows = 0;
+int g_peer_tx = 0;
 }  // namespace
 
 int mas_peer_durations_supported(int B, int F, int T_x, int T_y, int flags)
@@ -151,15 +152,18 @@ int mas_peer_durations_supported(int B, int F, int T_x, int T_y, int flags)
     return (lay.ok && (F >= env_int("MAS_PRIOR_TC_MIN_F", 32) || (flags & MAS_FLAG_FORCE_TENSOR))) ? 1 : 0;
 }
 
-int mas_set_peer_durations(int n_peers, const uint64_t *peer_ptrs, int64_t row0)
+int mas_set_peer_durations(int n_peers, const uint64_t *peer_ptrs, int64_t row0, int64_t rows, int T_x)
 {
     if (n_peers < 0 || n_peers > mas::kMaxPeers || (n_peers > 0 && !peer_ptrs) || row0 < 0) return MAS_ERR_SHAPE;
+    if (n_peers > 0 && (rows < 1 || T_x < 1)) return MAS_ERR_SHAPE;
     for (int i = 0; i < n_peers; ++i)
         if (!peer_ptrs[i] || peer_ptrs[i] % 4) return MAS_ERR_ALIGN;
     std::lock_guard<std::mutex> lk(g_peer_mu);
     g_npeer = n_peers;
     for (int i = 0; i < n_peers; ++i) g_peer[i] = peer_ptrs[i];
     g_peer_row0 = row0;
+    g_peer_rows = n_peers ? rows : 0;
+    g_peer_tx = n_peers ? T_x : 0;
     return MAS_OK;
 }
 
@@ -337,6 +341,7 @@ int mas_from_prior_f32(const float *mu_x, const float *logs, const float *y, con
             }
             if (!tc2) {   // fused all-gather of the durations over peer memory (mas_set_peer_durations)
                 std::lock_guard<std::mutex> lk(g_peer_mu);
+                if (g_npeer > 0 && (T_x != g_peer_tx || t_peer_row_extra + B > g_peer_rows)) return MAS_ERR_PEER;
                 t.npeer = g_npeer;
                 for (int i = 0; i < g_npeer; ++i) t.peer[i] = reinterpret_cast<int32_t *>(g_peer[i]);
                 t.peer_row0 = g_peer_row0 + t_peer_row_extra;

@@ -125,7 +125,7 @@ class PeerDurationGather:
         self.all.zero_()
         self.hdl = symm.rendezvous(self.all, self.group.group_name)
         ptrs = (ctypes.c_uint64 * self.world)(*[int(p) for p in self.hdl.buffer_ptrs])
-        _lib.check(_lib.load().mas_set_peer_durations(self.world, ptrs, self.rank * b_local),
+        _lib.check(_lib.load().mas_set_peer_durations(self.world, ptrs, self.rank * b_local, b_local, t_x),
                    "mas_set_peer_durations")
         torch.cuda.synchronize(device)
         self.hdl.barrier(channel=0)
@@ -143,7 +143,7 @@ class PeerDurationGather:
 
     def close(self) -> None:
         from . import _lib
-        _lib.check(_lib.load().mas_set_peer_durations(0, None, 0), "mas_set_peer_durations")
+        _lib.check(_lib.load().mas_set_peer_durations(0, None, 0, 0, 0), "mas_set_peer_durations")
 
 
 def maximum_path_from_prior_sharded(mu_x, y, t_x, t_y, *, group=None, rebuild_path=False):

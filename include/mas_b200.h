@@ -266,11 +266,13 @@ int mas_set_sm_reserve(int n_sms);
  * `durations`, its backtrack warp stores every utterance's row into row `row0 + b` of EACH of the n_peers
  * buffers (this rank's own buffer among them), so that no collective kernel runs at all; afterwards the
  * ranks only need a barrier.  peer_ptrs[i] = base of rank i's [world*B, T_x] int32 buffer as mapped in
- * this process.  n_peers = 0 switches it off (default).  Process-wide setting, honoured by
+ * this process; `rows` = utterances this rank may write (B of one call, or of one host-buffer call) and
+ * T_x the row length: a call with another T_x or more utterances is refused (MAS_ERR_PEER) instead of
+ * writing outside the buffers.  n_peers = 0 switches it off (default).  Process-wide setting, honoured by
  * mas_from_prior_f32 / mas_from_prior_host_f32 when mas_peer_durations_supported() says so for the shape.
  * No reference equivalent (the reference runs one independent MAS per rank and never exchanges durations).
  */
-int mas_set_peer_durations(int n_peers, const uint64_t *peer_ptrs, int64_t row0);
+int mas_set_peer_durations(int n_peers, const uint64_t *peer_ptrs, int64_t row0, int64_t rows, int T_x);
 int mas_peer_durations_supported(int B, int F, int T_x, int T_y, int flags);
 
 /* Kernel launches enqueued by this library in this process (bench.py's gpu_launches). */

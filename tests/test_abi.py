@@ -94,14 +94,15 @@ def test_peer_durations_setting_without_gpu(maslib):
     import ctypes
     lib = maslib
     two = (ctypes.c_uint64 * 2)(0x7f0000000000, 0x7f0000100000)
-    assert lib.mas_set_peer_durations(2, two, 0) == 0
-    assert lib.mas_set_peer_durations(0, None, 0) == 0             # off
-    assert lib.mas_set_peer_durations(2, None, 0) < 0              # pointers missing
-    assert lib.mas_set_peer_durations(17, two, 0) < 0              # more ranks than one NVLink domain
-    assert lib.mas_set_peer_durations(2, two, -1) < 0
+    assert lib.mas_set_peer_durations(2, two, 0, 1024, 190) == 0
+    assert lib.mas_set_peer_durations(0, None, 0, 0, 0) == 0       # off
+    assert lib.mas_set_peer_durations(2, None, 0, 1024, 190) < 0   # pointers missing
+    assert lib.mas_set_peer_durations(17, two, 0, 1024, 190) < 0   # more ranks than one NVLink domain
+    assert lib.mas_set_peer_durations(2, two, -1, 1024, 190) < 0
+    assert lib.mas_set_peer_durations(2, two, 0, 0, 190) < 0       # no room for a single utterance
     odd = (ctypes.c_uint64 * 1)(0x7f0000000002)
-    assert lib.mas_set_peer_durations(1, odd, 0) < 0               # int32 rows need 4-byte alignment
-    assert lib.mas_set_peer_durations(0, None, 0) == 0
+    assert lib.mas_set_peer_durations(1, odd, 0, 8, 190) < 0       # int32 rows need 4-byte alignment
+    assert lib.mas_set_peer_durations(0, None, 0, 0, 0) == 0
     assert b"peer" in lib.mas_strerror(-7)
     assert lib.mas_peer_durations_supported(1024, 80, 190, 872, 0) == 1    # tensor-core engine
     assert lib.mas_peer_durations_supported(1024, 16, 160, 512, 0) == 0    # CUDA-core engine (F < 32)

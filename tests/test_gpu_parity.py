@@ -523,7 +523,7 @@ def test_peer_durations_single_rank_and_refusal(cuda):
     buf = torch.full((row0 + B + 2, T_x), -7, dtype=torch.int32, device=cuda)
     lib = _lib.load()
     ptrs = (ctypes.c_uint64 * 1)(buf.data_ptr())
-    _lib.check(lib.mas_set_peer_durations(1, ptrs, row0), "mas_set_peer_durations")
+    _lib.check(lib.mas_set_peer_durations(1, ptrs, row0, B, T_x), "mas_set_peer_durations")
     try:
         path, dur = fused(mu_x, y, x_len, y_len, cuda)
         torch.cuda.synchronize()
@@ -531,8 +531,11 @@ def test_peer_durations_single_rank_and_refusal(cuda):
         assert (buf[:row0] == -7).all() and (buf[row0 + B:] == -7).all()
         with pytest.raises(ValueError):
             fused(mu_x, y, x_len, y_len, cuda, flags=ENGINES["cuda_core"])
+        _lib.check(lib.mas_set_peer_durations(1, ptrs, row0, B - 1, T_x), "mas_set_peer_durations")
+        with pytest.raises(ValueError):       # one utterance more than the peers' buffers hold
+            fused(mu_x, y, x_len, y_len, cuda)
     finally:
-        _lib.check(lib.mas_set_peer_durations(0, None, 0), "mas_set_peer_durations")
+        _lib.check(lib.mas_set_peer_durations(0, None, 0, 0, 0), "mas_set_peer_durations")
     buf.fill_(-7)
     fused(mu_x, y, x_len, y_len, cuda)
     torch.cuda.synchronize()
