@@ -58,6 +58,17 @@ __device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint
                  "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc)
                  : "memory");
 }
+// split descriptor + provably uniform operands: see mas_prior_tc.cu (one instruction per MMA for the issuer)
+__device__ __forceinline__ void tc_mma_ts2(uint32_t d_tmem, uint32_t a_tmem, uint32_t bdesc_lo, uint32_t bdesc_hi,
+                                           uint32_t idesc, uint32_t acc)
+{
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 bd;\n\tsetp.ne.b32 p, %5, 0;\n\tmov.b64 bd, {%2, %3};\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], bd, %4, p;\n\t}" ::"r"(d_tmem),
+                 "r"(a_tmem), "r"(bdesc_lo), "r"(bdesc_hi), "r"(idesc), "r"(acc)
+                 : "memory");
+}
+__device__ __forceinline__ uint32_t uniform_u32(uint32_t v) { return __reduce_min_sync(kFull, v); }
+
 // B operand = one 32-frame slab of y, K-MAJOR in shared memory, SWIZZLE_32B: per k step (8
 // features) a [32 frames][8 features] block of 32-byte rows, 1 KB contiguous; the two 16-byte
 // halves of row j are swapped when (j >> 2) & 1.  SBO = 256 B between groups of 8 rows.
@@ -727,45 +738,50 @@ __global__ void __launch_bounds__(kTcThreads, 1) mas_prior_tc2_kernel(const Prio
                         }
                     tc_fence_after();
                     m_i.begin();
-                    // Everything the issue loop uses is re-derived from lane 0's copy: the compiler then
-                    // knows these values are warp-uniform and keeps them (and the loop arithmetic on them)
-                    // in uniform registers -- otherwise every operand of every MMA goes through an R2UR.
+                    // Everything the issue loop uses is made provably warp-uniform first (mas_prior_tc.cu)
 #pragma unroll
-                    for (int c4 = 0; c4 < 4; ++c4) dcol[c4] = __shfl_sync(kFull, dcol[c4], 0);
+                    for (int c4 = 0; c4 < 4; ++c4) dcol[c4] = uniform_u32(dcol[c4]);
+                    uint32_t bhl[2], bll[2];
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
-                        bh[e] = __shfl_sync(kFull, bh[e], 0);
-                        bl[e] = __shfl_sync(kFull, bl[e], 0);
+                        bhl[e] = uniform_u32((uint32_t)bh[e]);
+                        bll[e] = uniform_u32((uint32_t)bl[e]);
                     }
-                    am = __shfl_sync(kFull, am, 0);
-                    const uint32_t ahi0 = tbase + L.col_ahi, alo0 = tbase + L.col_alo;
-                    // small terms first: a_lo*b_hi + a_hi*b_lo, then a_hi*b_hi.  One k step = 8 features
-                    // = 8 TMEM columns of A = 1 KB of B (64 descriptor address units).
-                    auto issue_all = [&](auto ks_tag) {
+                    const uint32_t bdhi = (uint32_t)(tc_bdesc(0) >> 32);
+                    am = (int)uniform_u32((uint32_t)am);
+                    const uint32_t ahi0 = uniform_u32(tbase + L.col_ahi), alo0 = uniform_u32(tbase + L.col_alo);
+                    const uint32_t fpu = uniform_u32((uint32_t)Fp);
+                    auto issue_all = [&](auto ks_tag, auto am_tag) {
                         constexpr int KS = decltype(ks_tag)::value;   // 0 = run-time k-step count (rolled loop)
+                        constexpr int AM = decltype(am_tag)::value;   // 0 = run-time accumulator mask
                         const int nk = KS ? KS : ksteps;
+                        const int m = AM ? AM : am;
 #pragma unroll
                         for (int pass = kExpPass0; pass < 3; ++pass) {
                             const uint32_t abase = (pass == 0) ? alo0 : ahi0;
-                            const uint64_t b0 = (pass == 1) ? bl[0] : bh[0], b1 = (pass == 1) ? bl[1] : bh[1];
+                            const uint32_t b0 = (pass == 1) ? bll[0] : bhl[0], b1 = (pass == 1) ? bll[1] : bhl[1];
 #pragma unroll
                             for (int j = 0; j < nk; ++j) {
                                 const uint32_t acc = ((pass - kExpPass0) | j) != 0;
                                 const uint32_t ac = abase + 8 * j;
                                 const uint32_t bo = (uint32_t)(64 * j);
-                                const uint64_t d0 = b0 + bo, d1 = b1 + bo;
-                                if (am & 1) tc_mma_ts(dcol[0], ac, d0, idesc, acc);
-                                if (am & 2) tc_mma_ts(dcol[1], ac + Fp, d0, idesc, acc);
-                                if (am & 4) tc_mma_ts(dcol[2], ac, d1, idesc, acc);
-                                if (am & 8) tc_mma_ts(dcol[3], ac + Fp, d1, idesc, acc);
+                                if (m & 1) tc_mma_ts2(dcol[0], ac, b0 + bo, bdhi, idesc, acc);
+                                if (m & 2) tc_mma_ts2(dcol[1], ac + fpu, b0 + bo, bdhi, idesc, acc);
+                                if (m & 4) tc_mma_ts2(dcol[2], ac, b1 + bo, bdhi, idesc, acc);
+                                if (m & 8) tc_mma_ts2(dcol[3], ac + fpu, b1 + bo, bdhi, idesc, acc);
                             }
                         }
                     };
                     // one elected lane issues the whole pair; with the k-step count known at compile time
                     // the loop unrolls and the operands of all 120 MMAs are immediates off a few registers
                     if (elect_one()) {
-                        if (ksteps == 10) issue_all(std::integral_constant<int, 10>{});
-                        else issue_all(std::integral_constant<int, 0>{});
+                        using K10 = std::integral_constant<int, 10>;
+                        if (ksteps != 10) issue_all(std::integral_constant<int, 0>{}, std::integral_constant<int, 0>{});
+                        else if (am == 15) issue_all(K10{}, std::integral_constant<int, 15>{});
+                        else if (am == 5) issue_all(K10{}, std::integral_constant<int, 5>{});
+                        else if (am == 3) issue_all(K10{}, std::integral_constant<int, 3>{});
+                        else if (am == 1) issue_all(K10{}, std::integral_constant<int, 1>{});
+                        else issue_all(K10{}, std::integral_constant<int, 0>{});
                     }
                     __syncwarp();
                     if (elect_one()) {
