@@ -38,8 +38,19 @@ EXPORTS = (
     "mas_frame_index", "mas_duration_loss_f32", "mas_crop_f32", "mas_path_segment",
     "mas_align_workspace_bytes", "mas_align_gather_f32", "mas_align_gather_bwd_f32",
     "mas_from_prior_host_f32", "mas_set_sm_reserve",
-    "mas_set_peer_durations", "mas_peer_durations_supported",
+    "mas_from_prior_peer_f32", "mas_from_prior_host_peer_f32", "mas_peer_durations_supported",
+    "mas_lengths_from_seq_masks",
 )
+
+
+class PeerGatherDesc(ctypes.Structure):
+    """`mas_peer_gather` of include/mas_b200.h: where the fused kernel stores every utterance's
+    durations (and frame index) in every rank's peer-mapped buffers.  Travels with the call."""
+    _fields_ = [("n_peers", ctypes.c_int),
+                ("durations_ptrs", ctypes.POINTER(ctypes.c_uint64)),
+                ("row0", ctypes.c_int64), ("rows", ctypes.c_int64), ("row_stride", ctypes.c_int64),
+                ("frame_idx_ptrs", ctypes.POINTER(ctypes.c_uint64)),
+                ("frame_idx_stride", ctypes.c_int64)]
 
 _lib = None
 
@@ -105,11 +116,16 @@ def load() -> ctypes.CDLL:
                                             ci, ci, ci, ci, vp, sz, ci, ci, vp, vp]
     lib.mas_set_sm_reserve.restype = ci
     lib.mas_set_sm_reserve.argtypes = [ci]
-    lib.mas_set_peer_durations.restype = ci
-    lib.mas_set_peer_durations.argtypes = [ci, ctypes.POINTER(ctypes.c_uint64), ctypes.c_int64, ctypes.c_int64, ci]
+    pg = ctypes.POINTER(PeerGatherDesc)
+    lib.mas_from_prior_peer_f32.restype = ci
+    lib.mas_from_prior_peer_f32.argtypes = lib.mas_from_prior_f32.argtypes + [pg]
+    lib.mas_from_prior_host_peer_f32.restype = ci
+    lib.mas_from_prior_host_peer_f32.argtypes = lib.mas_from_prior_host_f32.argtypes + [pg]
+    lib.mas_lengths_from_seq_masks.restype = ci
+    lib.mas_lengths_from_seq_masks.argtypes = [vp, ci, i64, i64, vp, ci, i64, i64, ci, ci, ci, vp, vp, vp]
     lib.mas_peer_durations_supported.restype = ci
     lib.mas_peer_durations_supported.argtypes = [ci, ci, ci, ci, ci]
-    if lib.mas_abi_version() != 1:
+    if lib.mas_abi_version() != 2:
         raise MasError("libmas_sm100.so ABI version mismatch; rebuild it")
     _lib = lib
     return lib

@@ -57,6 +57,31 @@ static int env_int(const char *name, int dflt)
     return (s && *s) ? std::atoi(s) : dflt;
 }
 
+// Tuning knobs (A/B measurements, profiling): the environment is read ONCE, at the first call into
+// the library, so that plan queries (mas_plan, mas_from_prior_plan, mas_peer_durations_supported)
+// and the launches that follow can never disagree.
+struct Tuning {
+    int prior_tc, prior_tc_min_f, stages, dp2_min_tx, prior_spill, prior_stats, fma_per_smsp, extra_fma;
+};
+static const Tuning &tuning()
+{
+    static const Tuning t = [] {
+        Tuning v;
+        v.prior_tc = env_int("MAS_PRIOR_TC", 1);
+        v.prior_tc_min_f = env_int("MAS_PRIOR_TC_MIN_F", 32);
+        v.stages = env_int("MAS_STAGES", 0);
+        v.dp2_min_tx = env_int("MAS_DP2_MIN_TX", 256);
+        v.prior_spill = env_int("MAS_PRIOR_SPILL", 0);
+        v.prior_stats = env_int("MAS_PRIOR_STATS", 0);
+        v.fma_per_smsp = env_int("MAS_PRIOR_FMA_PER_SMSP", 2);
+        if (v.fma_per_smsp < 1 || v.fma_per_smsp > 4) v.fma_per_smsp = 2;
+        v.extra_fma = env_int("MAS_PRIOR_EXTRA_FMA", 1);
+        if (v.extra_fma < 0 || v.extra_fma > 1) v.extra_fma = 1;
+        return v;
+    }();
+    return t;
+}
+
 // Shared-memory carve-up of the fast kernels and the plan that follows from it.
 // `extra_smem` = bytes the caller needs besides ring + bits (the fused kernel's operands).
 Plan choose_plan(int T_x, int T_y, int flags, FastLayout *lay, size_t extra_smem, int max_stages, int row_align)
@@ -78,7 +103,7 @@ Plan choose_plan(int T_x, int T_y, int flags, FastLayout *lay, size_t extra_smem
         if (total(2, fits) > (size_t)kSmemBudget) plan = kPlanGeneral;  // cannot happen for T_x<=512
         // ring depth: deepest ring that does not cost a resident CTA (or leaves >= 3 per SM)
         int S = 2;
-        const int forced = env_int("MAS_STAGES", 0);
+        const int forced = tuning().stages;
         auto occ = [&](int s) { return (int)((size_t)(kSmemBudget + 1024) / (total(s, fits) + 1024)); };
         for (int s = 3; s <= max_stages; ++s)
             if (total(s, fits) <= (size_t)kSmemBudget && (occ(s) >= occ(2) || occ(s) >= 3)) S = s;
@@ -125,7 +150,7 @@ const char *mas_strerror(int code)
     case MAS_ERR_WORKSPACE: return "workspace missing or too small";
     case MAS_ERR_ALIGN: return "pointer not aligned to its element size";
     case MAS_ERR_NO_DEVICE: return "no usable CUDA device";
-    case MAS_ERR_PEER: return "peer durations are set but this engine does not write peer memory, or the call does not fit the peer buffers";
+    case MAS_ERR_PEER: return "a peer gather was requested but this engine does not write peer memory, or the call does not fit the peer buffers";
     default: break;
     }
     if (code > 0) return cudaGetErrorString(static_cast<cudaError_t>(code));
@@ -134,36 +159,35 @@ const char *mas_strerror(int code)
 
 uint64_t mas_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
-namespace {
-std::mutex g_peer_mu;
-int g_npeer = 0;
-uint64_t g_peer[mas::kMaxPeers];
-long long g_peer_row0 = 0, g_peer_rows = 0;
-int g_peer_tx = 0;
-}  // namespace
+static bool tc_engine_selected(int F, int T_x, int T_y, int flags, mas::TcLayout *lay)
+{
+    if (!tuning().prior_tc || (flags & (MAS_FLAG_FORCE_GENERAL | MAS_FLAG_SPILL_BITS | MAS_FLAG_NO_TENSOR))) return false;
+    const mas::TcLayout l = mas::tc_layout(F, T_x, T_y);
+    if (lay) *lay = l;
+    // measured (profiles/config_sweep.py): below ~32 features the FMA work is so small that the
+    // CUDA-core kernel is as fast or faster (F=16: 0.157 vs 0.166 ms at B=1024, 160x512)
+    return l.ok && (F >= tuning().prior_tc_min_f || (flags & MAS_FLAG_FORCE_TENSOR));
+}
 
 int mas_peer_durations_supported(int B, int F, int T_x, int T_y, int flags)
 {
     (void)B;
     if (T_x < 1 || T_y < 1 || F < 1) return 0;
-    if (!env_int("MAS_PRIOR_TC", 1) || env_int("MAS_PRIOR_TC2", 0)) return 0;
-    if (flags & (MAS_FLAG_FORCE_GENERAL | MAS_FLAG_SPILL_BITS | MAS_FLAG_NO_TENSOR)) return 0;
-    const mas::TcLayout lay = mas::tc_layout(F, T_x, T_y);
-    return (lay.ok && (F >= env_int("MAS_PRIOR_TC_MIN_F", 32) || (flags & MAS_FLAG_FORCE_TENSOR))) ? 1 : 0;
+    return tc_engine_selected(F, T_x, T_y, flags, nullptr) ? 1 : 0;
 }
 
-int mas_set_peer_durations(int n_peers, const uint64_t *peer_ptrs, int64_t row0, int64_t rows, int T_x)
+// validate a per-call peer description against the call it accompanies
+static int check_peer(const mas_peer_gather *peer, int B, int T_x, int T_y, long long row_extra)
 {
-    if (n_peers < 0 || n_peers > mas::kMaxPeers || (n_peers > 0 && !peer_ptrs) || row0 < 0) return MAS_ERR_SHAPE;
-    if (n_peers > 0 && (rows < 1 || T_x < 1)) return MAS_ERR_SHAPE;
-    for (int i = 0; i < n_peers; ++i)
-        if (!peer_ptrs[i] || peer_ptrs[i] % 4) return MAS_ERR_ALIGN;
-    std::lock_guard<std::mutex> lk(g_peer_mu);
-    g_npeer = n_peers;
-    for (int i = 0; i < n_peers; ++i) g_peer[i] = peer_ptrs[i];
-    g_peer_row0 = row0;
-    g_peer_rows = n_peers ? rows : 0;
-    g_peer_tx = n_peers ? T_x : 0;
+    if (!peer || peer->n_peers == 0) return MAS_OK;
+    if (peer->n_peers < 0 || peer->n_peers > mas::kMaxPeers || !peer->durations_ptrs) return MAS_ERR_SHAPE;
+    if (peer->row0 < 0 || peer->rows < 1 || peer->row_stride < T_x) return MAS_ERR_PEER;
+    if (row_extra + B > peer->rows) return MAS_ERR_PEER;   // would write outside the peers' buffers
+    if (peer->frame_idx_ptrs && peer->frame_idx_stride < T_y) return MAS_ERR_PEER;
+    for (int i = 0; i < peer->n_peers; ++i) {
+        if (!peer->durations_ptrs[i] || peer->durations_ptrs[i] % 4) return MAS_ERR_ALIGN;
+        if (peer->frame_idx_ptrs && (!peer->frame_idx_ptrs[i] || peer->frame_idx_ptrs[i] % 4)) return MAS_ERR_ALIGN;
+    }
     return MAS_OK;
 }
 
@@ -197,7 +221,7 @@ static Plan plan_fast(int T_x, int T_y, int flags, MasArgs *a)
 {
     Plan plan = choose_plan(T_x, T_y, flags, &a->lay);
     a->dp_warps = 1;
-    if (plan != kPlanGeneral && T_x > env_int("MAS_DP2_MIN_TX", 256)) {
+    if (plan != kPlanGeneral && T_x > tuning().dp2_min_tx) {
         FastLayout l2;
         const Plan p2 = choose_plan(T_x, T_y, flags, &l2, 512, 3, 64);
         if (p2 != kPlanGeneral && l2.nstages >= 3) {
@@ -226,6 +250,19 @@ int mas_lengths_from_mask(const void *mask, int mask_dtype, int B, int T_x, int 
     if (B == 0) return MAS_OK;
     return (int)launch_lengths_from_mask(mask, mask_dtype, B, T_x, T_y, stride_b, stride_x, stride_y,
                                          t_x_out, t_y_out, static_cast<cudaStream_t>(stream));
+}
+
+int mas_lengths_from_seq_masks(const void *x_mask, int x_dtype, int64_t x_stride_b, int64_t x_stride_t,
+                               const void *y_mask, int y_dtype, int64_t y_stride_b, int64_t y_stride_t,
+                               int B, int T_x, int T_y, int32_t *t_x_out, int32_t *t_y_out, void *stream)
+{
+    if (!x_mask || !y_mask || !t_x_out || !t_y_out) return MAS_ERR_NULL;
+    if (!shape_ok(B, T_x, T_y)) return MAS_ERR_SHAPE;
+    if (element_size(x_dtype) == 0 || element_size(y_dtype) == 0) return MAS_ERR_DTYPE;
+    if (B == 0) return MAS_OK;
+    return (int)launch_seq_lengths(x_mask, x_dtype, x_stride_b, x_stride_t, y_mask, y_dtype, y_stride_b,
+                                   y_stride_t, B, T_x, T_y, t_x_out, t_y_out,
+                                   static_cast<cudaStream_t>(stream));
 }
 
 int mas_maximum_path(const void *value, int value_dtype, const float *cell_mask, const int32_t *t_x,
@@ -285,10 +322,17 @@ int mas_from_prior_plan(int B, int F, int T_x, int T_y, int flags)
     return plan == kPlanGeneral ? 1 : 0;
 }
 
-int mas_from_prior_f32(const float *mu_x, const float *logs, const float *y, const int32_t *t_x,
-                       const int32_t *t_y, void *path, int path_dtype, int32_t *durations,
-                       int32_t *frame_idx, float *score, float *log_prior_out, int B, int F, int T_x,
-                       int T_y, void *workspace, size_t workspace_bytes, int flags, void *stream)
+}  // extern "C"
+
+namespace mas {
+
+// mas_from_prior_f32 / mas_from_prior_peer_f32 / one chunk of the host-buffer entries.  `row_extra` =
+// first utterance of this launch within the caller's batch (chunked host entry): added to peer->row0.
+int from_prior_impl(const float *mu_x, const float *logs, const float *y, const int32_t *t_x,
+                    const int32_t *t_y, void *path, int path_dtype, int32_t *durations,
+                    int32_t *frame_idx, float *score, float *log_prior_out, int B, int F, int T_x,
+                    int T_y, void *workspace, size_t workspace_bytes, int flags, cudaStream_t st,
+                    const mas_peer_gather *peer, long long row_extra)
 {
     if (!mu_x || !y || !t_x || !t_y) return MAS_ERR_NULL;
     if (!path && !durations && !frame_idx && !score) return MAS_ERR_NULL;
@@ -300,66 +344,59 @@ int mas_from_prior_f32(const float *mu_x, const float *logs, const float *y, con
         (uintptr_t)t_x % 4 || (uintptr_t)t_y % 4 || (uintptr_t)durations % 4 ||
         (uintptr_t)frame_idx % 4 || (uintptr_t)score % 4 || (uintptr_t)log_prior_out % 4)
         return MAS_ERR_ALIGN;
+    const int prc = check_peer(peer, B, T_x, T_y, row_extra);
+    if (prc != MAS_OK) return prc;
+    const bool want_peer = peer && peer->n_peers > 0;
     if (B == 0) return MAS_OK;
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
 
     // tensor-core prior (mas_prior_tc.cu) for every shape it covers; MAS_PRIOR_TC=0 forces the
     // CUDA-core kernel (A/B measurements, and the shapes beyond 256 tokens / 96 features)
-    if (env_int("MAS_PRIOR_TC", 1) && !(flags & (MAS_FLAG_FORCE_GENERAL | MAS_FLAG_SPILL_BITS | MAS_FLAG_NO_TENSOR))) {
-        PriorTcArgs t{};
-        const bool tc2 = env_int("MAS_PRIOR_TC2", 0) != 0;   // experimental engine of mas_prior_tc2.cu (measured slower)
-        t.lay = tc2 ? tc2_layout(F, T_x, T_y) : tc_layout(F, T_x, T_y);
-        // measured (profiles/config_sweep.py): below ~32 features the FMA work is so small that the
-        // CUDA-core kernel is as fast or faster (F=16: 0.157 vs 0.166 ms at B=1024, 160x512)
-        if (t.lay.ok && (F >= env_int("MAS_PRIOR_TC_MIN_F", 32) || (flags & MAS_FLAG_FORCE_TENSOR))) {
-            t.mu_x = mu_x;
-            t.y = y;
-            t.t_x = t_x;
-            t.t_y = t_y;
-            t.path = path;
-            t.durations = durations;
-            t.frame_idx = frame_idx;
-            t.score = score;
-            t.lp_out = log_prior_out;
-            t.stats = nullptr;
-            if (env_int("MAS_PRIOR_STATS", 0)) {  // profiling aid: counters at the tail of an over-sized workspace
-                const size_t need = mas_workspace_bytes(B, T_x, T_y), sbytes = (size_t)1024 * 32 * 8;
-                if (workspace && workspace_bytes >= need + sbytes + 16)
-                    t.stats = reinterpret_cast<long long *>(static_cast<char *>(workspace) +
-                                                            ((workspace_bytes - sbytes) & ~(size_t)15));
-            }
-            t.B = B;
-            t.F = F;
-            t.T_x = T_x;
-            t.T_y = T_y;
-            t.path_esize = path ? esize : 4;
-            t.one = one_pattern(path_dtype);
-            t.npeer = 0;
-            if (tc2) {
-                std::lock_guard<std::mutex> lk(g_peer_mu);
-                if (g_npeer > 0) return MAS_ERR_PEER;
-            }
-            if (!tc2) {   // fused all-gather of the durations over peer memory (mas_set_peer_durations)
-                std::lock_guard<std::mutex> lk(g_peer_mu);
-                if (g_npeer > 0 && (T_x != g_peer_tx || t_peer_row_extra + B > g_peer_rows)) return MAS_ERR_PEER;
-                t.npeer = g_npeer;
-                for (int i = 0; i < g_npeer; ++i) t.peer[i] = reinterpret_cast<int32_t *>(g_peer[i]);
-                t.peer_row0 = g_peer_row0 + t_peer_row_extra;
-            }
-            return (int)(tc2 ? launch_from_prior_tc2(t, st) : launch_from_prior_tc(t, st));
+    PriorTcArgs t{};
+    if (tc_engine_selected(F, T_x, T_y, flags, &t.lay)) {
+        t.mu_x = mu_x;
+        t.y = y;
+        t.t_x = t_x;
+        t.t_y = t_y;
+        t.path = path;
+        t.durations = durations;
+        t.frame_idx = frame_idx;
+        t.score = score;
+        t.lp_out = log_prior_out;
+        t.stats = nullptr;
+        if (tuning().prior_stats) {  // profiling aid: counters at the tail of an over-sized workspace
+            const size_t need = mas_workspace_bytes(B, T_x, T_y), sbytes = (size_t)1024 * 32 * 8;
+            if (workspace && workspace_bytes >= need + sbytes + 16)
+                t.stats = reinterpret_cast<long long *>(static_cast<char *>(workspace) +
+                                                        ((workspace_bytes - sbytes) & ~(size_t)15));
         }
+        t.B = B;
+        t.F = F;
+        t.T_x = T_x;
+        t.T_y = T_y;
+        t.path_esize = path ? esize : 4;
+        t.one = one_pattern(path_dtype);
+        t.npeer = 0;
+        if (want_peer) {   // fused all-gather of the durations (and frame index) over peer memory
+            t.npeer = peer->n_peers;
+            for (int i = 0; i < peer->n_peers; ++i) {
+                t.peer[i] = reinterpret_cast<int32_t *>(peer->durations_ptrs[i]);
+                t.peer_fi[i] = peer->frame_idx_ptrs ? reinterpret_cast<int32_t *>(peer->frame_idx_ptrs[i]) : nullptr;
+            }
+            t.peer_row0 = peer->row0 + row_extra;
+            t.peer_stride = peer->row_stride;
+            t.peer_fi_stride = peer->frame_idx_ptrs ? peer->frame_idx_stride : 0;
+        }
+        return (int)launch_from_prior_tc(t, st);
     }
 
-    {   // fail loudly rather than leave the peers' buffers unwritten (mas_set_peer_durations)
-        std::lock_guard<std::mutex> lk(g_peer_mu);
-        if (g_npeer > 0) return MAS_ERR_PEER;
-    }
+    // fail loudly rather than leave the peers' buffers unwritten
+    if (want_peer) return MAS_ERR_PEER;
     PriorArgs a{};
     // prefer two direction-bit buffers in shared memory (backtrack of utterance k overlaps the
     // forward pass of k+1); else one; else the bits spill to the workspace
     Plan plan = choose_plan(T_x, T_y, flags, &a.lay, prior_extra_smem(F, T_x, T_y, true), 3);
     a.bits_slots = 2;
-    if (env_int("MAS_PRIOR_SPILL", 0)) {  // tuning knob: bits in L2/HBM, shared memory spent on a deeper ring
+    if (tuning().prior_spill) {  // tuning knob: bits in L2/HBM, shared memory spent on a deeper ring
         plan = choose_plan(T_x, T_y, flags | MAS_FLAG_SPILL_BITS, &a.lay,
                            prior_extra_smem(F, T_x, T_y, false), 6);
         a.bits_slots = 0;
@@ -406,16 +443,14 @@ int mas_from_prior_f32(const float *mu_x, const float *logs, const float *y, con
     a.score = score;
     a.bits_ws = static_cast<uint32_t *>(workspace);
     a.stats = nullptr;
-    if (env_int("MAS_PRIOR_STATS", 0)) {  // profiling aid: counters at the tail of an over-sized workspace
+    if (tuning().prior_stats) {  // profiling aid: counters at the tail of an over-sized workspace
         const size_t need = mas_workspace_bytes(B, T_x, T_y), sbytes = (size_t)1024 * 16 * 8;
         if (workspace_bytes >= need + sbytes + 16)
             a.stats = reinterpret_cast<long long *>(static_cast<char *>(workspace) +
                                                     ((workspace_bytes - sbytes) & ~(size_t)15));
     }
-    a.fma_per_smsp = env_int("MAS_PRIOR_FMA_PER_SMSP", 2);
-    if (a.fma_per_smsp < 1 || a.fma_per_smsp > 4) a.fma_per_smsp = 2;
-    a.extra_fma = env_int("MAS_PRIOR_EXTRA_FMA", 1);
-    if (a.extra_fma < 0 || a.extra_fma > 1) a.extra_fma = 1;
+    a.fma_per_smsp = tuning().fma_per_smsp;
+    a.extra_fma = tuning().extra_fma;
     a.B = B;
     a.F = F;
     a.T_x = T_x;
@@ -423,6 +458,31 @@ int mas_from_prior_f32(const float *mu_x, const float *logs, const float *y, con
     a.path_esize = path ? esize : 4;
     a.one = one_pattern(path_dtype);
     return (int)launch_from_prior(a, st);
+}
+
+}  // namespace mas
+
+extern "C" {
+
+int mas_from_prior_f32(const float *mu_x, const float *logs, const float *y, const int32_t *t_x,
+                       const int32_t *t_y, void *path, int path_dtype, int32_t *durations,
+                       int32_t *frame_idx, float *score, float *log_prior_out, int B, int F, int T_x,
+                       int T_y, void *workspace, size_t workspace_bytes, int flags, void *stream)
+{
+    return from_prior_impl(mu_x, logs, y, t_x, t_y, path, path_dtype, durations, frame_idx, score,
+                           log_prior_out, B, F, T_x, T_y, workspace, workspace_bytes, flags,
+                           static_cast<cudaStream_t>(stream), nullptr, 0);
+}
+
+int mas_from_prior_peer_f32(const float *mu_x, const float *logs, const float *y, const int32_t *t_x,
+                            const int32_t *t_y, void *path, int path_dtype, int32_t *durations,
+                            int32_t *frame_idx, float *score, float *log_prior_out, int B, int F,
+                            int T_x, int T_y, void *workspace, size_t workspace_bytes, int flags,
+                            void *stream, const mas_peer_gather *peer)
+{
+    return from_prior_impl(mu_x, logs, y, t_x, t_y, path, path_dtype, durations, frame_idx, score,
+                           log_prior_out, B, F, T_x, T_y, workspace, workspace_bytes, flags,
+                           static_cast<cudaStream_t>(stream), peer, 0);
 }
 
 int mas_generate_path(const void *durations, int dur_dtype, const int32_t *t_x, const int32_t *t_y,

@@ -11,7 +11,9 @@
 // chunk's longest utterance (rounded up to the kernels' 32-frame tile).  Padding beyond that
 // is never read by the kernels (mas_prior.cu loads whole tiles below t_y only).
 #include <algorithm>
+#include <map>
 #include <mutex>
+#include <utility>
 
 #include "mas_internal.h"
 
@@ -21,50 +23,51 @@ namespace {
 
 constexpr int kMaxChunks = 64;
 
-struct HostState {          // per device: one internal copy stream + events, created on first use
+// one internal copy stream + events per (device, caller stream), created on first use: calls on
+// different streams (or from different threads on different streams) never share a copy stream or
+// its events, so the H2D copies of one call cannot overtake the kernels of another
+struct HostState {
     cudaStream_t copy = nullptr;
     cudaEvent_t ready[kMaxChunks] = {};
     cudaEvent_t entry = nullptr;
-    bool ok = false;
 };
 std::mutex g_mu;
-HostState g_state[64];
+std::map<std::pair<int, cudaStream_t>, HostState *> g_state;
 
-HostState *host_state(int dev)
+HostState *host_state(int dev, cudaStream_t main)
 {
-    if (dev < 0 || dev >= 64) return nullptr;
     std::lock_guard<std::mutex> lk(g_mu);
-    HostState &s = g_state[dev];
-    if (!s.ok) {
-        if (cudaStreamCreateWithFlags(&s.copy, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
-        for (auto &e : s.ready)
-            if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
-        if (cudaEventCreateWithFlags(&s.entry, cudaEventDisableTiming) != cudaSuccess) return nullptr;
-        s.ok = true;
+    auto it = g_state.find({dev, main});
+    if (it != g_state.end()) return it->second;
+    HostState *s = new HostState;
+    bool ok = cudaStreamCreateWithFlags(&s->copy, cudaStreamNonBlocking) == cudaSuccess;
+    for (auto &e : s->ready) ok = ok && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&s->entry, cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) {
+        delete s;
+        return nullptr;
     }
-    return &s;
+    g_state[{dev, main}] = s;
+    return s;
 }
 
 inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
 }  // namespace
 
-// first utterance of the chunk being launched: added to the peer rows of mas_set_peer_durations (mas_api.cu)
-thread_local long long t_peer_row_extra = 0;
-
 }  // namespace mas
 
 using namespace mas;
 
-extern "C" int mas_from_prior_host_f32(const float *mu_x_host, const float *y_host,
-                                       const int32_t *t_x_host, const int32_t *t_y_host,
-                                       float *mu_x_dev, float *y_dev, int32_t *t_x_dev,
-                                       int32_t *t_y_dev, void *path, int path_dtype,
-                                       int32_t *durations, int32_t *frame_idx, float *score,
-                                       int32_t *durations_host, float *score_host, int B, int F,
-                                       int T_x, int T_y, void *workspace, size_t workspace_bytes,
-                                       int chunk, int flags, void *stream,
-                                       uint64_t *h2d_bytes_out)
+extern "C" int mas_from_prior_host_peer_f32(const float *mu_x_host, const float *y_host,
+                                            const int32_t *t_x_host, const int32_t *t_y_host,
+                                            float *mu_x_dev, float *y_dev, int32_t *t_x_dev,
+                                            int32_t *t_y_dev, void *path, int path_dtype,
+                                            int32_t *durations, int32_t *frame_idx, float *score,
+                                            int32_t *durations_host, float *score_host, int B, int F,
+                                            int T_x, int T_y, void *workspace, size_t workspace_bytes,
+                                            int chunk, int flags, void *stream,
+                                            uint64_t *h2d_bytes_out, const mas_peer_gather *peer)
 {
     if (!mu_x_host || !y_host || !t_x_host || !t_y_host || !mu_x_dev || !y_dev || !t_x_dev || !t_y_dev)
         return MAS_ERR_NULL;
@@ -76,9 +79,10 @@ extern "C" int mas_from_prior_host_f32(const float *mu_x_host, const float *y_ho
     if ((B + chunk - 1) / chunk > kMaxChunks) chunk = (B + kMaxChunks - 1) / kMaxChunks;
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return MAS_ERR_NO_DEVICE;
-    HostState *hs = host_state(dev);
+    cudaStream_t main = static_cast<cudaStream_t>(stream);
+    HostState *hs = host_state(dev, main);
     if (!hs) return MAS_ERR_NO_DEVICE;
-    cudaStream_t main = static_cast<cudaStream_t>(stream), copy = hs->copy;
+    cudaStream_t copy = hs->copy;
     const bool no_trim = (flags & MAS_FLAG_HOST_NO_TRIM) != 0;
     cudaError_t e;
 #define MAS_TRY(x)                  \
@@ -119,14 +123,13 @@ extern "C" int mas_from_prior_host_f32(const float *mu_x_host, const float *y_ho
         MAS_TRY(cudaEventRecord(hs->ready[ci], copy));
         MAS_TRY(cudaStreamWaitEvent(main, hs->ready[ci], 0));
         const size_t esz = (size_t)element_size(path_dtype);
-        t_peer_row_extra = b0;   // peer rows of this chunk (mas_set_peer_durations)
-        const int rc = mas_from_prior_f32(
+        const int rc = from_prior_impl(
             mu_x_dev + ox, nullptr, y_dev + oy, t_x_dev + b0, t_y_dev + b0,
             path ? static_cast<char *>(path) + (size_t)b0 * T_x * T_y * esz : nullptr, path_dtype,
             durations ? durations + (size_t)b0 * T_x : nullptr,
             frame_idx ? frame_idx + (size_t)b0 * T_y : nullptr, score ? score + b0 : nullptr, nullptr,
-            nb, F, T_x, T_y, workspace, workspace_bytes, flags & ~MAS_FLAG_HOST_NO_TRIM, main);
-        t_peer_row_extra = 0;
+            nb, F, T_x, T_y, workspace, workspace_bytes, flags & ~MAS_FLAG_HOST_NO_TRIM, main, peer,
+            b0);   // b0: peer rows of this chunk
         if (rc != MAS_OK) return rc;
     }
     if (durations_host)
@@ -136,4 +139,20 @@ extern "C" int mas_from_prior_host_f32(const float *mu_x_host, const float *y_ho
 #undef MAS_TRY
     if (h2d_bytes_out) *h2d_bytes_out = moved;
     return MAS_OK;
+}
+
+extern "C" int mas_from_prior_host_f32(const float *mu_x_host, const float *y_host,
+                                       const int32_t *t_x_host, const int32_t *t_y_host,
+                                       float *mu_x_dev, float *y_dev, int32_t *t_x_dev,
+                                       int32_t *t_y_dev, void *path, int path_dtype,
+                                       int32_t *durations, int32_t *frame_idx, float *score,
+                                       int32_t *durations_host, float *score_host, int B, int F,
+                                       int T_x, int T_y, void *workspace, size_t workspace_bytes,
+                                       int chunk, int flags, void *stream,
+                                       uint64_t *h2d_bytes_out)
+{
+    return mas_from_prior_host_peer_f32(mu_x_host, y_host, t_x_host, t_y_host, mu_x_dev, y_dev, t_x_dev,
+                                        t_y_dev, path, path_dtype, durations, frame_idx, score,
+                                        durations_host, score_host, B, F, T_x, T_y, workspace,
+                                        workspace_bytes, chunk, flags, stream, h2d_bytes_out, nullptr);
 }

@@ -52,6 +52,9 @@ Plan choose_plan(int T_x, int T_y, int flags, FastLayout *lay, size_t extra_smem
 cudaError_t launch_lengths_from_mask(const void *mask, int mask_dtype, int B, int T_x, int T_y,
                                      int64_t sb, int64_t sx, int64_t sy, int32_t *t_x, int32_t *t_y,
                                      cudaStream_t st);
+cudaError_t launch_seq_lengths(const void *xm, int xdt, int64_t xsb, int64_t xst, const void *ym, int ydt,
+                               int64_t ysb, int64_t yst, int B, int T_x, int T_y, int32_t *t_x, int32_t *t_y,
+                               cudaStream_t st);
 cudaError_t launch_fast(const MasArgs &a, int value_dtype, cudaStream_t st);
 cudaError_t launch_general(const MasArgs &a, int value_dtype, cudaStream_t st);
 cudaError_t launch_generate_path(const void *dur, int dur_dtype, const int32_t *t_x,
@@ -126,9 +129,10 @@ struct PriorTcArgs {
     float *score;
     long long *stats;      // optional [grid][32] cycle counters (MAS_PRIOR_STATS=1), else NULL
     float *lp_out;         // optional parity tap [B,T_x,T_y]: the prior exactly as the DP consumed it
-    int32_t *peer[kMaxPeers];   // mas_set_peer_durations: every rank's [world*B, T_x] buffer, or npeer == 0
+    int32_t *peer[kMaxPeers];      // mas_peer_gather: every rank's durations buffer, or npeer == 0
+    int32_t *peer_fi[kMaxPeers];   // and (optionally, else NULL) every rank's frame-index buffer
     int npeer;
-    long long peer_row0;
+    long long peer_row0, peer_stride, peer_fi_stride;
     int B, F, T_x, T_y;
     int path_esize;
     unsigned long long one;
@@ -136,10 +140,12 @@ struct PriorTcArgs {
 };
 TcLayout tc_layout(int F, int T_x, int T_y);
 cudaError_t launch_from_prior_tc(const PriorTcArgs &a, cudaStream_t st);
-TcLayout tc2_layout(int F, int T_x, int T_y);   // mas_prior_tc2.cu: DP straight from tensor memory
-cudaError_t launch_from_prior_tc2(const PriorTcArgs &a, cudaStream_t st);
 
-extern thread_local long long t_peer_row_extra;   // mas_api.cu: chunk offset of the host-buffer entry
+int from_prior_impl(const float *mu_x, const float *logs, const float *y, const int32_t *t_x,
+                    const int32_t *t_y, void *path, int path_dtype, int32_t *durations,
+                    int32_t *frame_idx, float *score, float *log_prior_out, int B, int F, int T_x,
+                    int T_y, void *workspace, size_t workspace_bytes, int flags, cudaStream_t st,
+                    const mas_peer_gather *peer, long long row_extra);
 int sm_count();
 int sm_reserve();   // SMs the persistent kernels leave free (mas_set_sm_reserve)
 void count_launch(int n = 1);

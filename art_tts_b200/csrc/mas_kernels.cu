@@ -66,6 +66,42 @@ cudaError_t launch_lengths_from_mask(const void *mask, int mask_dtype, int B, in
     return cudaGetLastError();
 }
 
+// lengths from the two sequence masks of the fused entry (tts.py:477-480 builds attn_mask from
+// x_mask [B,1,T_x] and y_mask [B,1,T_y]; summing them is what mask.sum(1)[:,0] / mask.sum(2)[:,0]
+// of their outer product gives, __init__.py:20-21): one launch instead of four eager torch ops
+__global__ void __launch_bounds__(128) seq_lengths_kernel(const void *xm, int xdt, int64_t xsb, int64_t xst,
+                                                          const void *ym, int ydt, int64_t ysb, int64_t yst,
+                                                          int T_x, int T_y, int32_t *t_x, int32_t *t_y)
+{
+    const int b = blockIdx.x;
+    double ax = 0.0, ay = 0.0;
+    for (int x = threadIdx.x; x < T_x; x += blockDim.x) ax += mask_elem(xm, xdt, b * xsb + x * xst);
+    for (int y = threadIdx.x; y < T_y; y += blockDim.x) ay += mask_elem(ym, ydt, b * ysb + y * yst);
+    __shared__ double red[2][4];
+    for (int o = 16; o > 0; o >>= 1) {
+        ax += __shfl_xor_sync(kFull, ax, o);
+        ay += __shfl_xor_sync(kFull, ay, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        red[0][threadIdx.x >> 5] = ax;
+        red[1][threadIdx.x >> 5] = ay;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        t_x[b] = static_cast<int32_t>(red[0][0] + red[0][1] + red[0][2] + red[0][3]);
+        t_y[b] = static_cast<int32_t>(red[1][0] + red[1][1] + red[1][2] + red[1][3]);
+    }
+}
+
+cudaError_t launch_seq_lengths(const void *xm, int xdt, int64_t xsb, int64_t xst, const void *ym, int ydt,
+                               int64_t ysb, int64_t yst, int B, int T_x, int T_y, int32_t *t_x, int32_t *t_y,
+                               cudaStream_t st)
+{
+    seq_lengths_kernel<<<B, 128, 0, st>>>(xm, xdt, xsb, xst, ym, ydt, ysb, yst, T_x, T_y, t_x, t_y);
+    count_launch();
+    return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------
 // fast kernel
 // ------------------------------------------------------------------------------------

@@ -16,21 +16,21 @@
 // in shared memory, so a tile costs 60 MMAs of 128x32x8 and no CUDA-core arithmetic beyond
 // the three adds of tts.py:495.
 //
-// Persistent CTA per SM, 12 warps, all hand-offs are mbarriers:
-//   warps 0-3  epilogue (TMEM lane quarter = warp id): per tile tcgen05.ld the accumulator,
-//              add the y / mu / const terms and write the swizzled tile the DP warp consumes
-//              (same ring layout as the other kernels)
-//   warps 8-11 mu_x movers (TMEM lane quarter = warp id - 8): run one utterance AHEAD -- hold
-//              the next utterance's mu_x in registers (global loads issued while the current
-//              one is still being multiplied) and, the moment its last MMA has retired, split
-//              it into tf32 hi/lo and tcgen05.st it into TMEM; also produce -0.5|mu|^2
-//   warp 4     DP warp        (mas_dp.cuh dp_forward, unchanged)
-//   warp 5     MMA issuer     (one lane): tiles are issued in PAIRS, interleaving the MMAs of
-//              their (up to four) independent accumulators -- back-to-back MMAs into the same
-//              accumulator serialise at ~100 cycles each (measured), independent ones overlap
-//   warp 6     slab loader    (cp.async y slabs in the MN-major SWIZZLE_128B_BASE32B layout,
-//              tf32 hi/lo split in place, -0.5|y|^2 per frame, bulk zero-fill of the path)
-//   warp 7     backtrack warp (unchanged: one utterance behind, second direction-bit buffer)
+// Persistent CTA per SM, 14 warps (kTc* below), all hand-offs are mbarriers:
+//   warps 0-3   epilogue (TMEM lane quarter = warp id): per tile tcgen05.ld the accumulator,
+//               add the y / mu / const terms and write the swizzled tile the DP warps consume
+//   warps 4, 13 DP warps (mas_dp.cuh dp_forward2: the token axis split over 64 lanes)
+//   warp 5      MMA issuer (one elected lane): tiles are issued in PAIRS, interleaving the MMAs of
+//               their (up to four) independent accumulators -- back-to-back MMAs into the same
+//               accumulator serialise at ~100 cycles each (measured), independent ones overlap
+//   warps 6, 7  slab loaders (alternate tiles): cp.async y slab -> staging -> one transposing pass
+//               into the K-major SWIZZLE_32B hi/lo slab, -0.5|y|^2 per frame; the even loader also
+//               issues the bulk (TMA) zero fill of the dense output path
+//   warps 8-11  mu_x movers (TMEM lane quarter = warp id - 8): run one utterance AHEAD -- hold
+//               the next utterance's mu_x in registers and, the moment its last MMA has retired,
+//               split it into tf32 hi/lo and tcgen05.st it into TMEM; also produce -0.5|mu|^2
+//   warp 12     backtrack warp (one utterance behind, second direction-bit buffer): path ones,
+//               durations, frame index, peer-memory rows of the fused all-gather
 #include <algorithm>
 #include <type_traits>
 
@@ -353,11 +353,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) mas_prior_tc_kernel(const Prior
                             a.path_esize, a.one, lane, 32);
             write_frame_idx(a.frame_idx ? a.frame_idx + (int64_t)u * T_y : nullptr, first, dur, T_x, ty, a.T_y,
                             lane, 32);
-            // fused all-gather of the durations (mas_set_peer_durations): the row of this utterance goes
-            // straight into row row0 + u of every rank's buffer over NVLink peer memory
+            // fused all-gather (mas_peer_gather): the rows of this utterance go straight into row
+            // row0 + u of every rank's buffers over NVLink peer memory (fire-and-forget stores)
             for (int p = 0; p < a.npeer; ++p) {
-                int32_t *row = a.peer[p] + (a.peer_row0 + u) * (long long)T_x;
+                int32_t *row = a.peer[p] + (a.peer_row0 + u) * a.peer_stride;
                 for (int x = lane; x < T_x; x += 32) row[x] = dur[x];
+                if (a.peer_fi[p])
+                    write_frame_idx(a.peer_fi[p] + (a.peer_row0 + u) * a.peer_fi_stride, first, dur, T_x, ty, a.T_y,
+                                    lane, 32);
             }
             __syncwarp();
         }

@@ -101,49 +101,97 @@ class DurationGatherer:
 class PeerDurationGather:
     """All-gather of the durations done BY the fused kernel over NVLink peer memory.
 
-    Every rank owns a [world * b_local, t_x] int32 buffer in symmetric memory
-    (torch.distributed._symmetric_memory); the buffers of all ranks are mapped into every process and
-    handed to the library (mas_set_peer_durations), whose backtrack warp stores each utterance's
-    durations into row `rank * b_local + b` of every rank's buffer.  No collective kernel runs: after
-    the MAS kernel the ranks only meet in `finish()` (a symmetric-memory barrier, ~7 us at 2 GPUs against
-    25-44 us for the NCCL all-gather), after which `self.all` holds the durations of the whole batch.
-    Only the tensor-core engine of maximum_path_from_prior does this (`supported()`); everything else
-    must use the NCCL gathers above.  Process-wide library state: one instance at a time, `close()` it."""
+    Every rank owns `slots` (default 2) [world * b_local, t_x_max] int32 buffers in symmetric memory
+    (torch.distributed._symmetric_memory), each mapped into every process.  `desc()` describes the
+    buffer set of the next step (a `mas_peer_gather`, passed WITH the call -- the library keeps no
+    peer state); the backtrack warp of the tensor-core kernel stores each utterance's durations into
+    row `rank * b_local + b` of every rank's buffer.  No collective kernel runs: after the MAS kernel
+    the ranks only meet in `finish()` (a symmetric-memory barrier on the caller's stream, ~7 us at 2
+    GPUs against 25-44 us for the NCCL all-gather), which returns the gathered [world*b_local, t_x]
+    view for that step.
 
-    def __init__(self, b_local: int, t_x: int, device, group: Optional[dist.ProcessGroup] = None):
+    Buffer lifetime (the write-after-read hazard of a single buffer): step i uses slot i % slots.  A
+    rank's kernel of step i+slots can only start after that rank passed the barrier of step
+    i+slots-1, i.e. after EVERY rank enqueued-and-ran everything that precedes its own barrier
+    i+slots-1 on the stream it calls finish() on.  So the tensor returned by finish() for step i is
+    valid for consumers enqueued on that same stream before the rank's finish() of step i+slots-1
+    (with the default two slots: before its next finish()).  Consumers on other streams must make
+    the calling stream wait for them before the next finish() (or copy the rows out).
+    Only the tensor-core engine of maximum_path_from_prior writes peer memory (`supported()`);
+    everything else must use the NCCL gathers above."""
+
+    def __init__(self, b_local: int, t_x: int, device, group: Optional[dist.ProcessGroup] = None,
+                 slots: int = 2, channel: int = 0, frame_idx_len: int = 0):
         import ctypes
 
         import torch.distributed._symmetric_memory as symm
 
         from . import _lib
+        self._lib, self._ct = _lib, ctypes
         self.group = group if group is not None else dist.group.WORLD
         self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
         if self.world > 16:
             raise ValueError("PeerDurationGather: at most 16 ranks (one NVLink domain)")
-        self.b_local, self.t_x = b_local, t_x
-        self.all = symm.empty((self.world * b_local, t_x), dtype=torch.int32, device=device)
-        self.all.zero_()
-        self.hdl = symm.rendezvous(self.all, self.group.group_name)
-        ptrs = (ctypes.c_uint64 * self.world)(*[int(p) for p in self.hdl.buffer_ptrs])
-        _lib.check(_lib.load().mas_set_peer_durations(self.world, ptrs, self.rank * b_local, b_local, t_x),
-                   "mas_set_peer_durations")
+        if slots < 2:
+            raise ValueError("PeerDurationGather needs >= 2 slots (see the class docstring)")
+        self.b_local, self.t_x, self.slots, self.channel = b_local, t_x, slots, channel
+        self.t_y = int(frame_idx_len)
+        self.step = 0
+        rows = self.world * b_local
+        # ONE symmetric allocation (one rendezvous) carved into the slots
+        per = rows * t_x + rows * self.t_y
+        self.buf = symm.empty((slots * per,), dtype=torch.int32, device=device)
+        self.buf.zero_()
+        self.hdl = symm.rendezvous(self.buf, self.group.group_name)
+        base = [int(p) for p in self.hdl.buffer_ptrs]
+        self.all, self.all_fi, self._dptr, self._fptr = [], [], [], []
+        for s in range(slots):
+            o = s * per
+            self.all.append(self.buf[o:o + rows * t_x].view(rows, t_x))
+            self._dptr.append((ctypes.c_uint64 * self.world)(*[p + 4 * o for p in base]))
+            if self.t_y:
+                o2 = o + rows * t_x
+                self.all_fi.append(self.buf[o2:o2 + rows * self.t_y].view(rows, self.t_y))
+                self._fptr.append((ctypes.c_uint64 * self.world)(*[p + 4 * o2 for p in base]))
         torch.cuda.synchronize(device)
-        self.hdl.barrier(channel=0)
+        self.hdl.barrier(channel=self.channel)
 
     @staticmethod
     def supported(B: int, F: int, T_x: int, T_y: int, flags: int = 0) -> bool:
         from . import _lib
         return bool(_lib.load().mas_peer_durations_supported(B, F, T_x, T_y, flags))
 
-    def finish(self) -> torch.Tensor:
-        """Call after maximum_path_from_prior on the same stream: once every rank's kernel of this step
-        has completed (its peer stores are then visible), returns the gathered durations."""
-        self.hdl.barrier(channel=0)
-        return self.all
+    def desc(self, b_call: Optional[int] = None):
+        """`mas_peer_gather` for the step about to be launched (slot = step % slots).  `b_call`:
+        utterances of the call when fewer than b_local (a ragged last shard)."""
+        ct = self._ct
+        s = self.step % self.slots
+        d = self._lib.PeerGatherDesc()
+        d.n_peers = self.world
+        d.durations_ptrs = ct.cast(self._dptr[s], ct.POINTER(ct.c_uint64))
+        d.row0 = self.rank * self.b_local
+        d.rows = self.b_local if b_call is None else int(b_call)
+        d.row_stride = self.t_x
+        if self.t_y:
+            d.frame_idx_ptrs = ct.cast(self._fptr[s], ct.POINTER(ct.c_uint64))
+            d.frame_idx_stride = self.t_y
+        else:
+            d.frame_idx_ptrs = None
+            d.frame_idx_stride = 0
+        return d
+
+    def finish(self):
+        """Call after maximum_path_from_prior(..., peer=self.desc()) on the same stream: once every
+        rank's kernel of this step has completed (its peer stores are then visible), returns the
+        gathered durations of the step (and the frame index when frame_idx_len was given); advances to
+        the next slot.  See the class docstring for how long the returned view stays valid."""
+        s = self.step % self.slots
+        self.hdl.barrier(channel=self.channel)
+        self.step += 1
+        return (self.all[s], self.all_fi[s]) if self.t_y else self.all[s]
 
     def close(self) -> None:
-        from . import _lib
-        _lib.check(_lib.load().mas_set_peer_durations(0, None, 0, 0, 0), "mas_set_peer_durations")
+        pass   # nothing process-wide to undo: the description travels with every call
 
 
 def maximum_path_from_prior_sharded(mu_x, y, t_x, t_y, *, group=None, rebuild_path=False):

@@ -28,6 +28,7 @@ __all__ = [
     "maximum_path_from_prior",
     "maximum_path_from_prior_host",
     "lengths_from_mask",
+    "lengths_from_seq_masks",
 ]
 
 _FLOAT_VALUE = (torch.float32, torch.float16, torch.bfloat16, torch.float64)
@@ -103,19 +104,20 @@ def maximum_path_lengths(value: torch.Tensor, t_x: torch.Tensor, t_y: torch.Tens
     return out[0] if len(out) == 1 else tuple(out)
 
 
-def maximum_path(value: torch.Tensor, mask: torch.Tensor, *, strict_mask: bool = False):
+def maximum_path(value: torch.Tensor, mask: torch.Tensor, *, strict_mask: bool = True):
     """Drop-in for the reference's `maximum_path(value, mask)` (__init__.py:8-23).
 
     value: [b, t_x, t_y] float tensor on a CUDA device;  mask: [b, t_x, t_y] 0/1.
     Returns the hard monotonic alignment [b, t_x, t_y] with entries {0,1}, in the dtype of
     `value * mask` and on value's device -- bit-exact with the reference's Cython kernel.
 
-    The reference multiplies every cell by the mask and reads the lengths from the mask's
-    first column/row.  For the rectangular sequence masks its callers build
-    (tts.py:477-480: x_mask[..., None] * y_mask[:, :, None]) the multiplication is the
-    identity on every cell the algorithm touches, so by default only that column and row of
-    the mask are read (8 B/cell of HBM traffic instead of 12).  Pass strict_mask=True to
-    apply the mask per cell as well (needed only for masks with holes)."""
+    Like the reference, every cell is multiplied by the mask (__init__.py:13) and the lengths
+    are read from the mask's first column / row (__init__.py:20-21): exact for ANY mask,
+    12 B/cell of HBM traffic.  For the rectangular sequence masks the reference's callers build
+    (tts.py:477-480: x_mask[..., None] * y_mask[:, :, None]) the multiplication is the identity
+    on every cell the algorithm touches; pass strict_mask=False there (or call
+    maximum_path_lengths) and only that column and row of the mask are read (8 B/cell).
+    strict_mask=False on a mask with holes gives a different path than the reference."""
     if value.shape != mask.shape:
         raise ValueError(f"value {tuple(value.shape)} and mask {tuple(mask.shape)} differ")
     _lib.require_cuda(value, "value")
@@ -135,15 +137,43 @@ def maximum_path(value: torch.Tensor, mask: torch.Tensor, *, strict_mask: bool =
     return maximum_path_lengths(value, t_x, t_y, out_dtype=out_dtype, cell_mask=cell_mask)
 
 
+def lengths_from_seq_masks(x_mask: torch.Tensor, y_mask: torch.Tensor,
+                           T_x: int, T_y: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """t_x = sum(x_mask[b]), t_y = sum(y_mask[b]) as int32, one kernel launch: the lengths the
+    reference would read off attn_mask = x_mask[..., None] * y_mask[:, :, None] (tts.py:477-480,
+    __init__.py:20-21).  Masks are [B,1,T] or [B,T], any dtype, any strides."""
+    _lib.require_cuda(x_mask, "x_mask")
+    _lib.require_cuda(y_mask, "y_mask")
+    B = x_mask.shape[0]
+    xm = x_mask.reshape(B, -1) if x_mask.dim() != 2 else x_mask
+    ym = y_mask.reshape(B, -1) if y_mask.dim() != 2 else y_mask
+    if xm.shape[1] != T_x or ym.shape[1] != T_y or ym.shape[0] != B:
+        raise ValueError("mask length does not match the tensor it masks")
+    dev = x_mask.device
+    t_x = torch.empty(B, dtype=torch.int32, device=dev)
+    t_y = torch.empty(B, dtype=torch.int32, device=dev)
+    if B == 0:
+        return t_x, t_y
+    with torch.cuda.device(dev):
+        code = _lib.load().mas_lengths_from_seq_masks(
+            _lib.ptr(xm), _lib.dtype_code(xm.dtype), xm.stride(0), xm.stride(1),
+            _lib.ptr(ym), _lib.dtype_code(ym.dtype), ym.stride(0), ym.stride(1),
+            B, T_x, T_y, _lib.ptr(t_x), _lib.ptr(t_y), _lib.stream_ptr(dev))
+    _lib.check(code, "mas_lengths_from_seq_masks")
+    return t_x, t_y
+
+
 def maximum_path_from_prior(mu_x: torch.Tensor, logs: Optional[torch.Tensor], y: torch.Tensor,
                             x_mask: torch.Tensor, y_mask: torch.Tensor, *,
                             return_score: bool = False, return_frame_idx: bool = False,
                             return_log_prior: bool = False, want_path: bool = True,
-                            flags: int = 0):
+                            flags: int = 0, peer=None):
     """Fused Gaussian log-prior + MAS + durations (replaces tts.py:483-505).
 
     mu_x [B,F,T_x], y [B,F,T_y] fp32;  x_mask [B,1,T_x], y_mask [B,1,T_y] 0/1 sequence masks
     (or int lengths [B]).  `logs` must be None: the reference's prior has unit variance.
+    `peer`: a `_lib.PeerGatherDesc` (see distributed.PeerDurationGather) -- the kernel also stores
+    the durations rows into every rank's peer-mapped buffer.
     Returns (path [B,T_x,T_y] in mu_x.dtype, durations [B,T_x] int32), followed by the
     optional extras in the order score [B] fp32, frame_idx [B,T_y] int32, log_prior."""
     if logs is not None:
@@ -159,16 +189,15 @@ def maximum_path_from_prior(mu_x: torch.Tensor, logs: Optional[torch.Tensor], y:
     mu32 = mu_x.detach().to(torch.float32).contiguous()
     y32 = y.detach().to(torch.float32).contiguous()
 
-    def lengths(m, T):
-        if m.dim() == 1:
-            return m.to(device=dev, dtype=torch.int32).contiguous()
-        m2 = m.reshape(B, -1)
-        if m2.shape[1] != T:
-            raise ValueError("mask length does not match the tensor it masks")
-        return m2.to(device=dev).sum(1).to(torch.int32)
-
-    t_x = lengths(x_mask, T_x)
-    t_y = lengths(y_mask, T_y)
+    if x_mask.dim() == 1 and y_mask.dim() == 1:       # int lengths [B]
+        t_x = x_mask.to(device=dev, dtype=torch.int32).contiguous()
+        t_y = y_mask.to(device=dev, dtype=torch.int32).contiguous()
+        if t_x.numel() != B or t_y.numel() != B:
+            raise ValueError("lengths must have one entry per utterance")
+    elif x_mask.dim() == 1 or y_mask.dim() == 1:
+        raise ValueError("pass either two masks or two length vectors")
+    else:                                              # sequence masks: one kernel, no eager torch ops
+        t_x, t_y = lengths_from_seq_masks(x_mask.to(dev), y_mask.to(dev), T_x, T_y)
     path = torch.empty((B, T_x, T_y), dtype=out_dtype, device=dev) if want_path else None
     dur = torch.empty((B, T_x), dtype=torch.int32, device=dev)
     score = torch.empty((B,), dtype=torch.float32, device=dev) if return_score else None
@@ -182,10 +211,11 @@ def maximum_path_from_prior(mu_x: torch.Tensor, logs: Optional[torch.Tensor], y:
         with torch.cuda.device(dev):
             nws = int(lib.mas_workspace_bytes(B, T_x, T_y))
             ws = _lib.workspace(dev, nws)
-            code = lib.mas_from_prior_f32(
+            code = lib.mas_from_prior_peer_f32(
                 _lib.ptr(mu32), None, _lib.ptr(y32), _lib.ptr(t_x), _lib.ptr(t_y), _lib.ptr(path),
                 _lib.dtype_code(out_dtype), _lib.ptr(dur), _lib.ptr(fidx), _lib.ptr(score),
-                _lib.ptr(lp), B, F, T_x, T_y, _lib.ptr(ws), ws.numel(), flags, _lib.stream_ptr(dev))
+                _lib.ptr(lp), B, F, T_x, T_y, _lib.ptr(ws), ws.numel(), flags, _lib.stream_ptr(dev),
+                ctypes.byref(peer) if peer is not None else None)
         _lib.check(code, "mas_from_prior_f32")
     out = [path, dur] if want_path else [dur]
     for flag, t in ((return_score, score), (return_frame_idx, fidx), (return_log_prior, lp)):
@@ -197,11 +227,32 @@ def maximum_path_from_prior(mu_x: torch.Tensor, logs: Optional[torch.Tensor], y:
 _staging = {}
 
 
+def _host_staging(dev, B, F, T_x, T_y):
+    """Device staging of the host-buffer entry: one grow-only flat buffer per (device, stream) -- the
+    library orders its copies against the caller's stream only, so two streams must not share one --
+    carved into the padded shapes of this call (varying padded shapes reuse the same memory)."""
+    key = (dev.index, torch.cuda.current_stream(dev).cuda_stream)
+    def up4(n):               # keep every piece 16-byte aligned (vectorised loads of the kernels)
+        return (n + 3) // 4 * 4
+
+    n1, n2 = B * F * T_x, B * F * T_y
+    o1 = up4(n1)
+    o2 = o1 + up4(n2)
+    o3 = o2 + up4(B)
+    need = o3 + B
+    buf = _staging.get(key)
+    if buf is None or buf.numel() < need:
+        buf = torch.empty(max(need, 1 << 16), dtype=torch.float32, device=dev)
+        _staging[key] = buf
+    return (buf[:n1].view(B, F, T_x), buf[o1:o1 + n2].view(B, F, T_y),
+            buf[o2:o2 + B].view(torch.int32), buf[o3:o3 + B].view(torch.int32))
+
+
 def maximum_path_from_prior_host(mu_x: torch.Tensor, y: torch.Tensor, x_lengths: torch.Tensor,
                                  y_lengths: torch.Tensor, device=None, *, want_path: bool = True,
                                  out_dtype: torch.dtype = torch.float32, chunk: int = 0,
                                  durations_host: Optional[torch.Tensor] = None,
-                                 score_host: Optional[torch.Tensor] = None, flags: int = 0):
+                                 score_host: Optional[torch.Tensor] = None, flags: int = 0, peer=None):
     """Fused prior + MAS for a batch that still lives in HOST memory (the data loader's pinned
     tensors; train_v2.py:203 -> tts.py:466 moves the whole padded batch first).
 
@@ -232,15 +283,8 @@ def maximum_path_from_prior_host(mu_x: torch.Tensor, y: torch.Tensor, x_lengths:
     lib = _lib.load()
     if B and lib.mas_from_prior_plan(B, F, T_x, T_y, flags) != 0:
         raise ValueError("shape needs the unfused plan; copy the batch and call maximum_path_from_prior")
-    key = (dev.index, B, F, T_x, T_y)
-    st = _staging.get(key)
-    if st is None:
-        _staging.clear()   # one shape at a time: the staging buffers are as large as the batch
-        st = (torch.empty((B, F, T_x), dtype=torch.float32, device=dev),
-              torch.empty((B, F, T_y), dtype=torch.float32, device=dev),
-              torch.empty((B,), dtype=torch.int32, device=dev),
-              torch.empty((B,), dtype=torch.int32, device=dev))
-        _staging[key] = st
+    with torch.cuda.device(dev):
+        st = _host_staging(dev, B, F, T_x, T_y)
     path = torch.empty((B, T_x, T_y), dtype=out_dtype, device=dev) if want_path else None
     dur = torch.empty((B, T_x), dtype=torch.int32, device=dev)
     score = torch.empty((B,), dtype=torch.float32, device=dev)
@@ -248,11 +292,12 @@ def maximum_path_from_prior_host(mu_x: torch.Tensor, y: torch.Tensor, x_lengths:
     if B:
         with torch.cuda.device(dev):
             ws = _lib.workspace(dev, int(lib.mas_workspace_bytes(B, T_x, T_y)))
-            code = lib.mas_from_prior_host_f32(
+            code = lib.mas_from_prior_host_peer_f32(
                 _lib.ptr(mu_x), _lib.ptr(y), _lib.ptr(tx), _lib.ptr(ty), _lib.ptr(st[0]),
                 _lib.ptr(st[1]), _lib.ptr(st[2]), _lib.ptr(st[3]), _lib.ptr(path),
                 _lib.dtype_code(out_dtype), _lib.ptr(dur), None, _lib.ptr(score),
                 _lib.ptr(durations_host), _lib.ptr(score_host), B, F, T_x, T_y, _lib.ptr(ws),
-                ws.numel(), int(chunk), flags, _lib.stream_ptr(dev), ctypes.byref(moved))
+                ws.numel(), int(chunk), flags, _lib.stream_ptr(dev), ctypes.byref(moved),
+                ctypes.byref(peer) if peer is not None else None)
         _lib.check(code, "mas_from_prior_host_f32")
     return path, dur, score, int(moved.value)

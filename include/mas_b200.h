@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define MAS_ABI_VERSION 1
+#define MAS_ABI_VERSION 2
 
 /* element types accepted for value / mask / path tensors */
 enum {
@@ -48,8 +48,9 @@ enum {
     MAS_ERR_WORKSPACE = -4, /* workspace missing or smaller than *_workspace_bytes */
     MAS_ERR_ALIGN = -5,     /* pointer not aligned to its element size             */
     MAS_ERR_NO_DEVICE = -6, /* no sm_100 device / driver available                 */
-    MAS_ERR_PEER = -7       /* mas_set_peer_durations is active but this call would run an engine
-                               that does not write peer memory (mas_peer_durations_supported)     */
+    MAS_ERR_PEER = -7       /* a mas_peer_gather was passed but this call would run an engine that does
+                               not write peer memory (mas_peer_durations_supported), or the call does
+                               not fit the peers' buffers                                           */
 };
 
 /* flags for mas_maximum_path / mas_from_prior_f32 */
@@ -77,6 +78,17 @@ const char *mas_strerror(int code);
 int mas_lengths_from_mask(const void *mask, int mask_dtype, int B, int T_x, int T_y,
                           int64_t stride_b, int64_t stride_x, int64_t stride_y,
                           int32_t *t_x_out, int32_t *t_y_out, void *stream);
+
+/*
+ * The same for the fused entry, whose caller holds the two sequence masks the reference multiplies
+ * into attn_mask (tts.py:477-480): t_x = sum(x_mask[b]), t_y = sum(y_mask[b]) -- what
+ * mask.sum(1)[:,0] / mask.sum(2)[:,0] give on their outer product.  Strides in elements
+ * (batch, time), so [B,1,T] views need no copy.
+ */
+int mas_lengths_from_seq_masks(const void *x_mask, int x_dtype, int64_t x_stride_b, int64_t x_stride_t,
+                               const void *y_mask, int y_dtype, int64_t y_stride_b, int64_t y_stride_t,
+                               int B, int T_x, int T_y, int32_t *t_x_out, int32_t *t_y_out,
+                               void *stream);
 
 /*
  * Bytes of scratch mas_maximum_path / mas_from_prior_f32 need for this shape (packed
@@ -261,18 +273,49 @@ int mas_set_sm_reserve(int n_sms);
 
 /*
  * Data-parallel training (train_v1_1_dist.py:249): the only exchange of the path is the
- * all-gather of the int32 durations.  With peer-mapped buffers (NVLink peer memory: CUDA IPC / VMM handles,
- * e.g. torch.distributed._symmetric_memory) the fused tensor-core kernel does it itself: besides
- * `durations`, its backtrack warp stores every utterance's row into row `row0 + b` of EACH of the n_peers
- * buffers (this rank's own buffer among them), so that no collective kernel runs at all; afterwards the
- * ranks only need a barrier.  peer_ptrs[i] = base of rank i's [world*B, T_x] int32 buffer as mapped in
- * this process; `rows` = utterances this rank may write (B of one call, or of one host-buffer call) and
- * T_x the row length: a call with another T_x or more utterances is refused (MAS_ERR_PEER) instead of
- * writing outside the buffers.  n_peers = 0 switches it off (default).  Process-wide setting, honoured by
- * mas_from_prior_f32 / mas_from_prior_host_f32 when mas_peer_durations_supported() says so for the shape.
- * No reference equivalent (the reference runs one independent MAS per rank and never exchanges durations).
+ * all-gather of the int32 durations (optionally the frame index).  With peer-mapped buffers (NVLink peer
+ * memory: CUDA IPC / VMM handles, e.g. torch.distributed._symmetric_memory) the fused tensor-core kernel
+ * does it itself: besides `durations`, its backtrack warp stores every utterance's row into row
+ * `row0 + b` of EACH of the n_peers buffers (this rank's own among them), so that no collective kernel
+ * runs at all; afterwards the ranks only need a barrier.
+ *
+ * The description travels WITH THE CALL (no process-wide state): any number of streams, devices and
+ * buffer sets may be in flight, and a caller alternates two buffer sets (step parity) so that a fast rank's
+ * next step never overwrites rows a slower rank is still reading.
+ *   durations_ptrs[i]  base of rank i's [rows_total, row_stride] int32 buffer as mapped in this process
+ *   row0               first row this call writes (rank * B for a batch-sharded step)
+ *   rows               rows this call may write, counted from row0: B of the call (of the whole
+ *                      host-buffer call for mas_from_prior_host_peer_f32); more -> MAS_ERR_PEER
+ *   row_stride         elements between rows, >= T_x (one buffer serves every padded T_x up to it)
+ *   frame_idx_ptrs     NULL, or [n_peers] bases of [rows_total, frame_idx_stride] int32 buffers that
+ *                      receive the token index of every frame (-1 on padding), frame_idx_stride >= T_y
+ * Only the tensor-core engine writes peer memory (mas_peer_durations_supported); every other plan
+ * refuses the call with MAS_ERR_PEER rather than leave the buffers unwritten.  n_peers == 0 or a NULL
+ * description = plain mas_from_prior_f32.  No reference equivalent (the reference runs one independent
+ * MAS per rank and never exchanges durations).
  */
-int mas_set_peer_durations(int n_peers, const uint64_t *peer_ptrs, int64_t row0, int64_t rows, int T_x);
+typedef struct mas_peer_gather {
+    int n_peers;
+    const uint64_t *durations_ptrs;
+    int64_t row0, rows, row_stride;
+    const uint64_t *frame_idx_ptrs;
+    int64_t frame_idx_stride;
+} mas_peer_gather;
+
+int mas_from_prior_peer_f32(const float *mu_x, const float *logs, const float *y,
+                            const int32_t *t_x, const int32_t *t_y, void *path, int path_dtype,
+                            int32_t *durations, int32_t *frame_idx, float *score,
+                            float *log_prior_out, int B, int F, int T_x, int T_y, void *workspace,
+                            size_t workspace_bytes, int flags, void *stream,
+                            const mas_peer_gather *peer);
+int mas_from_prior_host_peer_f32(const float *mu_x_host, const float *y_host, const int32_t *t_x_host,
+                                 const int32_t *t_y_host, float *mu_x_dev, float *y_dev,
+                                 int32_t *t_x_dev, int32_t *t_y_dev, void *path, int path_dtype,
+                                 int32_t *durations, int32_t *frame_idx, float *score,
+                                 int32_t *durations_host, float *score_host, int B, int F, int T_x,
+                                 int T_y, void *workspace, size_t workspace_bytes, int chunk,
+                                 int flags, void *stream, uint64_t *h2d_bytes_out,
+                                 const mas_peer_gather *peer);
 int mas_peer_durations_supported(int B, int F, int T_x, int T_y, int flags);
 
 /* Kernel launches enqueued by this library in this process (bench.py's gpu_launches). */

@@ -42,6 +42,18 @@ def seeded_case(seed, B, T_x, T_y, kind):
     return value, t_x, t_y
 
 
+def cfg3_inputs(n_vocab=149, B=64, T_x=190, T_y=872, n_feats=80, seed=3):
+    """Same recipe as tests/golden/make_golden.py::cfg3_inputs (keep in sync)."""
+    rng = np.random.default_rng(seed)
+    x_lengths = rng.integers(60, T_x + 1, B).astype(np.int64)
+    y_lengths = np.minimum(870, 4 * x_lengths + rng.integers(0, 100, B)).astype(np.int64)
+    x_lengths[0], y_lengths[0] = T_x, 870
+    x = rng.integers(0, n_vocab, (B, T_x)).astype(np.int64)
+    y = rng.standard_normal((B, n_feats, T_y), dtype=np.float32)
+    y *= (np.arange(T_y)[None, None, :] < y_lengths[:, None, None])
+    return x, x_lengths, y, y_lengths
+
+
 def rect_mask(t_x, t_y, T_x, T_y, dtype=np.float32):
     m = (np.arange(T_x)[None, :, None] < np.asarray(t_x)[:, None, None]) & \
         (np.arange(T_y)[None, None, :] < np.asarray(t_y)[:, None, None])

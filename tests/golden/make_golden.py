@@ -17,8 +17,16 @@ Outputs (committed):
                      y_cut_mask, mu_y as handed to the decoder, dur_loss, prior_loss and the
                      autograd gradients of (dur_loss + prior_loss) w.r.t. mu_x and logw
 
+  generate_path.npz  the reference's own model.utils.generate_path (utils.py:26-43) on the inference
+                     call site's inputs (tts.py:130-147): int64 / fp32 durations, length_scale 1.0 / 1.3
+  cfg3_gradtts.npz   BASELINE config 3 at its stated size: GradTTS(params_v2) compute_loss, B=64,
+                     T_x<=190, T_y<=872, out_size=172 -- inputs by seeded recipe (+ sha256), reference
+                     durations, losses, sha256 of log_prior and of the path
+
 Run:  python tests/golden/make_golden.py            (everything)
       python tests/golden/make_golden.py --only loss  (just loss_block_gradtts.npz)
+      python tests/golden/make_golden.py --only gp    (just generate_path.npz)
+      python tests/golden/make_golden.py --only cfg3  (just cfg3_gradtts.npz)
 """
 from __future__ import annotations
 
@@ -147,14 +155,150 @@ def loss_block(shim):
         grad_mu_x=enc["mu_x"].grad.numpy(), grad_logw=enc["logw"].grad.numpy())
 
 
+def generate_path_golden():
+    """The reference's generate_path on what its inference path feeds it (tts.py:130-147):
+    w_ceil = ceil(w) * length_scale (fp32, fractional when length_scale != 1), y_lengths =
+    clamp_min(sum(w_ceil), 1).long(), mask = x_mask[..., None] * y_mask[:, :, None]; plus the
+    integer durations MAS itself produces (the all-gather path rebuilds dense paths from those)."""
+    import torch
+    from model.utils import fix_len_compatibility, generate_path, sequence_mask
+
+    out, names = {}, []
+    rng = np.random.default_rng(2025)
+
+    def call_site(name, w, x_lengths, length_scale):
+        B, T_x = w.shape
+        x_mask = sequence_mask(x_lengths, T_x).unsqueeze(1).float()
+        w = w.unsqueeze(1) * x_mask
+        w_ceil = torch.ceil(w) * length_scale
+        y_lengths = torch.clamp_min(torch.sum(w_ceil, [1, 2]), 1).long()
+        T_y = fix_len_compatibility(int(y_lengths.max()))
+        y_mask = sequence_mask(y_lengths, T_y).unsqueeze(1).to(x_mask.dtype)
+        attn_mask = x_mask.unsqueeze(-1) * y_mask.unsqueeze(2)
+        path = generate_path(w_ceil.squeeze(1), attn_mask.squeeze(1))
+        out[f"{name}.duration"] = w_ceil.squeeze(1).numpy()
+        out[f"{name}.x_lengths"] = x_lengths.numpy().astype(np.int32)
+        out[f"{name}.y_lengths"] = y_lengths.numpy().astype(np.int32)
+        out[f"{name}.T_y"] = np.int32(T_y)
+        out[f"{name}.path_packed"] = np.packbits(path.numpy().astype(np.uint8), axis=-1)
+        out[f"{name}.path_dtype"] = np.array(str(path.dtype))
+        names.append(name)
+
+    x_lengths = torch.tensor([37, 12, 1, 30, 25])
+    logw = torch.from_numpy(rng.standard_normal((5, 37)).astype(np.float32) * 0.7 + 1.0)
+    call_site("fp32_scale1", torch.exp(logw), x_lengths, 1.0)
+    call_site("fp32_scale1p3", torch.exp(logw), x_lengths, 1.3)
+    call_site("fp32_scale0p77", torch.exp(logw), x_lengths, 0.77)
+    xl = torch.tensor([190, 64, 128])
+    call_site("fp32_long", torch.exp(torch.from_numpy(rng.standard_normal((3, 190)).astype(np.float32) * 0.5 + 1.2)),
+              xl, 1.0)
+    # integer durations with a mask given directly (what MAS produces; int64 like attn.sum(-1).long())
+    for name, dt in (("int64", torch.int64), ("int32", torch.int32)):
+        B, T_x, T_y = 4, 21, 64
+        t_x = np.array([21, 9, 1, 16], np.int32)
+        t_y = np.array([64, 30, 5, 63], np.int32)
+        dur = np.zeros((B, T_x), np.int64)
+        for b in range(B):   # a random monotonic alignment: every token >= 1 frame
+            cuts = np.sort(rng.choice(np.arange(1, t_y[b]), t_x[b] - 1, replace=False)) if t_x[b] > 1 else []
+            edges = np.concatenate([[0], cuts, [t_y[b]]]).astype(np.int64)
+            dur[b, :t_x[b]] = np.diff(edges)
+        mask = torch.from_numpy(rect_mask(t_x, t_y, T_x, T_y))
+        path = generate_path(torch.from_numpy(dur).to(dt), mask)
+        out[f"{name}.duration"] = dur.astype(np.int64 if dt == torch.int64 else np.int32)
+        out[f"{name}.x_lengths"], out[f"{name}.y_lengths"] = t_x, t_y
+        out[f"{name}.T_y"] = np.int32(T_y)
+        out[f"{name}.path_packed"] = np.packbits(path.numpy().astype(np.uint8), axis=-1)
+        out[f"{name}.path_dtype"] = np.array(str(path.dtype))
+        names.append(name)
+    out["names"] = np.array(names)
+    np.savez_compressed(os.path.join(HERE, "generate_path.npz"), **out)
+
+
+def cfg3_inputs(n_vocab=149, B=64, T_x=190, T_y=872, n_feats=80, seed=3):
+    """Seeded inputs of the config-3 capture (shared with tests/conftest.py::cfg3_inputs, keep in
+    sync): ragged LJSpeech-shape lengths, token ids U{0..148}, y ~ N(0,1) * mask."""
+    rng = np.random.default_rng(seed)
+    x_lengths = rng.integers(60, T_x + 1, B).astype(np.int64)
+    y_lengths = np.minimum(870, 4 * x_lengths + rng.integers(0, 100, B)).astype(np.int64)
+    x_lengths[0], y_lengths[0] = T_x, 870
+    x = rng.integers(0, n_vocab, (B, T_x)).astype(np.int64)
+    y = rng.standard_normal((B, n_feats, T_y), dtype=np.float32)
+    y *= (np.arange(T_y)[None, None, :] < y_lengths[:, None, None])
+    return x, x_lengths, y, y_lengths
+
+
+def cfg3_golden():
+    """BASELINE config 3 at its stated size (tts.py:450-563, params_v2.py:57,61)."""
+    import importlib
+    import random
+
+    import torch
+    from model import GradTTS, monotonic_align
+
+    p2 = importlib.import_module("configs.params_v2")
+    torch.manual_seed(p2.random_seed)
+    n_vocab = 149
+    g = GradTTS(n_vocab, p2.n_spks, p2.spk_emb_dim, p2.n_enc_channels, p2.filter_channels,
+                p2.filter_channels_dp, p2.n_heads, p2.n_enc_layers, p2.enc_kernel, p2.enc_dropout,
+                p2.window_size, p2.n_feats, p2.dec_dim, p2.beta_min, p2.beta_max, p2.pe_scale)
+    g.eval()
+    x, x_lengths, y, y_lengths = cfg3_inputs(n_vocab=n_vocab, n_feats=p2.n_feats)
+    enc, dec, mas = {}, {}, {}
+    h = g.encoder.register_forward_hook(lambda m, i, o: enc.update(mu_x=o[0], logw=o[1], x_mask=o[2]))
+
+    def fake_decoder_loss(y_, y_mask_, mu_y_, spk=None):
+        dec.update(y=y_.detach().clone(), y_mask=y_mask_.detach().clone(), mu_y=mu_y_.detach().clone())
+        return torch.zeros(()), None
+
+    real_mp = monotonic_align.maximum_path
+
+    def spy(value, mask):
+        mas["log_prior"] = value.detach().clone()
+        path = real_mp(value, mask)
+        mas["attn"] = path.detach().clone()
+        return path
+
+    g.decoder.compute_loss = fake_decoder_loss
+    monotonic_align.maximum_path = spy
+    seed = 373
+    random.seed(seed)
+    with torch.no_grad():
+        dur_loss, prior_loss, _ = g.compute_loss(torch.from_numpy(x), torch.from_numpy(x_lengths),
+                                                 torch.from_numpy(y), torch.from_numpy(y_lengths),
+                                                 out_size=p2.out_size)
+    monotonic_align.maximum_path = real_mp
+    h.remove()
+    attn = mas["attn"].numpy()
+    lp = mas["log_prior"].numpy()
+    tx, ty = x_lengths.astype(np.int32), y_lengths.astype(np.int32)
+    score = np.zeros(len(tx), np.float64)   # total alignment log-likelihood = sum of lp on the path
+    for b in range(len(tx)):
+        score[b] = float((lp[b].astype(np.float64) * attn[b]).sum())
+    np.savez_compressed(
+        os.path.join(HERE, "cfg3_gradtts.npz"),
+        recipe=np.array([64, 190, 872, 80, 3], np.int64), out_size=np.int32(p2.out_size),
+        random_seed=np.int32(seed), x_sha256=np.array(sha(x)), y_sha256=np.array(sha(y)),
+        # mu_x is an encoder output (conv/attention stack): stored, fp16-exact storage is not enough
+        mu_x=enc["mu_x"].detach().numpy(), logw=enc["logw"].detach().numpy(),
+        x_lengths=tx, y_lengths=ty,
+        durations=attn.sum(-1).astype(np.int32), path_sha256=np.array(sha(attn.astype(np.uint8))),
+        log_prior_sha256=np.array(sha(lp)), log_prior_absmax=np.float32(np.abs(lp).max()),
+        # a thin sample of the prior for the 1e-5 bar without storing 42 MB: every 19th token row
+        log_prior_rows=lp[:, ::19, :].astype(np.float32),
+        score=score, dur_loss=np.float32(dur_loss.item()), prior_loss=np.float32(prior_loss.item()),
+        mu_y_sha256=np.array(sha(dec["mu_y"].numpy())), y_cut_sha256=np.array(sha(dec["y"].numpy())),
+        y_cut_mask_sum=dec["y_mask"].numpy().sum(-1).astype(np.int32).reshape(-1))
+
+
 def main():
     shim = make_shim()
     sys.path.insert(0, shim)
     import torch
     from model import monotonic_align  # the reference's own wrapper + compiled kernel
 
-    if "--only" in sys.argv and sys.argv[sys.argv.index("--only") + 1] == "loss":
-        loss_block(shim)
+    if "--only" in sys.argv:
+        which = sys.argv[sys.argv.index("--only") + 1]
+        {"loss": lambda: loss_block(shim), "gp": generate_path_golden, "cfg3": cfg3_golden}[which]()
         shutil.rmtree(shim, ignore_errors=True)
         return
 
@@ -303,6 +447,8 @@ def main():
     capture(a, x, x_lengths, y, y_lengths, "prior_arttts.npz", {"x_traits": x.numpy()})
 
     loss_block(shim)
+    generate_path_golden()
+    cfg3_golden()
     shutil.rmtree(shim, ignore_errors=True)
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):

@@ -34,7 +34,7 @@ def test_no_torch_or_python_symbols_in_library(maslib):
 
 
 def test_version_strerror_plan_workspace(maslib):
-    assert maslib.mas_abi_version() == 1
+    assert maslib.mas_abi_version() == 2
     assert maslib.mas_strerror(0) == b"ok"
     assert b"NULL" in maslib.mas_strerror(-1)
     assert maslib.mas_plan(16, 190, 870, 0) == 0        # LJSpeech shape: bits in shared memory
@@ -88,26 +88,47 @@ def test_argument_validation_without_gpu(maslib):
     assert bw(one, null, null, null, null, one, null, null, one, 1, 80, 1 << 20, 8, 8, null) == -2
 
 
-def test_peer_durations_setting_without_gpu(maslib):
-    """mas_set_peer_durations (fused all-gather over peer memory): argument validation and the shape
-    query, neither of which touches a device."""
-    import ctypes
+def test_peer_gather_description_validated_without_gpu(maslib):
+    """mas_peer_gather (fused all-gather over peer memory) travels with the call: its validation and
+    the shape query answer before any launch, so neither touches a device."""
+    from art_tts_b200 import _lib
     lib = maslib
+    null, one = ctypes.c_void_p(None), ctypes.c_void_p(16)
     two = (ctypes.c_uint64 * 2)(0x7f0000000000, 0x7f0000100000)
-    assert lib.mas_set_peer_durations(2, two, 0, 1024, 190) == 0
-    assert lib.mas_set_peer_durations(0, None, 0, 0, 0) == 0       # off
-    assert lib.mas_set_peer_durations(2, None, 0, 1024, 190) < 0   # pointers missing
-    assert lib.mas_set_peer_durations(17, two, 0, 1024, 190) < 0   # more ranks than one NVLink domain
-    assert lib.mas_set_peer_durations(2, two, -1, 1024, 190) < 0
-    assert lib.mas_set_peer_durations(2, two, 0, 0, 190) < 0       # no room for a single utterance
     odd = (ctypes.c_uint64 * 1)(0x7f0000000002)
-    assert lib.mas_set_peer_durations(1, odd, 0, 8, 190) < 0       # int32 rows need 4-byte alignment
-    assert lib.mas_set_peer_durations(0, None, 0, 0, 0) == 0
+
+    def call(d, B=8, T_x=190, T_y=872):
+        return lib.mas_from_prior_peer_f32(one, null, one, one, one, one, 0, one, null, null, null, B, 80,
+                                           T_x, T_y, one, 1 << 20, 0, null, ctypes.byref(d))
+
+    def desc(n=2, ptrs=two, row0=0, rows=1024, stride=190, fptrs=None, fstride=0):
+        d = _lib.PeerGatherDesc()
+        d.n_peers = n
+        d.durations_ptrs = ctypes.cast(ptrs, ctypes.POINTER(ctypes.c_uint64)) if ptrs is not None else None
+        d.row0, d.rows, d.row_stride = row0, rows, stride
+        d.frame_idx_ptrs = ctypes.cast(fptrs, ctypes.POINTER(ctypes.c_uint64)) if fptrs is not None else None
+        d.frame_idx_stride = fstride
+        return d
+
+    assert call(desc(ptrs=None)) == -2                 # pointers missing
+    assert call(desc(n=17)) == -2                      # more ranks than one NVLink domain
+    assert call(desc(row0=-1)) == -7
+    assert call(desc(rows=0)) == -7                    # no room for a single utterance
+    assert call(desc(rows=7)) == -7                    # B = 8 does not fit
+    assert call(desc(stride=189)) == -7                # rows shorter than T_x
+    assert call(desc(n=1, ptrs=odd)) == -5             # int32 rows need 4-byte alignment
+    assert call(desc(fptrs=two, fstride=871)) == -7    # frame-index rows shorter than T_y
+    assert call(desc(), B=0) == 0                      # valid description, empty batch: nothing to do
     assert b"peer" in lib.mas_strerror(-7)
     assert lib.mas_peer_durations_supported(1024, 80, 190, 872, 0) == 1    # tensor-core engine
     assert lib.mas_peer_durations_supported(1024, 16, 160, 512, 0) == 0    # CUDA-core engine (F < 32)
     assert lib.mas_peer_durations_supported(32, 80, 512, 4096, 0) == 0     # beyond 256 tokens
     assert lib.mas_peer_durations_supported(1024, 80, 190, 872, 16) == 0   # MAS_FLAG_NO_TENSOR
+    # sequence-mask lengths entry
+    lm = lib.mas_lengths_from_seq_masks
+    assert lm(null, 0, 4, 1, one, 0, 8, 1, 1, 4, 8, one, one, null) == -1
+    assert lm(one, 9, 4, 1, one, 0, 8, 1, 1, 4, 8, one, one, null) == -3
+    assert lm(one, 0, 4, 1, one, 0, 8, 1, 0, 4, 8, one, one, null) == 0
 
 
 def test_python_surface_refuses_cpu_tensors(maslib):

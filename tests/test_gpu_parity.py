@@ -10,7 +10,7 @@ import pytest
 import torch
 
 import oracle
-from conftest import GOLDEN, path_from_durations, rect_mask, seeded_case
+from conftest import GOLDEN, cfg3_inputs, path_from_durations, rect_mask, seeded_case
 
 pytestmark = pytest.mark.gpu
 
@@ -37,11 +37,13 @@ def test_small_goldens_bit_exact(cuda, golden_small):
     g = golden_small
     for name in g["names"]:
         value, mask, want = g[f"{name}.value"], g[f"{name}.mask"], g[f"{name}.path"]
-        strict = name == "holes"
-        got = run_mas(value, mask, cuda, strict_mask=strict)
+        got = run_mas(value, mask, cuda)             # default: per-cell mask, like the reference
         assert got.dtype == torch.from_numpy(want).dtype, name
         assert got.shape == want.shape
         assert np.array_equal(got.cpu().numpy(), want), name
+        if name != "holes":                          # rectangular masks: the 8 B/cell path is exact too
+            fast = run_mas(value, mask, cuda, strict_mask=False)
+            assert fast.dtype == got.dtype and torch.equal(fast, got), name
 
 
 @pytest.mark.parametrize("flags", [0, 1], ids=["fast", "general"])
@@ -252,6 +254,60 @@ def test_generate_path_matches_reference_formula(cuda):
     assert np.array_equal(got.cpu().numpy(), oracle.generate_path(dur.astype(np.int32), mask))
 
 
+def test_generate_path_matches_reference_goldens(cuda):
+    """generate_path_kernel against the reference's own model.utils.generate_path (utils.py:26-43)
+    on its inference call site's inputs (tts.py:130-147): fp32 durations with length_scale
+    1.0 / 1.3 / 0.77 and the integer durations MAS produces (tests/golden/generate_path.npz)."""
+    from art_tts_b200 import utils
+    g = np.load(os.path.join(GOLDEN, "generate_path.npz"))
+    for name in g["names"]:
+        dur, T_y = g[f"{name}.duration"], int(g[f"{name}.T_y"])
+        mask = rect_mask(g[f"{name}.x_lengths"], g[f"{name}.y_lengths"], dur.shape[1], T_y)
+        want = np.unpackbits(g[f"{name}.path_packed"], axis=-1)[:, :, :T_y].astype(np.float32)
+        got = utils.generate_path(torch.from_numpy(dur).to(cuda), torch.from_numpy(mask).to(cuda))
+        assert got.dtype == torch.float32, name
+        assert np.array_equal(got.cpu().numpy(), want), name
+
+
+def test_config3_size_reference_capture(cuda):
+    """BASELINE config 3 at its stated size: mu_x captured from the reference's GradTTS(params_v2)
+    encoder, B=64, T_x<=190, T_y<=872 (tests/golden/cfg3_gradtts.npz).  Fused kernel (both engines)
+    against the reference's log-prior rows, alignment and losses; drop-in on the kernel's own prior
+    bit-exact against the oracle."""
+    from art_tts_b200 import alignment, monotonic_align
+    g = np.load(os.path.join(GOLDEN, "cfg3_gradtts.npz"))
+    _, x_len, y, y_len = cfg3_inputs()
+    assert hashlib.sha256(y.tobytes()).hexdigest() == str(g["y_sha256"])
+    mu_x = g["mu_x"]
+    B, F, T_x = mu_x.shape
+    T_y = y.shape[2]
+    mask = rect_mask(x_len, y_len, T_x, T_y)
+    want_path = path_from_durations(g["durations"], y_len, T_y)
+    assert hashlib.sha256(want_path.tobytes()).hexdigest() == str(g["path_sha256"])
+    rows = g["log_prior_rows"]
+    m = mask[:, ::19, :].astype(bool)
+    for engine in ("tensor_core", "cuda_core"):
+        path, dur, score, lp = fused(mu_x, y, x_len, y_len, cuda, return_score=True,
+                                     return_log_prior=True, flags=ENGINES[engine])
+        lp_np = lp.cpu().numpy()
+        rel = np.abs(lp_np[:, ::19, :] - rows)[m] / np.abs(rows[m])
+        assert rel.max() <= 1e-5, (engine, rel.max())                       # prior within 1e-5 relative
+        agree = (path.to(torch.uint8).cpu().numpy() == want_path).mean()
+        assert agree >= 0.999, (engine, agree)                              # >= 99.9 % of cells
+        assert np.allclose(score.cpu().numpy(), g["score"], rtol=1e-4), engine   # log-likelihood 1e-4 rel
+        tok = (dur.cpu().numpy() == g["durations"]).mean()
+        assert tok >= 0.99, (engine, tok)
+        # drop-in on the kernel's own prior: bit-exact against the oracle on the same tensor
+        got = monotonic_align.maximum_path(lp, torch.from_numpy(mask).to(cuda))
+        assert np.array_equal(got.cpu().numpy(), oracle.maximum_path(lp_np, mask, n_threads=8)), engine
+        assert torch.equal(got, path), engine
+    # duration loss on the reference's durations (tts.py:503-506)
+    d = torch.from_numpy(g["durations"]).to(cuda)
+    logw = torch.from_numpy(g["logw"]).to(cuda)
+    loss = alignment.duration_loss_from_durations(logw, d, torch.from_numpy(x_len.astype(np.int32)))
+    assert np.isclose(float(loss), float(g["dur_loss"]), rtol=1e-5)
+
+
 # ------------------------------------------------------------------ fused prior + MAS
 def fused(mu_x, y, x_len, y_len, cuda, **kw):
     from art_tts_b200 import monotonic_align
@@ -296,17 +352,11 @@ def test_fused_matches_reference_model_capture(cuda, fname):
         assert (fi[b, y_len[b]:] == -1).all()
 
 
-# MAS_FLAG_NO_TENSOR / MAS_FLAG_FORCE_TENSOR; "tensor_core_tmem_dp" = the experimental engine of
-# csrc/mas_prior_tc2.cu (DP warps read the accumulators straight from tensor memory), opt-in by
-# environment (MAS_PRIOR_TC2=1, read on every call)
-ENGINES = {"auto": 0, "cuda_core": 16, "tensor_core": 32, "tensor_core_tmem_dp": 32}
+# MAS_FLAG_NO_TENSOR / MAS_FLAG_FORCE_TENSOR
+ENGINES = {"auto": 0, "cuda_core": 16, "tensor_core": 32}
 
 
 def select_engine(monkeypatch, engine):
-    if engine == "tensor_core_tmem_dp":
-        monkeypatch.setenv("MAS_PRIOR_TC2", "1")
-    else:
-        monkeypatch.delenv("MAS_PRIOR_TC2", raising=False)
     return ENGINES[engine]
 
 
@@ -341,7 +391,7 @@ def test_fused_vs_oracle_configs(cuda, F, B, T_x, T_y, seed, engine, monkeypatch
     assert torch.equal(p2, path) and torch.equal(d2, dur)
 
 
-@pytest.mark.parametrize("engine", ["tensor_core", "tensor_core_tmem_dp"])
+@pytest.mark.parametrize("engine", ["tensor_core"])
 @pytest.mark.parametrize("T_x", [1, 31, 32, 33, 63, 64, 65, 127, 128, 129, 191, 192, 255, 256, 257])
 def test_tensor_core_engine_token_axis_edges(cuda, T_x, engine, monkeypatch):
     """Token counts around every ownership boundary of the tensor-core kernel: 32 lanes x 2 DP
@@ -476,7 +526,7 @@ def test_entry_points_are_cuda_graph_capturable_and_stream_ordered(cuda):
         assert torch.equal(a, b)
 
 
-@pytest.mark.parametrize("engine", ["cuda_core", "tensor_core", "tensor_core_tmem_dp"])
+@pytest.mark.parametrize("engine", ["cuda_core", "tensor_core"])
 def test_fused_degenerate_and_empty_utterances(cuda, engine, monkeypatch):
     """Empty utterances (t_x == 0 or t_y == 0: all-zero path, like the reference's all-zero mask),
     t_x == t_y (pure diagonal), t_x == 1, and the reference's degenerate t_x > t_y case (backtrack
@@ -507,10 +557,12 @@ def test_fused_degenerate_and_empty_utterances(cuda, engine, monkeypatch):
     assert np.allclose(lp_np[m], ref_lp[m], rtol=1e-5, atol=1e-4)
 
 
-def test_peer_durations_single_rank_and_refusal(cuda):
-    """mas_set_peer_durations with this GPU's own buffer as the only peer (the multi-GPU form is
-    tests/multi_gpu_peer_gather.py under torchrun): the tensor-core engine writes the rows at row0 + b, the
-    CUDA-core engine refuses the call instead of leaving the buffer unwritten."""
+def test_peer_gather_single_rank_and_refusal(cuda):
+    """mas_peer_gather with this GPU's own buffers as the only peer (the multi-GPU form is
+    tests/test_gpu_multi.py): the tensor-core engine writes durations and frame index at row0 + b
+    through the row strides, the CUDA-core engine refuses the call instead of leaving the buffers
+    unwritten, a call that does not fit the buffers is refused, and without a description nothing
+    is written (no process-wide state)."""
     import ctypes
     from art_tts_b200 import _lib
     rng = np.random.default_rng(5)
@@ -519,24 +571,36 @@ def test_peer_durations_single_rank_and_refusal(cuda):
     y_len = np.minimum(T_y, 4 * x_len + rng.integers(0, 20, B)).astype(np.int32)
     mu_x = rng.standard_normal((B, F, T_x)).astype(np.float32)
     y = rng.standard_normal((B, F, T_y)).astype(np.float32)
-    row0 = 3
-    buf = torch.full((row0 + B + 2, T_x), -7, dtype=torch.int32, device=cuda)
-    lib = _lib.load()
+    row0, stride, fstride = 3, T_x + 9, T_y + 4        # buffers padded to a larger T_x / T_y
+    buf = torch.full((row0 + B + 2, stride), -7, dtype=torch.int32, device=cuda)
+    fbuf = torch.full((row0 + B + 2, fstride), -7, dtype=torch.int32, device=cuda)
     ptrs = (ctypes.c_uint64 * 1)(buf.data_ptr())
-    _lib.check(lib.mas_set_peer_durations(1, ptrs, row0, B, T_x), "mas_set_peer_durations")
-    try:
-        path, dur = fused(mu_x, y, x_len, y_len, cuda)
-        torch.cuda.synchronize()
-        assert torch.equal(buf[row0:row0 + B], dur)
-        assert (buf[:row0] == -7).all() and (buf[row0 + B:] == -7).all()
-        with pytest.raises(ValueError):
-            fused(mu_x, y, x_len, y_len, cuda, flags=ENGINES["cuda_core"])
-        _lib.check(lib.mas_set_peer_durations(1, ptrs, row0, B - 1, T_x), "mas_set_peer_durations")
-        with pytest.raises(ValueError):       # one utterance more than the peers' buffers hold
-            fused(mu_x, y, x_len, y_len, cuda)
-    finally:
-        _lib.check(lib.mas_set_peer_durations(0, None, 0, 0, 0), "mas_set_peer_durations")
+    fptrs = (ctypes.c_uint64 * 1)(fbuf.data_ptr())
+
+    def desc(rows=B, with_fi=True, row_stride=stride):
+        d = _lib.PeerGatherDesc()
+        d.n_peers = 1
+        d.durations_ptrs = ctypes.cast(ptrs, ctypes.POINTER(ctypes.c_uint64))
+        d.row0, d.rows, d.row_stride = row0, rows, row_stride
+        d.frame_idx_ptrs = ctypes.cast(fptrs, ctypes.POINTER(ctypes.c_uint64)) if with_fi else None
+        d.frame_idx_stride = fstride if with_fi else 0
+        return d
+
+    path, dur, fi = fused(mu_x, y, x_len, y_len, cuda, return_frame_idx=True, peer=desc())
+    assert torch.equal(buf[row0:row0 + B, :T_x], dur)
+    assert torch.equal(fbuf[row0:row0 + B, :T_y], fi)
+    assert (buf[:row0] == -7).all() and (buf[row0 + B:] == -7).all() and (buf[:, T_x:] == -7).all()
+    assert (fbuf[:row0] == -7).all() and (fbuf[row0 + B:] == -7).all() and (fbuf[:, T_y:] == -7).all()
+    with pytest.raises(ValueError):           # the CUDA-core engine does not write peer memory
+        fused(mu_x, y, x_len, y_len, cuda, flags=ENGINES["cuda_core"], peer=desc())
+    with pytest.raises(ValueError):           # one utterance more than the peers' buffers hold
+        fused(mu_x, y, x_len, y_len, cuda, peer=desc(rows=B - 1))
+    with pytest.raises(ValueError):           # rows shorter than the call's T_x
+        fused(mu_x, y, x_len, y_len, cuda, peer=desc(row_stride=T_x - 1))
     buf.fill_(-7)
-    fused(mu_x, y, x_len, y_len, cuda)
-    torch.cuda.synchronize()
+    fbuf.fill_(-7)
+    fused(mu_x, y, x_len, y_len, cuda, peer=desc(with_fi=False))
+    assert torch.equal(buf[row0:row0 + B, :T_x], dur) and (fbuf == -7).all()
+    buf.fill_(-7)
+    fused(mu_x, y, x_len, y_len, cuda)        # no description: plain call, nothing written
     assert (buf == -7).all()

@@ -8,7 +8,7 @@ import pytest
 
 import oracle
 from oracle import ref as oref
-from conftest import GOLDEN, path_from_durations, rect_mask, seeded_case
+from conftest import GOLDEN, cfg3_inputs, path_from_durations, rect_mask, seeded_case
 
 
 def test_oracle_matches_reference_small_goldens(golden_small):
@@ -88,6 +88,48 @@ def test_generate_path_is_inverse_of_mas():
     mask = rect_mask(t_x, t_y, 40, 130)
     path = oracle.maximum_path(value, mask)
     assert np.array_equal(oracle.generate_path(path.sum(-1), mask), path)
+
+
+def test_generate_path_restatement_matches_reference_goldens():
+    """oracle.generate_path against the outputs of the reference's own model.utils.generate_path
+    (utils.py:26-43) on its inference call site's inputs (tts.py:130-147): fp32 durations with
+    length_scale 1.0 / 1.3 / 0.77, and the int64 / int32 durations MAS produces."""
+    g = np.load(os.path.join(GOLDEN, "generate_path.npz"))
+    for name in g["names"]:
+        dur, T_y = g[f"{name}.duration"], int(g[f"{name}.T_y"])
+        mask = rect_mask(g[f"{name}.x_lengths"], g[f"{name}.y_lengths"], dur.shape[1], T_y)
+        want = np.unpackbits(g[f"{name}.path_packed"], axis=-1)[:, :, :T_y]
+        got = oracle.generate_path(dur, mask)
+        assert got.dtype == np.float32, name              # mask.dtype, like the reference
+        assert str(g[f"{name}.path_dtype"]) == "torch.float32"
+        assert np.array_equal(got, want.astype(np.float32)), name
+
+
+def test_config3_size_capture_against_oracle():
+    """BASELINE config 3 at its stated size (B=64, T_x<=190, T_y<=872, params_v2): the oracle's
+    prior and MAS against what the reference's GradTTS.compute_loss produced."""
+    g = np.load(os.path.join(GOLDEN, "cfg3_gradtts.npz"))
+    x, x_len, y, y_len = cfg3_inputs()
+    assert hashlib.sha256(x.tobytes()).hexdigest() == str(g["x_sha256"])
+    assert hashlib.sha256(y.tobytes()).hexdigest() == str(g["y_sha256"])
+    assert np.array_equal(x_len.astype(np.int32), g["x_lengths"])
+    mu_x = g["mu_x"]
+    lp = oracle.log_prior(mu_x, y)
+    rows = g["log_prior_rows"]
+    sub = lp[:, ::19, :]
+    m = rect_mask(x_len, y_len, 190, 872)[:, ::19, :].astype(bool)
+    rel = np.abs(sub - rows)[m] / np.abs(rows[m])
+    assert rel.max() <= 1e-5, rel.max()
+    mask = rect_mask(x_len, y_len, 190, 872)
+    path, score = oracle.maximum_path(lp, mask, return_scores=True, n_threads=4)
+    want = path_from_durations(g["durations"], y_len, 872)
+    assert hashlib.sha256(want.tobytes()).hexdigest() == str(g["path_sha256"])   # durations <-> path
+    assert (path.astype(np.uint8) == want).mean() >= 0.999
+    assert np.allclose(score, g["score"], rtol=1e-4)
+    # duration loss from the reference's durations (tts.py:503-506)
+    x_mask = (np.arange(190)[None, None, :] < x_len[:, None, None]).astype(np.float32)
+    logw_ = oracle.duration_targets(want.astype(np.float32), x_mask)
+    assert np.isclose(oracle.duration_loss(g["logw"], logw_, x_len), g["dur_loss"], rtol=1e-5)
 
 
 @pytest.mark.parametrize("fname,F", [("prior_gradtts.npz", 80), ("prior_arttts.npz", 16)])
