@@ -2,11 +2,20 @@
 """bench.py -- MAS alignment cells/s on B200 (BASELINE.json metric), one JSON line on rank 0.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--op fused|dropin]
+                  [--scaling strong|weak]
 
-A "step" is one pass of the hot path over one synthetic batch of BASELINE config 5:
-B=1024 LJSpeech-shape utterances per GPU (T_text<=190, T_mel<=870 padded to 872, n_feats=80, ragged,
-length-bucketed), i.e.  (mu_x, y, lengths) -> log-prior -> MAS -> (path, durations), followed
-at N>1 by the NCCL all-gather of the int32 durations.  cells = B*T_text*T_mel (padded).
+A "step" is one pass of the hot path over one synthetic batch of BASELINE config 5: a GLOBAL batch
+of B=1024 LJSpeech-shape utterances (T_text<=190, T_mel<=870 padded to 872, n_feats=80, ragged,
+length-bucketed), i.e.  (mu_x, y, lengths) -> log-prior -> MAS -> (path, durations), followed at N>1
+by the all-gather of the int32 durations.  cells = 1024*T_text*T_mel (padded).
+
+  --scaling strong (default, what BASELINE config 5 / SURVEY 8e state): the global batch is dealt
+      longest-first over the ranks (distributed.length_bucket_order) and every rank runs its
+      contiguous shard of 1024/N utterances.  One launch of 128 utterances is one utterance
+      latency on 148 SMs, so at N>1 the steps run back to back on several streams (CUDA graphs of
+      kernel + barrier chains), the peer-memory gather of step i under the kernel of step i+1.
+      The B=1024-per-GPU (weak) figure is reported beside it under "weak".
+  --scaling weak: B=1024 per GPU (round-1 behaviour), global batch 1024*N.
 
   value  : whole-job cells/s, inputs resident in HBM, CUDA-event timed, max over ranks
   e2e    : same op through the public API with pinned HOST buffers; H2D of (mu_x, y, lengths)
@@ -14,6 +23,7 @@ at N>1 by the NCCL all-gather of the int32 durations.  cells = B*T_text*T_mel (p
   roofline / cpu_baseline / clocks / gpu_launches : see the task contract and DESIGN.md
   drop_in: the bit-exact maximum_path(value, mask) kernel on the same batch shape
            (value [B,T_x,T_y] fp32 resident; 8 B/cell HBM roofline)
+  configs: BASELINE configs 1-4 (parity-test shapes) timed per call with an L2 flush in between
 
 --impl reference times the reference's own host implementation (tts.py:483-505 restated with
 torch CPU ops + the reference's compiled Cython kernel from oracle/_ref, OpenMP build, all host
@@ -24,6 +34,7 @@ from __future__ import annotations
 
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -41,7 +52,8 @@ METRIC = "mas_alignment_cells_per_s"
 UNIT = "cells/s"
 # T_mel: 870 frames padded to 872 by fix_len_compatibility (src/model/utils.py:13-17), which is
 # what the reference's collate hands to compute_loss (data_textmel.py:132-153); lengths stay <= 870
-B_PER_GPU, T_X, T_Y, T_Y_MAXLEN, N_FEATS = 1024, 190, 872, 870, 80
+GLOBAL_B, T_X, T_Y, T_Y_MAXLEN, N_FEATS = 1024, 190, 872, 870, 80
+L2_BYTES = 126 << 20
 
 
 def parse():
@@ -51,23 +63,25 @@ def parse():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--op", default="fused", choices=["fused", "dropin"])
-    ap.add_argument("--batch", type=int, default=B_PER_GPU)
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
+    ap.add_argument("--batch", type=int, default=GLOBAL_B,
+                    help="global batch (strong) / batch per GPU (weak)")
     ap.add_argument("--cpu-sample", type=int, default=64, help="utterances in the CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-dropin", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the config 1-4 timings")
+    ap.add_argument("--no-weak", action="store_true", help="strong scaling, N>1: skip the weak figure")
     ap.add_argument("--e2e-chunk", type=int, default=0, help="utterances per H2D chunk (0 = library default)")
     ap.add_argument("--e2e-no-trim", action="store_true", help="copy whole padded rows")
-    # default "serial": measured on 2 GPUs, the overlapped gather is 3 % faster when it works (0.347 vs
-    # 0.357 ms) but the fused kernel is persistent with one CTA per SM, and whenever the collective's CTAs
-    # still hold an SM at the next launch the CTAs that do not fit run as a second wave (0.78-1.6 ms observed)
-    ap.add_argument("--gather", default="auto", choices=["auto", "overlap", "serial", "p2p"],
-                    help="N>1: all-gather of step i in line after its kernel, on a side stream under the kernel of step "
-                         "i+1, or done by the fused kernel itself over NVLink peer memory (+ a barrier); auto = p2p when "
-                         "every rank can set it up (fused op, tensor-core engine, symmetric memory), else serial")
-    ap.add_argument("--reserve-sms", type=int, default=-1,
-                    help="SMs the persistent kernel leaves to the overlapped collective (default 0: measured "
-                         "at N=8, reserving 8 SMs costs 8%% and the gather overlaps anyway)")
+    ap.add_argument("--gather", default="auto", choices=["auto", "serial", "p2p"],
+                    help="N>1: all-gather of the durations by NCCL in line after the kernel, or done by the fused "
+                         "kernel itself over NVLink peer memory (+ a barrier); auto = p2p when every rank can set "
+                         "it up (fused op, tensor-core engine, symmetric memory), else serial")
+    ap.add_argument("--streams", type=int, default=3, help="strong scaling, N>1: steps in flight per GPU")
+    ap.add_argument("--chain", type=int, default=4, help="steps per captured CUDA graph (even)")
+    ap.add_argument("--no-graphs", action="store_true", help="strong scaling, N>1: eager launches on the streams")
+    ap.add_argument("--no-numa", action="store_true", help="do not bind the rank to its GPU's NUMA node")
     ap.add_argument("--engine", default="auto", choices=["auto", "tensor", "cuda"],
                     help="prior engine of the fused kernel (auto: 3xTF32 tensor cores for F >= 32)")
     return ap.parse_args()
@@ -84,18 +98,21 @@ def make_lengths(B, seed):
     return t_x[order], t_y[order]
 
 
-def config_dict(args, world):
+def config_dict(args, world, b_local=None, pipeline=None):
+    strong = args.scaling == "strong"
+    gb = args.batch if strong else args.batch * world
+    wl = (f"config5: global B={gb} LJSpeech-shape length-bucketed, batch-sharded over {world} GPU(s)"
+          if strong else f"config5 (weak): B={args.batch}/GPU LJSpeech-shape length-bucketed")
+    wl += ", fused prior+MAS+durations" if args.op == "fused" else ", maximum_path(value, mask)"
     return {
-        "workload": "config5: B=1024/GPU LJSpeech-shape length-bucketed, fused prior+MAS+durations"
-                    if args.op == "fused" else
-                    "config5: B=1024/GPU LJSpeech-shape length-bucketed, maximum_path(value, mask)",
-        "op": args.op, "engine": args.engine, "batch_per_gpu": args.batch, "global_batch": args.batch * world,
+        "workload": wl, "op": args.op, "engine": args.engine, "global_batch": gb,
+        "batch_per_gpu": b_local if b_local is not None else (gb // world if strong else args.batch),
         "T_text": T_X, "T_mel": T_Y, "n_feats": N_FEATS, "ragged": True,
         "cells_definition": "B*T_text*T_mel (padded)",
-        "l2_policy": "inputs+outputs per step (>= 1 GB) exceed the 126 MB L2; no explicit flush",
-        "collective": ("all_gather(durations int32 [B,T_text]), " +
-                       ("auto: fused over NVLink peer memory, else NCCL in line" if args.gather == "auto" else args.gather)
-                       if world > 1 else "none"),
+        "l2_policy": "inputs+outputs touched between two uses of the same input set exceed the 126 MB L2 "
+                     "(N=1: 1 GB per step; N>1: input sets rotate); no explicit flush",
+        "collective": ("all_gather(durations int32 [B,T_text]), " + args.gather) if world > 1 else "none",
+        "pipeline": pipeline,
     }
 
 
@@ -162,8 +179,8 @@ def cpu_mas_baseline(t_x, t_y, n_sample, budget_s=12.0):
     value = -(rng.random((n, T_X, T_Y), dtype=np.float32) * 100 + 50)
     tx, ty = np.ascontiguousarray(t_x[:n]), np.ascontiguousarray(t_y[:n])
     kind = "reference" if ref.available("omp") else "port"
-    cores = os.cpu_count() or 1
-    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    os.environ["OMP_NUM_THREADS"] = str(cores)
     best, t_end, reps = None, time.perf_counter() + budget_s, 0
     while reps < 3 or (time.perf_counter() < t_end and reps < 20):
         v = value.copy()
@@ -178,8 +195,10 @@ def cpu_mas_baseline(t_x, t_y, n_sample, budget_s=12.0):
         reps += 1
     cells = n * T_X * T_Y
     return {"value": cells / best, "unit": UNIT, "cores": cores, "kind": kind,
-            "sample": f"maximum_path_c only, B={n} of the workload's utterances, "
-                      f"{T_X}x{T_Y} padded, best of {reps}"}
+            "sample": f"maximum_path_c ONLY (no prior block, no wrapper), B={n} of the workload's utterances, "
+                      f"{T_X}x{T_Y} padded, best of {reps}",
+            "note": "north_star's '>=100x host Cython' is quoted against THIS kernel-only figure; "
+                    "--impl reference times the whole host path (prior block + wrapper + kernel)"}
 
 
 def run_reference(args):
@@ -190,10 +209,11 @@ def run_reference(args):
     from oracle import prior_torch, ref
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
-    n = min(args.cpu_sample, args.batch)
-    t_x, t_y = make_lengths(args.batch, 1000)
-    t_x, t_y = t_x[:: max(1, args.batch // n)][:n], t_y[:: max(1, args.batch // n)][:n]
+    os.environ["OMP_NUM_THREADS"] = str(cores)
+    gb = args.batch
+    n = min(args.cpu_sample, gb)
+    t_x, t_y = make_lengths(gb, 1000)
+    t_x, t_y = t_x[:: max(1, gb // n)][:n], t_y[:: max(1, gb // n)][:n]
     g = torch.Generator().manual_seed(0)
     x_mask = (torch.arange(T_X)[None, :] < torch.from_numpy(t_x)[:, None]).float().unsqueeze(1)
     y_mask = (torch.arange(T_Y)[None, :] < torch.from_numpy(t_y)[:, None]).float().unsqueeze(1)
@@ -224,13 +244,14 @@ def run_reference(args):
     cells = n * T_X * T_Y
     val = cells * done / dt
     kind = "reference" if kind_used in ("omp", "serial") else "port"
-    sample = (f"B={n} utterances of the workload per step (strided sample of the length-bucketed "
-              f"batch), torch-CPU log-prior block + maximum_path wrapper + Cython/OpenMP kernel"
+    sample = (f"B={n} utterances of the workload per step (strided sample of the length-bucketed global "
+              f"batch; cells/s normalised by the sample's own cells), torch-CPU log-prior block + "
+              f"maximum_path wrapper + Cython/OpenMP kernel"
               if args.op == "fused" else
               f"B={n} utterances per step, maximum_path wrapper + Cython/OpenMP kernel")
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
             "steps": done, "warmup": args.warmup, "ms_per_step": 1e3 * dt / done,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": config_dict(args, max(1, args.gpus)),
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -241,10 +262,47 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------
+class Shard:
+    """One rank's share of a batch: lengths + `nsets` input sets (rotated so that an input set is
+    not re-read out of L2), resident in HBM."""
+
+    def __init__(self, t_x_np, t_y_np, dev, seed, nsets, want_value):
+        self.B = len(t_x_np)
+        self.t_x_np, self.t_y_np = np.ascontiguousarray(t_x_np), np.ascontiguousarray(t_y_np)
+        self.t_x = torch.from_numpy(self.t_x_np).to(dev)
+        self.t_y = torch.from_numpy(self.t_y_np).to(dev)
+        self.cells = self.B * T_X * T_Y
+        self.valid_cells = int((self.t_x_np.astype(np.int64) * self.t_y_np).sum())
+        xm = (torch.arange(T_X, device=dev)[None, :] < self.t_x[:, None]).float()
+        ym = (torch.arange(T_Y, device=dev)[None, :] < self.t_y[:, None]).float()
+        g = torch.Generator(device=dev).manual_seed(seed)
+        self.sets = []
+        for _ in range(nsets):
+            mu_x = torch.randn(self.B, N_FEATS, T_X, device=dev, generator=g) * xm[:, None, :]
+            y = torch.randn(self.B, N_FEATS, T_Y, device=dev, generator=g) * ym[:, None, :]
+            self.sets.append((mu_x, y))
+        self.value = -(torch.rand(self.B, T_X, T_Y, device=dev, generator=g) * 100 + 50) if want_value else None
+
+    # SURVEY 8(d) / VERDICT r1: 4 B per padded cell of dense path out + 4*T_x durations + the VALID
+    # inputs 4*F*(t_x + t_y) per utterance (padding is never read)
+    def fused_alg_bytes(self):
+        return (4 * self.cells + 4 * self.B * T_X +
+                4 * N_FEATS * int(self.t_x_np.astype(np.int64).sum() + self.t_y_np.astype(np.int64).sum()))
+
+    def dropin_alg_bytes(self):
+        return 8 * self.cells   # read value fp32 once + write dense fp32 path once
+
+
+def nsets_for(b_local):
+    per_step = b_local * (4 * N_FEATS * (T_X + T_Y) + 4 * T_X * T_Y)
+    return 1 if per_step >= 3 * L2_BYTES else int(math.ceil(3 * L2_BYTES / per_step)) + 1
+
+
 def run_ours(args):
     import torch.distributed as dist
-    from art_tts_b200 import _lib, monotonic_align
+    from art_tts_b200 import _lib, monotonic_align, numa
     from art_tts_b200 import build as mas_build
+    from art_tts_b200.distributed import PeerDurationGather, length_bucket_order, shard_bounds
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -253,89 +311,35 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    all_cpus = os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") else None
+    bound = None if args.no_numa else numa.bind_to_device_node(local)   # before any host buffer is pinned
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     if not os.path.exists(mas_build.LIB):
         raise SystemExit("libmas_sm100.so missing: run __graft_entry__.build() first")
     _lib.load()
-
-    B = args.batch
-    cells = B * T_X * T_Y
-    t_x_np, t_y_np = make_lengths(B, 1000 + rank)
-    t_x = torch.from_numpy(t_x_np).to(dev)
-    t_y = torch.from_numpy(t_y_np).to(dev)
-    valid_cells = int((t_x_np.astype(np.int64) * t_y_np).sum())
-    torch.manual_seed(rank)
-    xm = (torch.arange(T_X, device=dev)[None, :] < t_x[:, None]).float()
-    ym = (torch.arange(T_Y, device=dev)[None, :] < t_y[:, None]).float()
-    mu_x = torch.randn(B, N_FEATS, T_X, device=dev) * xm[:, None, :]
-    y = torch.randn(B, N_FEATS, T_Y, device=dev) * ym[:, None, :]
-    dur_all = torch.empty(world * B, T_X, dtype=torch.int32, device=dev) if world > 1 else None
-    gatherer = None
-    reserve = 0
-    if world > 1 and args.gather == "overlap":
-        from art_tts_b200.distributed import DurationGatherer
-        gatherer = DurationGatherer(B, T_X, dev)   # gather of step i overlaps the kernel of step i+1
-        # the fused kernel is persistent (one CTA per SM): leave a few SMs to the collective's CTAs
-        reserve = 0 if args.reserve_sms < 0 else args.reserve_sms
-        _lib.check(_lib.load().mas_set_sm_reserve(reserve), "mas_set_sm_reserve")
-
-    peer = None
-    if world > 1 and args.gather in ("p2p", "auto"):
-        from art_tts_b200.distributed import PeerDurationGather
-        can = args.op == "fused" and args.engine != "cuda" and PeerDurationGather.supported(B, N_FEATS, T_X, T_Y)
-        if args.gather == "p2p" and not can:
-            raise SystemExit("--gather p2p: only the tensor-core engine of the fused op writes peer memory")
-        # every rank must take the same branch: agree before the (collective) rendezvous and after it
-        flag = torch.tensor([1 if can else 0], device=dev)
-        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-        if int(flag.item()):
-            try:
-                peer = PeerDurationGather(B, T_X, dev)
-            except Exception as e:   # no symmetric memory on this box: NCCL gather in line
-                if args.gather == "p2p":
-                    raise
-                print(f"[bench] rank {rank}: peer-memory gather unavailable ({type(e).__name__}: {e}); using NCCL",
-                      file=sys.stderr)
-            flag = torch.tensor([1 if peer is not None else 0], device=dev)
-            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-            if not int(flag.item()) and peer is not None:
-                peer.close()
-                peer = None
-        args.gather = "p2p" if peer is not None else ("serial" if args.gather == "auto" else args.gather)
-
-    value = None
-    if args.op == "dropin" or not args.no_dropin:
-        value = -(torch.rand(B, T_X, T_Y, device=dev) * 100 + 50)
-
+    strong = args.scaling == "strong"
+    fused = args.op == "fused"
     eng_flags = {"auto": 0, "tensor": _lib.FLAG_FORCE_TENSOR, "cuda": _lib.FLAG_NO_TENSOR}[args.engine]
     tensor_engine = args.engine == "tensor" or (args.engine == "auto" and N_FEATS >= 32)
+    want_value = (not fused) or not args.no_dropin
 
-    def step_fused():
-        path, dur = monotonic_align.maximum_path_from_prior(mu_x, None, y, t_x, t_y, flags=eng_flags)
-        if peer is not None:
-            peer.finish()            # the kernel wrote every rank's buffer; the ranks only meet here
-        elif gatherer is not None:
-            gatherer.gather(dur)
-        elif world > 1:
-            dist.all_gather_into_tensor(dur_all, dur)
-        return path, dur
+    # ---- the batch: strong = ONE global batch dealt over the ranks, weak = one batch per rank
+    def strong_shard(gb):
+        t_x_g, t_y_g = make_lengths(gb, 1000)
+        order = length_bucket_order(torch.from_numpy(t_x_g), torch.from_numpy(t_y_g), world).numpy()
+        lo, hi = shard_bounds(gb, rank, world)
+        return t_x_g[order[lo:hi]], t_y_g[order[lo:hi]]
 
-    def step_dropin():
-        path, dur = monotonic_align.maximum_path_lengths(value, t_x, t_y, return_durations=True)
-        if gatherer is not None:
-            gatherer.gather(dur)
-        elif world > 1:
-            dist.all_gather_into_tensor(dur_all, dur)
-        return path, dur
-
-    step = step_fused if args.op == "fused" else step_dropin
-    if world > 1:   # bring up every NCCL channel/connection before anything is timed
-        for _ in range(8):
-            dist.all_gather_into_tensor(dur_all, dur_all[:B])
-        torch.cuda.synchronize()
-        dist.barrier()
+    if strong:
+        tx_np, ty_np = strong_shard(args.batch)
+        global_cells = args.batch * T_X * T_Y
+    else:
+        tx_np, ty_np = make_lengths(args.batch, 1000 + rank)
+        global_cells = args.batch * world * T_X * T_Y
+    shard = Shard(tx_np, ty_np, dev, 7 + rank, nsets_for(len(tx_np)), want_value)
+    B = shard.B
 
     def barrier():
         torch.cuda.synchronize()
@@ -343,42 +347,200 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, warmup):
-        for _ in range(warmup):
-            fn()
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    # ---- gather mode: every rank must take the same branch
+    def make_peers(b_local, n, slots=2):
+        """n PeerDurationGather instances (one per stream), or None when any rank cannot."""
+        can = fused and args.engine != "cuda" and PeerDurationGather.supported(b_local, N_FEATS, T_X, T_Y)
+        flag = torch.tensor([1 if can else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if not int(flag.item()):
+            return None
+        peers = []
+        try:
+            for j in range(n):
+                peers.append(PeerDurationGather(b_local, T_X, dev, slots=slots, channel=j))
+        except Exception as e:   # no symmetric memory on this box: NCCL gather in line
+            print(f"[bench] rank {rank}: peer-memory gather unavailable ({type(e).__name__}: {e}); using NCCL",
+                  file=sys.stderr)
+            peers = None
+        flag = torch.tensor([1 if peers is not None else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        return peers if int(flag.item()) else None
+
+    peers = None
+    nstreams = max(1, args.streams) if (strong and world > 1) else 1
+    if world > 1:
+        for _ in range(8):   # bring up every NCCL channel/connection before anything is timed
+            w = torch.empty(world * 8, dtype=torch.int32, device=dev)
+            dist.all_gather_into_tensor(w, w[:8])
+        if args.gather in ("auto", "p2p"):
+            peers = make_peers(B, nstreams)
+            if peers is None and args.gather == "p2p":
+                raise SystemExit("--gather p2p: needs the tensor-core engine of the fused op and symmetric memory")
+        args.gather = "p2p" if peers is not None else "serial"
+        if peers is None:
+            nstreams = 1     # one communicator: keep the NCCL gathers on one stream
+    dur_all = torch.empty(world * B, T_X, dtype=torch.int32, device=dev) if world > 1 else None
+
+    # ---- one step (on the CURRENT stream), input set k, gather through peers[j]
+    def step(k=0, j=0):
+        mu_x, y = shard.sets[k % len(shard.sets)]
+        if fused:
+            pj = peers[j] if peers is not None else None
+            path, dur = monotonic_align.maximum_path_from_prior(
+                mu_x, None, y, shard.t_x, shard.t_y, flags=eng_flags,
+                peer=pj.desc() if pj is not None else None)
+            if pj is not None:
+                return path, dur, pj.finish()     # the kernel wrote every rank's buffer; the ranks only meet here
+        else:
+            path, dur = monotonic_align.maximum_path_lengths(shard.value, shard.t_x, shard.t_y,
+                                                             return_durations=True)
+        if world > 1:
+            dist.all_gather_into_tensor(dur_all, dur)
+        return path, dur, dur_all
+
+    # ---- N>1: the gathered buffer must equal the NCCL all-gather of the local durations
+    gather_verified = None
+    if world > 1:
+        ok = True
+        for it in range(2 * nstreams):
+            _, dur, got = step(it, it % nstreams)
+            want = torch.empty(world * B, T_X, dtype=torch.int32, device=dev)
+            dist.all_gather_into_tensor(want, dur)
+            ok = ok and bool(torch.equal(got, want))
+        flag = torch.tensor([1 if ok else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        gather_verified = bool(int(flag.item()))
+        if not gather_verified:
+            raise SystemExit("gathered durations differ from the NCCL all-gather of the local durations")
+
+    # ---- timing helpers
+    def timed_serial(fn, steps, warmup):
+        """K calls back to back on the current stream."""
+        for i in range(warmup):
+            fn(i)
         barrier()
         l0 = _lib.launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(steps):
-            fn()
-        if gatherer is not None:
-            gatherer.wait()          # the last gathers are inside the timed region
+        for i in range(steps):
+            fn(i)
         e1.record()
         barrier()
-        ms = e0.elapsed_time(e1)
-        launches = _lib.launch_count() - l0
-        if world > 1:
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms / steps, launches
+        return max_over_ranks(e0.elapsed_time(e1)) / steps, _lib.launch_count() - l0
 
+    pipeline = {"mode": "single stream, eager launches", "streams": 1}
+
+    def timed_pipelined(steps, warmup):
+        """Strong scaling, N>1: `nstreams` steps in flight.  Stream j runs chains of kernel -> barrier
+        (captured once as a CUDA graph of `chain` steps), so the peer-memory gather + barrier of one
+        step run under the kernels of the steps on the other streams."""
+        main = torch.cuda.current_stream()
+        streams = [torch.cuda.Stream(device=dev) for _ in range(nstreams)]
+        chain = max(2, args.chain // 2 * 2)      # even: the two gather slots keep alternating across replays
+        graphs, keep = [], []
+        if not args.no_graphs:
+            try:
+                for j, s in enumerate(streams):
+                    with torch.cuda.stream(s):
+                        for i in range(2):
+                            step(i, j)             # warm-up outside capture (function attributes, workspaces)
+                    torch.cuda.synchronize()
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, stream=s):
+                        for i in range(chain):
+                            keep.append(step(j * chain + i, j))
+                    graphs.append(g)
+            except Exception as e:
+                print(f"[bench] rank {rank}: CUDA-graph capture of the step chain failed ({type(e).__name__}: {e}); "
+                      f"eager launches", file=sys.stderr)
+                graphs = []
+                torch.cuda.synchronize()
+        flag = torch.tensor([1 if len(graphs) == nstreams else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        use_graphs = bool(int(flag.item()))
+        pipeline.update({"mode": ("CUDA graphs of %d-step kernel+barrier chains" % chain) if use_graphs
+                         else "eager launches", "streams": nstreams, "chain": chain if use_graphs else 1})
+        per_round = nstreams * (chain if use_graphs else 1)
+        launches_per_step = [None]
+
+        def run(n):
+            rounds, rem = divmod(n, per_round)
+            for _ in range(rounds):
+                for j, s in enumerate(streams):
+                    with torch.cuda.stream(s):
+                        if use_graphs:
+                            graphs[j].replay()
+                        else:
+                            step(j, j)
+            for i in range(rem):                   # the remainder of K: eager, round-robin
+                with torch.cuda.stream(streams[i % nstreams]):
+                    step(i, i % nstreams)
+
+        def fork():
+            ev = torch.cuda.Event()
+            ev.record(main)
+            for s in streams:
+                s.wait_event(ev)
+
+        def join():
+            for s in streams:
+                main.wait_stream(s)
+
+        fork()
+        l0 = _lib.launch_count()
+        run(-(-max(per_round, warmup) // per_round) * per_round)    # whole rounds: gather slots keep alternating
+        join()
+        barrier()
+        if use_graphs:   # launches replayed from a graph are not counted by the library: count two eager steps
+            with torch.cuda.stream(streams[0]):
+                l1 = _lib.launch_count()
+                step(0, 0)
+                step(1, 0)
+                launches_per_step[0] = (_lib.launch_count() - l1) / 2
+            barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(main)
+        fork()
+        l0 = _lib.launch_count()
+        run(steps)
+        join()
+        e1.record(main)
+        barrier()
+        launches = (launches_per_step[0] * steps) if use_graphs else (_lib.launch_count() - l0)
+        return max_over_ranks(e0.elapsed_time(e1)) / steps, launches
+
+    # ---- headline
     clocks = Clocks(local)
     if rank == 0:
         clocks.start()
-    ms_step, launches = timed(step, args.steps, max(3, args.warmup))
+    if strong and world > 1 and nstreams > 1:
+        ms_step, launches = timed_pipelined(args.steps, max(3, args.warmup))
+    else:
+        ms_step, launches = timed_serial(lambda i: step(i, 0), args.steps, max(3, args.warmup))
     clk = clocks.stop() if rank == 0 else None
-    value_cells = cells * world / (ms_step * 1e-3)
+    value_cells = global_cells / (ms_step * 1e-3)
+    valid = torch.tensor([shard.valid_cells], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(valid)
+    valid_global = float(valid.item())
 
-    # ---- per-kernel time for the roofline: CUDA events around the kernel launch alone
-    def kernel_only():
-        if args.op == "fused":
-            monotonic_align.maximum_path_from_prior(mu_x, None, y, t_x, t_y, flags=eng_flags)
+    # ---- per-kernel time for the roofline: CUDA events around the kernel launches alone (no gather)
+    def kernel_only(i):
+        mu_x, y = shard.sets[i % len(shard.sets)]
+        if fused:
+            monotonic_align.maximum_path_from_prior(mu_x, None, y, shard.t_x, shard.t_y, flags=eng_flags)
         else:
-            monotonic_align.maximum_path_lengths(value, t_x, t_y, return_durations=True)
+            monotonic_align.maximum_path_lengths(shard.value, shard.t_x, shard.t_y, return_durations=True)
 
-    k_ms, _ = timed(kernel_only, args.steps, 2)
+    k_ms, _ = timed_serial(kernel_only, args.steps, 3)
     peaks = {}
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -387,81 +549,86 @@ def run_ours(args):
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
-    if args.op == "fused":
-        # 4*F*(T_x+T_y) in + 4*T_x durations + 4 B/cell dense path out, per utterance
-        alg_bytes = B * (4 * N_FEATS * (T_X + T_Y) + 4 * T_X + 4 * T_X * T_Y)
-    else:
-        alg_bytes = 8 * cells   # read value fp32 once + write dense fp32 path once
-    ach = alg_bytes / (k_ms * 1e-3) / 1e9
-    kname = ("mas_prior_tc_kernel" if tensor_engine else "mas_prior_kernel") if args.op == "fused" \
-        else "mas_fast_kernel"
-    # measured DRAM bytes per launch of this kernel on this workload (ncu --set full,
-    # dram__bytes_read.sum + dram__bytes_write.sum; profiles/r1_traffic.json names the capture)
-    traffic = None
-    try:
-        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
-            tj = json.load(f)
-        if B == B_PER_GPU:
-            traffic = tj.get(kname, {}).get("dram_bytes_per_launch")
-    except Exception:
-        pass
-    roofline = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
-                "frac": ach / hbm_peak, "traffic": traffic, "peak_source": peak_src,
-                "kernel": kname, "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg_bytes,
-                "frac_of_nominal_8tbs": ach / 8000.0}   # also quoted against the nominal ~8 TB/s
-    if args.op == "fused" and tensor_engine:
+    traffic_tab = {}
+    for name in ("r2_traffic.json", "r1_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                traffic_tab = json.load(f)
+            traffic_tab["_file"] = "profiles/" + name
+            break
+        except Exception:
+            continue
+
+    def roofline_of(kname, alg_bytes, ms, b_local):
+        ach = alg_bytes / (ms * 1e-3) / 1e9
+        ent = traffic_tab.get(kname, {}) if b_local == GLOBAL_B else {}
+        traffic = ent.get("dram_bytes_per_launch")
+        r = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+             "traffic": traffic,
+             "traffic_source": (f"ncu --set full capture of this kernel on this workload, recorded in "
+                                f"{traffic_tab.get('_file')} (constant, not re-measured in this run)"
+                                if traffic is not None else None),
+             "dram_frac": (traffic / (ms * 1e-3) / 1e9 / hbm_peak) if traffic is not None else None,
+             "peak_source": peak_src, "kernel": kname, "kernel_ms": ms,
+             "algorithmic_bytes_per_launch": alg_bytes, "utterances_per_launch": b_local,
+             "algorithmic_bytes_definition": ("4*B*T_x*T_y dense path + 4*B*T_x durations + 4*F*sum(t_x+t_y) "
+                                              "valid inputs" if kname != "mas_fast_kernel" else
+                                              "8 B per padded cell (value read + path written)"),
+             "frac_of_nominal_8tbs": ach / 8000.0}
+        return r
+
+    kname = (("mas_prior_tc_kernel" if tensor_engine else "mas_prior_kernel") if fused else "mas_fast_kernel")
+    roofline = roofline_of(kname, shard.fused_alg_bytes() if fused else shard.dropin_alg_bytes(), k_ms, B)
+    if fused and tensor_engine:
         roofline["engine"] = ("tcgen05.mma kind::tf32, 3xTF32 split (fp32-level accuracy), mu_x in TMEM; "
                               "the CUDA-core engine (--engine cuda) is the fp32 FMA variant")
-    if args.op == "fused" and not tensor_engine:
+    if fused and not tensor_engine:
         # the binding resource at F=80 is the fp32 FMA pipe, not HBM: report it too
         sm_mhz = (clk or {}).get("sm_mhz") or 1965.0
         fma_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
-        flops = 2.0 * N_FEATS * valid_cells
+        flops = 2.0 * N_FEATS * shard.valid_cells
         roofline["fp32_alu"] = {"achieved_tflops": flops / (k_ms * 1e-3) / 1e12,
                                 "peak_tflops_at_observed_clock": fma_peak,
                                 "frac": flops / (k_ms * 1e-3) / 1e12 / fma_peak,
                                 "flops_counted": "2*F per VALID cell (t_x*t_y)"}
 
-    # ---- drop-in kernel on the same shape (secondary figure, resident value tensor)
+    # ---- drop-in kernel on the same shard (secondary figure, resident value tensor)
     drop = None
-    if args.op == "fused" and not args.no_dropin:
-        d_ms, _ = timed(lambda: monotonic_align.maximum_path_lengths(value, t_x, t_y,
-                                                                     return_durations=True),
-                        args.steps, 3)
-        d_ach = 8 * cells / (d_ms * 1e-3) / 1e9
-        drop = {"value": cells / (d_ms * 1e-3), "unit": UNIT, "ms_per_step": d_ms,
-                "roofline": {"bound": "hbm", "achieved": d_ach, "peak": hbm_peak, "unit": "GB/s",
-                             "frac": d_ach / hbm_peak,
-                             "traffic": (tj.get("mas_fast_kernel", {}).get("dram_bytes_per_launch")
-                                         if traffic is not None else None),
-                             "kernel": "mas_fast_kernel", "algorithmic_bytes_per_launch": 8 * cells}}
+    if fused and not args.no_dropin:
+        d_ms, _ = timed_serial(lambda i: monotonic_align.maximum_path_lengths(
+            shard.value, shard.t_x, shard.t_y, return_durations=True), args.steps, 3)
+        drop = {"value": shard.cells * world / (d_ms * 1e-3) if strong else shard.cells / (d_ms * 1e-3),
+                "unit": UNIT, "ms_per_step": d_ms, "utterances_per_launch": B,
+                "roofline": roofline_of("mas_fast_kernel", shard.dropin_alg_bytes(), d_ms, B)}
 
     # ---- e2e: pinned host buffers in, durations + score out, every step
     e2e = None
     if not args.no_e2e:
-        if args.op == "fused":
-            h_in = [mu_x.cpu().pin_memory(), y.cpu().pin_memory(), t_x.cpu().pin_memory(),
-                    t_y.cpu().pin_memory()]
+        mu_x, y = shard.sets[0]
+        if fused:
+            h_in = [mu_x.cpu().pin_memory(), y.cpu().pin_memory(), shard.t_x.cpu().pin_memory(),
+                    shard.t_y.cpu().pin_memory()]
         else:
-            h_in = [value.cpu().pin_memory(), t_x.cpu().pin_memory(), t_y.cpu().pin_memory()]
-        d_in = [torch.empty_like(h, device=dev) for h in h_in] if args.op != "fused" else []
+            h_in = [shard.value.cpu().pin_memory(), shard.t_x.cpu().pin_memory(), shard.t_y.cpu().pin_memory()]
+        d_in = [torch.empty_like(h, device=dev) for h in h_in] if not fused else []
         h_dur = torch.empty(B, T_X, dtype=torch.int32).pin_memory()
         h_score = torch.empty(B, dtype=torch.float32).pin_memory()
         h2d = sum(h.numel() * h.element_size() for h in h_in)
         d2h = h_dur.numel() * 4 + h_score.numel() * 4
-
         moved = [h2d]
+        pe = peers[0] if peers is not None else None
 
-        def e2e_step():
-            if args.op == "fused":
+        def e2e_step(i):
+            if fused:
                 # host-buffer entry point: trimmed, chunked H2D overlapped with the kernels,
                 # D2H of durations + score enqueued behind the last chunk
                 path, dur, score, moved[0] = monotonic_align.maximum_path_from_prior_host(
                     h_in[0], h_in[1], h_in[2], h_in[3], dev, chunk=args.e2e_chunk,
                     durations_host=h_dur, score_host=h_score,
-                    flags=(_lib.FLAG_HOST_NO_TRIM if args.e2e_no_trim else 0) | eng_flags)
-                if peer is not None:
-                    peer.finish()
+                    flags=(_lib.FLAG_HOST_NO_TRIM if args.e2e_no_trim else 0) | eng_flags,
+                    peer=pe.desc() if pe is not None else None)
+                if pe is not None:
+                    pe.finish()
                 elif world > 1:
                     dist.all_gather_into_tensor(dur_all, dur)
             else:
@@ -475,12 +642,51 @@ def run_ours(args):
                 h_score.copy_(score, non_blocking=True)
             torch.cuda.current_stream().synchronize()   # the caller reads the result every step
 
-        e_ms, _ = timed(e2e_step, max(3, args.steps // 2), 2)
-        e2e = {"value": cells * world / (e_ms * 1e-3), "unit": UNIT, "ms_per_step": e_ms,
-               "h2d_bytes_per_step": int(moved[0]), "d2h_bytes_per_step": d2h,
-               "padded_input_bytes": h2d,
-               "api": "art_tts_b200.monotonic_align.maximum_path_from_prior_host" if args.op == "fused"
+        e_ms, _ = timed_serial(e2e_step, max(3, args.steps // 2), 2)
+        tot = torch.tensor([float(moved[0]), float(d2h)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tot)
+        e2e = {"value": global_cells / (e_ms * 1e-3), "unit": UNIT, "ms_per_step": e_ms,
+               "h2d_bytes_per_step": int(tot[0].item()), "d2h_bytes_per_step": int(tot[1].item()),
+               "bytes_counted": "summed over all ranks (one global batch per step)" if strong else
+                                "summed over all ranks (one batch per rank per step)",
+               "numa_binding": bound,
+               "api": "art_tts_b200.monotonic_align.maximum_path_from_prior_host" if fused
                       else "art_tts_b200.monotonic_align.maximum_path_lengths"}
+
+    # ---- strong scaling, N>1: the weak figure (B = global batch PER GPU) beside it
+    weak = None
+    if strong and world > 1 and not args.no_weak:
+        torch.cuda.empty_cache()
+        wt_x, wt_y = make_lengths(args.batch, 1000 + rank)
+        wshard = Shard(wt_x, wt_y, dev, 7 + rank, 1, False)
+        wpeers = make_peers(wshard.B, 1) if args.gather == "p2p" else None
+        wdur = torch.empty(world * wshard.B, T_X, dtype=torch.int32, device=dev)
+
+        def wstep(i):
+            mu_x, y = wshard.sets[0]
+            if fused:
+                pj = wpeers[0] if wpeers is not None else None
+                _, dur = monotonic_align.maximum_path_from_prior(mu_x, None, y, wshard.t_x, wshard.t_y,
+                                                                 flags=eng_flags,
+                                                                 peer=pj.desc() if pj is not None else None)
+                if pj is not None:
+                    pj.finish()
+                    return
+            else:
+                return
+            dist.all_gather_into_tensor(wdur, dur)
+
+        if fused:
+            w_ms, _ = timed_serial(wstep, max(10, args.steps // 2), 5)
+            weak = {"scaling": "weak", "batch_per_gpu": wshard.B, "global_batch": wshard.B * world,
+                    "value": wshard.cells * world / (w_ms * 1e-3), "unit": UNIT, "ms_per_step": w_ms,
+                    "collective": "p2p" if wpeers is not None else "serial"}
+
+    # ---- BASELINE configs 1-4 (parity-test shapes): per-call time with an L2 flush in between
+    configs = None
+    if world == 1 and not args.no_configs:
+        configs = time_configs(dev, monotonic_align, _lib)
 
     if world > 1:
         dist.barrier()
@@ -491,18 +697,76 @@ def run_ours(args):
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_mas_baseline(t_x_np, t_y_np, args.cpu_sample)
+        if all_cpus is not None:
+            os.sched_setaffinity(0, all_cpus)     # the host baseline gets every core of the box
+        cpu = cpu_mas_baseline(tx_np, ty_np, args.cpu_sample)
 
     line = {"metric": METRIC, "value": value_cells, "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_step,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": config_dict(args, world),
-            "valid_cells_per_s": valid_cells * world / (ms_step * 1e-3),
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": config_dict(args, world, B, pipeline),
+            "valid_cells_per_s": valid_global / (ms_step * 1e-3),
             "roofline": roofline, "cpu_baseline": cpu, "clocks": clk, "e2e": e2e,
-            "gpu_launches": int(launches), "drop_in": drop}
+            "gpu_launches": int(launches), "gather_verified": gather_verified,
+            "drop_in": drop, "weak": weak, "configs": configs}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def time_configs(dev, monotonic_align, _lib, iters=20):
+    """BASELINE configs 1-4 through both entries: median per-call device time, the 126 MB L2 flushed
+    (a 256 MB write) before every timed call -- these shapes are far smaller than L2."""
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    out = {}
+    shapes = {
+        "cfg1": dict(B=16, T_x=190, T_y=870, F=80, kind="ljs", seed=0),
+        "cfg2": dict(B=32, T_x=160, T_y=512, F=16, kind="art", seed=1),
+        "cfg3": dict(B=64, T_x=190, T_y=872, F=80, kind="ljs", seed=37),
+        "cfg4": dict(B=32, T_x=512, T_y=4096, F=80, kind="full", seed=4),
+    }
+    for name, c in shapes.items():
+        rng = np.random.default_rng(c["seed"])
+        B, T_x, T_y, F = c["B"], c["T_x"], c["T_y"], c["F"]
+        if c["kind"] == "ljs":
+            t_x = rng.integers(60, T_x + 1, B).astype(np.int32)
+            t_y = np.minimum(min(T_y, 870), 4 * t_x + rng.integers(0, 100, B)).astype(np.int32)
+            t_x[0], t_y[0] = T_x, min(T_y, 870)
+        elif c["kind"] == "art":
+            t_x = rng.integers(20, T_x + 1, B).astype(np.int32)
+            t_y = np.minimum(T_y, 3 * t_x + rng.integers(0, 61, B)).astype(np.int32)
+        else:
+            t_x, t_y = np.full(B, T_x, np.int32), np.full(B, T_y, np.int32)
+        tx, ty = torch.from_numpy(t_x).to(dev), torch.from_numpy(t_y).to(dev)
+        g = torch.Generator(device=dev).manual_seed(c["seed"])
+        mu_x = torch.randn(B, F, T_x, device=dev, generator=g)
+        y = torch.randn(B, F, T_y, device=dev, generator=g)
+        value = -(torch.rand(B, T_x, T_y, device=dev, generator=g) * 100 + 50)
+
+        def med(fn):
+            ts = []
+            for i in range(iters + 3):
+                flush.fill_(i & 1)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                fn()
+                e1.record()
+                e1.synchronize()
+                if i >= 3:
+                    ts.append(e0.elapsed_time(e1))
+            return float(np.median(ts))
+
+        d_ms = med(lambda: monotonic_align.maximum_path_lengths(value, tx, ty, return_durations=True))
+        f_ms = med(lambda: monotonic_align.maximum_path_from_prior(mu_x, None, y, tx, ty))
+        cells = B * T_x * T_y
+        out[name] = {"B": B, "T_text": T_x, "T_mel": T_y, "n_feats": F,
+                     "dropin_ms": d_ms, "dropin_cells_per_s": cells / (d_ms * 1e-3),
+                     "dropin_gbs_8B_per_cell": 8 * cells / (d_ms * 1e-3) / 1e9,
+                     "fused_ms": f_ms, "fused_cells_per_s": cells / (f_ms * 1e-3),
+                     "fused_plan": int(_lib.load().mas_from_prior_plan(B, F, T_x, T_y, 0)),
+                     "timing": f"median of {iters} calls, CUDA events, L2 flushed before each"}
+        del mu_x, y, value
+    return out
 
 
 def main():
