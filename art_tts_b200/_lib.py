@@ -19,6 +19,8 @@ FLAG_SPILL_BITS = 4
 FLAG_HOST_NO_TRIM = 8
 FLAG_NO_TENSOR = 16
 FLAG_FORCE_TENSOR = 32
+FLAG_LOCKSTEP_DP = 64
+FLAG_SKEWED_DP = 128
 
 _DTYPES = {
     torch.float32: MAS_F32,

@@ -61,7 +61,7 @@ static int env_int(const char *name, int dflt)
 // the library, so that plan queries (mas_plan, mas_from_prior_plan, mas_peer_durations_supported)
 // and the launches that follow can never disagree.
 struct Tuning {
-    int prior_tc, prior_tc_min_f, stages, dp2_min_tx, prior_spill, prior_stats, fma_per_smsp, extra_fma;
+    int prior_tc, prior_tc_min_f, stages, dp2_min_tx, prior_spill, prior_stats, fma_per_smsp, extra_fma, fast3;
 };
 static const Tuning &tuning()
 {
@@ -75,6 +75,7 @@ static const Tuning &tuning()
         v.prior_stats = env_int("MAS_PRIOR_STATS", 0);
         v.fma_per_smsp = env_int("MAS_PRIOR_FMA_PER_SMSP", 2);
         if (v.fma_per_smsp < 1 || v.fma_per_smsp > 4) v.fma_per_smsp = 2;
+        v.fast3 = env_int("MAS_FAST3", 0);   // skewed-lane drop-in kernel: opt-in until its HBM staging beats the lock-step one
         v.extra_fma = env_int("MAS_PRIOR_EXTRA_FMA", 1);
         if (v.extra_fma < 0 || v.extra_fma > 1) v.extra_fma = 1;
         return v;
@@ -219,6 +220,14 @@ int mas_plan(int B, int T_x, int T_y, int flags)
 // dp_forward2); that needs a third ring stage and 64-row alignment of the tiles.
 static Plan plan_fast(int T_x, int T_y, int flags, MasArgs *a)
 {
+    a->skewed = 0;
+    if ((tuning().fast3 || (flags & MAS_FLAG_SKEWED_DP)) &&
+        !(flags & (MAS_FLAG_FORCE_GENERAL | MAS_FLAG_SPILL_BITS | MAS_FLAG_LOCKSTEP_DP)) &&
+        fast3_layout(T_x, T_y, &a->lay)) {
+        a->skewed = 1;          // skewed-lane recurrence (mas_fast3.cu), direction bits in shared memory
+        a->dp_warps = 1;
+        return kPlanFastSmemBits;
+    }
     Plan plan = choose_plan(T_x, T_y, flags, &a->lay);
     a->dp_warps = 1;
     if (plan != kPlanGeneral && T_x > tuning().dp2_min_tx) {
@@ -309,7 +318,8 @@ int mas_maximum_path(const void *value, int value_dtype, const float *cell_mask,
         a.load_mode = (T_y % 4 == 0 && (uintptr_t)value % 16 == 0) ? 2 : 1;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const cudaError_t e = (plan == kPlanGeneral) ? launch_general(a, value_dtype, st)
-                                                 : launch_fast(a, value_dtype, st);
+                          : a.skewed           ? launch_fast3(a, value_dtype, st)
+                                               : launch_fast(a, value_dtype, st);
     return (int)e;
 }
 
@@ -431,7 +441,9 @@ int from_prior_impl(const float *mu_x, const float *logs, const float *y, const 
         m.path_esize = path ? esize : 4;
         m.one = one_pattern(path_dtype);
         m.load_mode = (T_y % 4 == 0 && (uintptr_t)log_prior_out % 16 == 0) ? 2 : 1;
-        return (int)((p2 == kPlanGeneral) ? launch_general(m, MAS_F32, st) : launch_fast(m, MAS_F32, st));
+        return (int)((p2 == kPlanGeneral) ? launch_general(m, MAS_F32, st)
+                     : m.skewed           ? launch_fast3(m, MAS_F32, st)
+                                          : launch_fast(m, MAS_F32, st));
     }
     a.mu_x = mu_x;
     a.y = y;

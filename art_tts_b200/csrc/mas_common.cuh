@@ -179,6 +179,19 @@ __device__ __forceinline__ void zero_fill_part(char *base, int64_t nbytes, int p
     for (int64_t i = lo + tid; i < hi; i += nthr) st_zero16(b16 + (i << 4));
 }
 
+// ---------------------------------------------------------------- bulk (TMA) loads
+// cp.async.bulk global -> shared::cta: the copy engine moves `bytes` (a multiple of 16, both addresses
+// 16-byte aligned) and reports them to the mbarrier (complete_tx); no register staging, no LSU miss
+// queue entry per 16 bytes -- a CTA with 128 staging threads keeps tens of KB in flight this way,
+// which per-thread cp.async (LDGSTS) does not (measured: profiles/r2_fast3_phases.txt).
+__device__ __forceinline__ void bulk_load(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
 // ---------------------------------------------------------------- bulk (TMA) zero fill
 // cp.async.bulk shared::cta -> global: the copy engine streams a zeroed shared buffer to HBM,
 // so clearing the dense output costs one instruction per `zbytes` instead of one 16-byte

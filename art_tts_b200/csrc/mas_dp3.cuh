@@ -1,0 +1,283 @@
+// mas_dp3.cuh -- the MAS recurrence with SKEWED LANES: one warp, no shuffle on the critical path.
+//
+// Reference semantics (paths relative to /root/reference/): forward core.pyx:17-30, backtrack
+// core.pyx:15,32-35.  Same results as mas_dp.cuh, different schedule and a cheaper cell:
+//
+//   * lane r owns the XPL consecutive tokens x = r*XPL + j and, at warp iteration tau, works on frame
+//     f = tau - r: every lane runs ONE FRAME BEHIND its left neighbour.  The only cross-lane value of
+//     the recurrence, V[x-1, f-1] for the lane's first token, was therefore produced by lane r-1 two
+//     iterations earlier; its shuffle is issued a whole iteration before it is consumed.  In the
+//     lock-step formulation (mas_dp.cuh) the same shuffle sits on a diagonal dependency chain and an
+//     in-order warp stalls on it with nothing else to issue (ncu, profiles/r1: 73 cycles per frame for
+//     3 tokens per lane, 70 % of them stall cycles).
+//   * the values of iteration tau+2 are loaded (LDS.32, conflict-free by layout) while iteration tau
+//     is computed, so shared-memory latency is off the chain as well.
+//   * what is left is ISSUE-bound on the 16-lane ALU pipe (FSETP / FSEL / FMNMX / LOP3 / SHF occupy it
+//     two cycles per warp instruction; FADD runs on the FMA pipe).  The cell is therefore
+//         d = cur - up            FADD   (up > cur  <=>  cur - up < 0: exact without NaN; V is never -0)
+//         acc = (acc << 1) | d>>31  SHF  (funnel shift takes the sign bit straight out of d)
+//         V = fmax(up, cur) + v   FMNMX + FADD
+//     = 2 ALU + 2 FMA-pipe instructions, against FSETP + FSEL + SEL/LOP3 + FADD (+ guards) before.
+//     fmax(up, cur) is the reference's (up > cur) ? up : cur on every input without NaN.
+//   * no per-cell guards: the PRODUCER stores 0.0 for every cell above the diagonal (x > f), so those
+//     cells stay exactly -1e9 (max(-1e9, -1e9) + 0) as the reference's `x == y ? -1e9` needs; only
+//     block 0 (whose lanes also see frames < 0) selects, and the last blocks capture V at f == t_y-1
+//     (the score) instead of freezing the recurrence.
+//   * direction words are accumulated MSB first; at the end of a 32-iteration block the frame-aligned
+//     word of chunk g-1 is funnelshift_r(brev(previous), brev(current), lane).
+//
+// The schedule is stated in plain Python in tests/dp3_model.py and checked there against the oracle
+// (tests/test_dp3_model.py); this file is its transcription.
+//
+// Ring layout ("pre-skewed rows"): row x (natural token order) is a circular buffer of kRing3Cols
+// frames, row pitch kRing3Cols + 4 floats.  Frame f of the utterance whose first tile is tile g0 of
+// the ring's lifetime sits at float column
+//       col = (32*g0 + f + shift(r)) & (kRing3Cols - 1),   r = x / XPL,
+//       shift(r) = ((r + 3) & ~3) + 4 * (((r >> 2) - XPL * r) & 7)
+// i.e. the lane skew rounded up to a multiple of four frames plus a per-lane ROTATION of the ring (no
+// XOR swizzle): a run of consecutive frames of one row is a run of consecutive floats (mod the ring
+// length), 16-byte aligned, so a producer moves the 32 frames of a row with ONE bulk (TMA) copy -- or
+// aligned cp.async / STS.128 chunks.  The consumer lane reads column (32*g0 + tau + shift(r) - r) &
+// mask of its own rows, the same expression for every lane up to a per-lane constant, and for every
+// XPL in 1..8 the 32 lanes hit 32 distinct banks: bank = 4 j + tau + ((-r) & 3) + 4 (r >> 2) (mod 32)
+// with the +4 floats of row pitch (brute-forced as well, profiles/ring3_banks.py).
+#pragma once
+
+#include "mas_dp.cuh"
+
+namespace mas {
+
+constexpr int kRing3Cols = 128;                 // frames per row ring: 4 tiles of 32
+constexpr int kRing3Pitch = kRing3Cols + 4;     // floats per row
+constexpr int kRing3Stages = kRing3Cols / kTileY;
+
+// ring shift of the rows owned by lane r when every lane owns xpl tokens (a multiple of 4 floats)
+__device__ __forceinline__ int dp3_shift(int r, int xpl) { return ((r + 3) & ~3) + ((((r >> 2) - xpl * r) & 7) << 2); }
+
+// float column (within its row) of lifetime frame fl (= 32*g0 + f) for a row owned by lane r; a run of
+// frames is contiguous up to the wrap at kRing3Cols
+__device__ __forceinline__ int dp3_col(int r, int xpl, int fl) { return (fl + dp3_shift(r, xpl)) & (kRing3Cols - 1); }
+
+struct Ring3 {
+    float *rows;        // xrows x kRing3Pitch floats, 16-byte aligned
+    uint64_t *full;     // [4] producers -> DP warp, one per tile (stage = tile & 3)
+    uint64_t *empty;    // [4] DP warp -> producers
+};
+
+__device__ __forceinline__ float lds32(uint32_t addr)
+{
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+
+// values of one iteration for this lane's XPL tokens (rows x0 .. x0+XPL-1, same column)
+template <int XPL>
+__device__ __forceinline__ void dp3_load(float (&v)[XPL], uint32_t rowbase, uint32_t t4)
+{
+    const uint32_t a = rowbase + (t4 & (uint32_t)(kRing3Cols * 4 - 4));
+#pragma unroll
+    for (int j = 0; j < XPL; ++j) v[j] = lds32(a + (uint32_t)(j * kRing3Pitch * 4));
+}
+
+// 32 iterations (one block).  `f` = this lane's frame at the block's first iteration (tau - lane).
+// EDGE blocks: `head` (block 0) selects "x > f -> -1e9" (also covers f < 0, where the ring holds stale
+// data); every EDGE block captures V at f == ty - 1 into sv.  `wait_bar` (may be null): barrier of the
+// NEXT tile, waited before the last 8 iterations -- their prefetches are the first loads that touch it.
+template <int XPL, bool EDGE>
+__device__ __forceinline__ void dp3_iter8(float (&V)[XPL], uint32_t (&acc)[XPL], float (&buf)[2][XPL],
+                                          float (&sv)[XPL], float &left, uint32_t &t4, uint32_t rowbase,
+                                          int lane, int x0, int &f, int ty, bool head)
+{
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        // state at the end of the previous iteration: consumed one iteration from now
+        const float cap = __shfl_up_sync(kFull, V[XPL - 1], 1);
+        const float(&v)[XPL] = buf[u & 1];
+#pragma unroll
+        for (int j = XPL - 1; j >= 0; --j) {
+            const float up = (j == 0) ? left : V[j > 0 ? j - 1 : 0];   // V[x-1, f-1]
+            const float d = __fsub_rn(V[j], up);                       // < 0  <=>  up > cur (core.pyx:30)
+            acc[j] = __funnelshift_l(__float_as_uint(d), acc[j], 1);
+            float nv = __fadd_rn(fmaxf(up, V[j]), v[j]);
+            if (EDGE) {
+                nv = (head && x0 + j > f) ? kNeg : nv;                 // not reachable yet (or f < 0)
+                sv[j] = (f == ty - 1) ? nv : sv[j];
+            }
+            V[j] = nv;
+        }
+        left = (lane == 0) ? kNeg : cap;   // token 0: v_prev = -1e9 after frame 0 (core.pyx:23-27)
+        dp3_load<XPL>(buf[u & 1], rowbase, t4);   // iteration tau + 2
+        t4 += 4u;
+        if (EDGE) ++f;
+    }
+}
+
+template <int XPL, bool EDGE>
+__device__ __forceinline__ void dp3_block(float (&V)[XPL], uint32_t (&acc)[XPL], float (&buf)[2][XPL],
+                                          float (&sv)[XPL], float &left, uint32_t &t4, uint32_t rowbase,
+                                          int lane, int x0, int f, int ty, bool head, uint64_t *wait_bar,
+                                          uint32_t wait_parity, long long *wait_acc)
+{
+#pragma unroll 1
+    for (int k = 0; k < 3; ++k) dp3_iter8<XPL, EDGE>(V, acc, buf, sv, left, t4, rowbase, lane, x0, f, ty, head);
+    if (wait_bar) {
+        if (wait_acc) {   // profiling aid: cycles this warp spends starved of tiles
+            const long long t0 = clock64();
+            mbar_wait(wait_bar, wait_parity);
+            *wait_acc += clock64() - t0;
+        } else {
+            mbar_wait(wait_bar, wait_parity);
+        }
+    }
+    dp3_iter8<XPL, EDGE>(V, acc, buf, sv, left, t4, rowbase, lane, x0, f, ty, head);
+}
+
+// frame-aligned direction words of chunk c from the previous (already bit-reversed) and the current
+// (MSB-first) block accumulators
+template <int XPL>
+__device__ __forceinline__ void dp3_flush(uint32_t *bits, int xrows, int nch, int c, int lane, int x0,
+                                          uint32_t (&prev)[XPL], uint32_t (&acc)[XPL])
+{
+#pragma unroll
+    for (int j = 0; j < XPL; ++j) {
+        const uint32_t cur = __brev(acc[j]);
+        uint32_t w = __funnelshift_r(prev[j], cur, lane);
+        const int x = x0 + j;
+        if ((x >> 5) == c) w |= 1u << (x & 31);   // x == y always steps down (core.pyx:34 `index == y`)
+        if (x == 0) w = 0u;                        // token 0 never does
+        if (c >= 0 && c < nch) bits[(size_t)c * xrows + x] = w;
+        prev[j] = cur;
+        acc[j] = 0u;
+    }
+}
+
+// Forward pass of one utterance by ONE warp (1 <= t_x <= t_y, XPL == ceil(t_x / 32) <= 8).  Consumes
+// tiles g0 .. g0+ceil(t_y/32)-1 of the ring's lifetime -- whose producers store 0.0 above the diagonal --
+// writes bits[chunk * xrows + x] (natural token order) and returns V[t_x-1, t_y-1] in every lane.
+template <int XPL>
+__device__ __noinline__ float dp3_forward(const Ring3 ring, uint32_t *bits, int xrows, int tx, int ty,
+                                          int lane, int g0, long long *wait_acc = nullptr)
+{
+    float V[XPL], buf[2][XPL], sv[XPL];
+    uint32_t acc[XPL], prev[XPL];
+#pragma unroll
+    for (int j = 0; j < XPL; ++j) {
+        V[j] = kNeg;
+        sv[j] = 0.0f;
+        acc[j] = 0u;
+        prev[j] = 0u;
+    }
+    const int x0 = lane * XPL;
+    const int ntiles = (ty + kTileY - 1) / kTileY;   // == nch
+    const int nblk = (ty + 31 + kTileY - 1) / kTileY;
+    const uint32_t rowbase = smem_u32(ring.rows) + (uint32_t)(x0 * kRing3Pitch * 4);
+    uint32_t t4 = (uint32_t)((32 * g0 + dp3_shift(lane, XPL) - lane) * 4);   // byte column of iteration 0
+    float left = (lane == 0) ? 0.0f : kNeg;     // frame 0: v_prev(x=0) = 0, everything else -1e9
+    {
+        long long t0 = 0;
+        if (wait_acc) t0 = clock64();
+        mbar_wait(&ring.full[g0 & 3], (uint32_t)(g0 >> 2) & 1u);
+        if (wait_acc) *wait_acc += clock64() - t0;
+    }
+    dp3_load<XPL>(buf[0], rowbase, t4);
+    t4 += 4u;
+    dp3_load<XPL>(buf[1], rowbase, t4);
+    t4 += 4u;
+    for (int g = 0; g < nblk; ++g) {
+        const bool head = g == 0;
+        const bool tail = 32 * g + 31 >= ty - 1;
+        const int gt = g0 + g + 1;
+        uint64_t *wb = (g + 1 < ntiles) ? &ring.full[gt & 3] : nullptr;
+        const uint32_t wp = (uint32_t)(gt >> 2) & 1u;
+        if (head || tail)
+            dp3_block<XPL, true>(V, acc, buf, sv, left, t4, rowbase, lane, x0, 32 * g - lane, ty, head, wb, wp,
+                                 wait_acc);
+        else
+            dp3_block<XPL, false>(V, acc, buf, sv, left, t4, rowbase, lane, x0, 32 * g - lane, ty, false, wb, wp,
+                                  wait_acc);
+        dp3_flush<XPL>(bits, xrows, ntiles, g - 1, lane, x0, prev, acc);
+        if (g >= 1) {   // every lane is past frame 32g: tile g-1 is free
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ring.empty[(g0 + g - 1) & 3]);
+        }
+    }
+    dp3_flush<XPL>(bits, xrows, ntiles, nblk - 1, lane, x0, prev, acc);   // t_y = 1 (mod 32)
+    __syncwarp();
+    if (lane == 0)
+        for (int t = max(nblk - 1, 0); t < ntiles; ++t) mbar_arrive(&ring.empty[(g0 + t) & 3]);
+    const int ql = (tx - 1) / XPL, qj = (tx - 1) - ql * XPL;
+    float s = 0.0f;
+#pragma unroll
+    for (int j = 0; j < XPL; ++j)
+        if (j == qj) s = sv[j];
+    return __shfl_sync(kFull, s, ql);
+}
+
+template <int XPLMAX>
+__device__ __forceinline__ float dp3_forward_dispatch(const Ring3 &ring, uint32_t *bits, int xrows, int tx,
+                                                      int ty, int lane, int g0, long long *wacc = nullptr)
+{
+    const int xpl = (tx + 31) >> 5;
+#define MAS_CASE3(N)                                                                             \
+    case N:                                                                                      \
+        if constexpr (N <= XPLMAX) return dp3_forward<N>(ring, bits, xrows, tx, ty, lane, g0, wacc); \
+        break;
+    switch (xpl) {
+        MAS_CASE3(1) MAS_CASE3(2) MAS_CASE3(3) MAS_CASE3(4) MAS_CASE3(5) MAS_CASE3(6) MAS_CASE3(7) MAS_CASE3(8)
+    default: break;
+    }
+#undef MAS_CASE3
+    return 0.0f;
+}
+
+// Backtrack over direction words in NATURAL token order (bits[chunk * xrows + x], shared memory), one
+// lane (core.pyx:32-35).  Jumps from token boundary to token boundary: inside a 32-frame word the next
+// decrement is the highest set bit at or below the current frame.  Only the FIRST FRAME of every token
+// is recorded (first[x]; durations follow in parallel: dur[x] = first[x+1] - first[x]), addresses are
+// running pointers, and the word of the next token is prefetched, so one transition is the dependent
+// chain mask -> AND -> FLO -> add (~25 cycles; the round-1 walk cost 165 per token).
+// Requires 1 <= t_x <= t_y (every token gets >= 1 frame).
+__device__ __forceinline__ void backtrack_nat(const uint32_t *bits, int xrows, int tx, int ty, int *first)
+{
+    int idx = tx - 1;
+    int c = (ty - 1) >> 5, s = (ty - 1) & 31;
+    const uint32_t rowb = (uint32_t)xrows * 4u;
+    uint32_t pw = smem_u32(bits) + 4u * (uint32_t)(c * xrows + idx);   // &bits[c][idx]
+    auto ld = [](uint32_t a) {
+        uint32_t w;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(a));
+        return w;
+    };
+    uint32_t w = ld(pw);
+    uint32_t wn = idx > 0 ? ld(pw - 4u) : 0u;
+    while (idx > 0) {
+        const uint32_t m = w & (0xffffffffu >> (31 - s));
+        if (m == 0u) {            // stays on this token down to the chunk start
+            if (c == 0) break;    // (cannot happen for idx > 0 when t_x <= t_y: bit idx of chunk idx>>5 is set)
+            --c;
+            pw -= rowb;
+            s = 31;
+            w = ld(pw);
+            wn = ld(pw - 4u);
+            continue;
+        }
+        const int p = 31 - __clz(m);
+        first[idx] = (c << 5) + p;
+        --idx;
+        pw -= 4u;
+        w = wn;
+        if (p == 0) {             // crossed into the previous chunk
+            --c;                  // c >= 1 here: frame 0 belongs to token 0 and idx was > 0
+            pw -= rowb;
+            s = 31;
+            w = ld(pw);
+        } else {
+            s = p - 1;
+        }
+        wn = idx > 0 ? ld(pw - 4u) : 0u;
+    }
+    first[0] = 0;
+}
+
+}  // namespace mas

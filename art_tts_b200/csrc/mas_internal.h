@@ -38,6 +38,8 @@ struct MasArgs {
     int B, T_x, T_y;
     int path_esize;
     int dp_warps;          // 1, or 2 for long utterances (mas_fast2_kernel: two DP warps split the tokens)
+    int skewed;            // 1: mas_fast3_kernel (skewed-lane recurrence, ring of mas_dp3.cuh)
+    long long *stats;      // optional [B][16] phase cycle counters (profiles/microbench/fast3_phases.cu), else NULL
     int load_mode;         // fast kernel staging: 0 = LDG/STS (any dtype, cell mask), 1 = cp.async 4 B,
                            // 2 = cp.async 16 B (fp32, rows 16-byte aligned)
     unsigned long long one;
@@ -57,6 +59,9 @@ cudaError_t launch_seq_lengths(const void *xm, int xdt, int64_t xsb, int64_t xst
                                cudaStream_t st);
 cudaError_t launch_fast(const MasArgs &a, int value_dtype, cudaStream_t st);
 cudaError_t launch_general(const MasArgs &a, int value_dtype, cudaStream_t st);
+// mas_fast3.cu: drop-in kernel on the skewed-lane recurrence (T_x <= 256)
+bool fast3_layout(int T_x, int T_y, FastLayout *lay);
+cudaError_t launch_fast3(const MasArgs &a, int value_dtype, cudaStream_t st);
 cudaError_t launch_generate_path(const void *dur, int dur_dtype, const int32_t *t_x,
                                  const int32_t *t_y, void *path, int esize, unsigned long long one,
                                  int B, int T_x, int T_y, cudaStream_t st);

@@ -104,7 +104,7 @@ def maximum_path_lengths(value: torch.Tensor, t_x: torch.Tensor, t_y: torch.Tens
     return out[0] if len(out) == 1 else tuple(out)
 
 
-def maximum_path(value: torch.Tensor, mask: torch.Tensor, *, strict_mask: bool = True):
+def maximum_path(value: torch.Tensor, mask: torch.Tensor, *, strict_mask: bool = True, flags: int = 0):
     """Drop-in for the reference's `maximum_path(value, mask)` (__init__.py:8-23).
 
     value: [b, t_x, t_y] float tensor on a CUDA device;  mask: [b, t_x, t_y] 0/1.
@@ -134,7 +134,7 @@ def maximum_path(value: torch.Tensor, mask: torch.Tensor, *, strict_mask: bool =
             value = value * mask
     if value.dtype not in _FLOAT_VALUE:
         value = value.to(out_dtype)
-    return maximum_path_lengths(value, t_x, t_y, out_dtype=out_dtype, cell_mask=cell_mask)
+    return maximum_path_lengths(value, t_x, t_y, out_dtype=out_dtype, cell_mask=cell_mask, flags=flags)
 
 
 def lengths_from_seq_masks(x_mask: torch.Tensor, y_mask: torch.Tensor,

@@ -62,7 +62,10 @@ enum {
     MAS_FLAG_HOST_NO_TRIM = 8,  /* mas_from_prior_host_f32: copy whole padded rows            */
     MAS_FLAG_NO_TENSOR = 16,    /* mas_from_prior_f32: fp32 FMA prior on CUDA cores instead of  */
                                 /* the 3xTF32 tensor-core prior                                 */
-    MAS_FLAG_FORCE_TENSOR = 32  /* tensor-core prior whenever the shape allows it (default: F >= 32) */
+    MAS_FLAG_FORCE_TENSOR = 32, /* tensor-core prior whenever the shape allows it (default: F >= 32) */
+    MAS_FLAG_LOCKSTEP_DP = 64,  /* mas_maximum_path: the lock-step recurrence kernels (the default)      */
+    MAS_FLAG_SKEWED_DP = 128    /* mas_maximum_path: the skewed-lane recurrence kernel (mas_fast3.cu,    */
+                                /* T_x <= 256; same results, A/B measurements and tests)                 */
 };
 
 int mas_abi_version(void);

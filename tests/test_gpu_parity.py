@@ -44,9 +44,11 @@ def test_small_goldens_bit_exact(cuda, golden_small):
         if name != "holes":                          # rectangular masks: the 8 B/cell path is exact too
             fast = run_mas(value, mask, cuda, strict_mask=False)
             assert fast.dtype == got.dtype and torch.equal(fast, got), name
+        skew = run_mas(value, mask, cuda, flags=128)  # skewed-lane kernel (every dtype / staging mode)
+        assert skew.dtype == got.dtype and torch.equal(skew, got), name
 
 
-@pytest.mark.parametrize("flags", [0, 1], ids=["fast", "general"])
+@pytest.mark.parametrize("flags", [0, 128, 1], ids=["lockstep", "skewed", "general"])
 def test_seeded_goldens_bit_exact(cuda, golden_seeded, flags):
     g = golden_seeded
     for name in g["names"]:
@@ -63,7 +65,7 @@ def test_seeded_goldens_bit_exact(cuda, golden_seeded, flags):
 
 
 # ------------------------------------------------------------------ oracle on random inputs
-@pytest.mark.parametrize("flags", [0, 1], ids=["fast", "general"])
+@pytest.mark.parametrize("flags", [0, 128, 1], ids=["lockstep", "skewed", "general"])
 def test_random_ragged_vs_oracle(cuda, flags):
     rng = np.random.default_rng(2024 + flags)
     for it in range(30):
