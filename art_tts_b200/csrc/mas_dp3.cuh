@@ -29,39 +29,50 @@
 // The schedule is stated in plain Python in tests/dp3_model.py and checked there against the oracle
 // (tests/test_dp3_model.py); this file is its transcription.
 //
-// Ring layout ("pre-skewed rows"): row x (natural token order) is a circular buffer of kRing3Cols
-// frames, row pitch kRing3Cols + 4 floats.  Frame f of the utterance whose first tile is tile g0 of
-// the ring's lifetime sits at float column
-//       col = (32*g0 + f + shift(r)) & (kRing3Cols - 1),   r = x / XPL,
-//       shift(r) = ((r + 3) & ~3) + 4 * (((r >> 2) - XPL * r) & 7)
-// i.e. the lane skew rounded up to a multiple of four frames plus a per-lane ROTATION of the ring (no
-// XOR swizzle): a run of consecutive frames of one row is a run of consecutive floats (mod the ring
-// length), 16-byte aligned, so a producer moves the 32 frames of a row with ONE bulk (TMA) copy -- or
-// aligned cp.async / STS.128 chunks.  The consumer lane reads column (32*g0 + tau + shift(r) - r) &
-// mask of its own rows, the same expression for every lane up to a per-lane constant, and for every
-// XPL in 1..8 the 32 lanes hit 32 distinct banks: bank = 4 j + tau + ((-r) & 3) + 4 (r >> 2) (mod 32)
-// with the +4 floats of row pitch (brute-forced as well, profiles/ring3_banks.py).
+// Ring layout: row x (natural token order) is a circular buffer of RC frames (128 or 96), row pitch
+// RC + 4 floats; frame f of the utterance whose first tile is tile g0 of the ring's lifetime sits at
+// float column (32*g0 + f) mod RC -- the same column in every row, so producers write aligned 16-byte
+// chunks (cp.async / STS.128; thread-per-row STS.128 of consecutive rows is conflict-free thanks to the
+// +4 pad) and utterances of different lengths can follow each other in one ring.  The skew lives in the
+// CONSUMER's address: lane r reads column (32*g0 + tau - r) mod RC of its own rows, a per-lane register
+// advanced by 4 bytes per iteration; bank = 4 (r XPL + j) + tau - r = (4 XPL - 1) r + const (mod 32),
+// and 4 XPL - 1 is odd: the 32 lanes always hit 32 distinct banks (profiles/ring3_banks.py).
 #pragma once
 
 #include "mas_dp.cuh"
 
 namespace mas {
 
-constexpr int kRing3Cols = 128;                 // frames per row ring: 4 tiles of 32
-constexpr int kRing3Pitch = kRing3Cols + 4;     // floats per row
+// frames per row ring: 128 (4 tiles, a mask wraps the column) or 96 (3 tiles, where shared memory is
+// short -- the fused tensor-core kernel: compare + select wraps it); row pitch = ring + 4 floats
+constexpr int kRing3Cols = 128;
+constexpr int kRing3Pitch = kRing3Cols + 4;
 constexpr int kRing3Stages = kRing3Cols / kTileY;
 
-// ring shift of the rows owned by lane r when every lane owns xpl tokens (a multiple of 4 floats)
-__device__ __forceinline__ int dp3_shift(int r, int xpl) { return ((r + 3) & ~3) + ((((r >> 2) - xpl * r) & 7) << 2); }
+template <int RC>
+struct Ring3Geom {
+    static_assert(RC == 128 || RC == 96, "ring of 3 or 4 tiles");
+    static constexpr int cols = RC, pitch = RC + 4, stages = RC / kTileY;
+    __device__ __forceinline__ static int stage(int g) { return RC == 128 ? (g & 3) : (g % 3); }
+    __device__ __forceinline__ static uint32_t parity(int g) { return (uint32_t)(RC == 128 ? (g >> 2) : (g / 3)) & 1u; }
+    __device__ __forceinline__ static int wrap(int c) { return RC == 128 ? (c & 127) : (c % 96); }   // c >= 0
+};
 
-// float column (within its row) of lifetime frame fl (= 32*g0 + f) for a row owned by lane r; a run of
-// frames is contiguous up to the wrap at kRing3Cols
-__device__ __forceinline__ int dp3_col(int r, int xpl, int fl) { return (fl + dp3_shift(r, xpl)) & (kRing3Cols - 1); }
+// x / xpl for x < 512, xpl <= 16 (lane that owns token x)
+struct XDiv {
+    uint32_t inv;
+    __device__ __forceinline__ explicit XDiv(int xpl) : inv((65536u + xpl - 1) / xpl) {}
+    __device__ __forceinline__ int operator()(int x) const { return (int)((uint32_t)x * inv >> 16); }
+};
+
+// float column (within every row) of lifetime frame fl (= 32*g0 + f >= 0)
+template <int RC = kRing3Cols>
+__device__ __forceinline__ int dp3_col(int fl) { return Ring3Geom<RC>::wrap(fl); }
 
 struct Ring3 {
-    float *rows;        // xrows x kRing3Pitch floats, 16-byte aligned
-    uint64_t *full;     // [4] producers -> DP warp, one per tile (stage = tile & 3)
-    uint64_t *empty;    // [4] DP warp -> producers
+    float *rows;        // xrows x pitch floats, 16-byte aligned
+    uint64_t *full;     // [stages] producers -> DP warp, one per tile
+    uint64_t *empty;    // [stages] DP warp -> producers
 };
 
 __device__ __forceinline__ float lds32(uint32_t addr)
@@ -72,25 +83,41 @@ __device__ __forceinline__ float lds32(uint32_t addr)
 }
 
 // values of one iteration for this lane's XPL tokens (rows x0 .. x0+XPL-1, same column)
-template <int XPL>
+// `t4` = byte column, already wrapped into the ring.  The destination is declared read-write: the load
+// then cannot be hoisted above the last use of the value it replaces, so ptxas reuses the register in
+// place instead of loading into a fresh one and MOV-ing it over right away -- a MOV that waits out the
+// whole shared-memory latency once per loop trip (ncu: the top short_sb stall of the first version).
+template <int XPL, int RC>
 __device__ __forceinline__ void dp3_load(float (&v)[XPL], uint32_t rowbase, uint32_t t4)
 {
-    const uint32_t a = rowbase + (t4 & (uint32_t)(kRing3Cols * 4 - 4));
+    const uint32_t a = rowbase + t4;
 #pragma unroll
-    for (int j = 0; j < XPL; ++j) v[j] = lds32(a + (uint32_t)(j * kRing3Pitch * 4));
+    for (int j = 0; j < XPL; ++j)
+        asm volatile("ld.shared.f32 %0, [%1];" : "+f"(v[j]) : "r"(a + (uint32_t)(j * (RC + 4) * 4)));
+}
+template <int RC>
+__device__ __forceinline__ uint32_t dp3_next(uint32_t t4)
+{
+    if (RC == 128) return (t4 + 4u) & 508u;
+    return (t4 == (uint32_t)(RC * 4 - 4)) ? 0u : t4 + 4u;
 }
 
 // 32 iterations (one block).  `f` = this lane's frame at the block's first iteration (tau - lane).
 // EDGE blocks: `head` (block 0) selects "x > f -> -1e9" (also covers f < 0, where the ring holds stale
 // data); every EDGE block captures V at f == ty - 1 into sv.  `wait_bar` (may be null): barrier of the
 // NEXT tile, waited before the last 8 iterations -- their prefetches are the first loads that touch it.
-template <int XPL, bool EDGE>
-__device__ __forceinline__ void dp3_iter8(float (&V)[XPL], uint32_t (&acc)[XPL], float (&buf)[2][XPL],
+// kDp3Unroll iterations, fully unrolled.  Kept SHORT on purpose: the L0 instruction cache of a
+// sub-partition is ~6 KB and the fused kernels run an epilogue warp's tile loop next to this one
+// (ncu on the first version, 8 iterations = 4.6 KB at 6 tokens per lane: 62 % of the DP warp's samples
+// were stall_no_inst, profiles/r2_tc_dp3_icache.txt)
+constexpr int kDp3Unroll = 2;
+template <int XPL, bool EDGE, int RC>
+__device__ __forceinline__ void dp3_itern(float (&V)[XPL], uint32_t (&acc)[XPL], float (&buf)[2][XPL],
                                           float (&sv)[XPL], float &left, uint32_t &t4, uint32_t rowbase,
                                           int lane, int x0, int &f, int ty, bool head)
 {
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
+    for (int u = 0; u < kDp3Unroll; ++u) {
         // state at the end of the previous iteration: consumed one iteration from now
         const float cap = __shfl_up_sync(kFull, V[XPL - 1], 1);
         const float(&v)[XPL] = buf[u & 1];
@@ -107,20 +134,21 @@ __device__ __forceinline__ void dp3_iter8(float (&V)[XPL], uint32_t (&acc)[XPL],
             V[j] = nv;
         }
         left = (lane == 0) ? kNeg : cap;   // token 0: v_prev = -1e9 after frame 0 (core.pyx:23-27)
-        dp3_load<XPL>(buf[u & 1], rowbase, t4);   // iteration tau + 2
-        t4 += 4u;
+        dp3_load<XPL, RC>(buf[u & 1], rowbase, t4);   // iteration tau + 2
+        t4 = dp3_next<RC>(t4);
         if (EDGE) ++f;
     }
 }
 
-template <int XPL, bool EDGE>
+template <int XPL, bool EDGE, int RC>
 __device__ __forceinline__ void dp3_block(float (&V)[XPL], uint32_t (&acc)[XPL], float (&buf)[2][XPL],
                                           float (&sv)[XPL], float &left, uint32_t &t4, uint32_t rowbase,
                                           int lane, int x0, int f, int ty, bool head, uint64_t *wait_bar,
                                           uint32_t wait_parity, long long *wait_acc)
 {
 #pragma unroll 1
-    for (int k = 0; k < 3; ++k) dp3_iter8<XPL, EDGE>(V, acc, buf, sv, left, t4, rowbase, lane, x0, f, ty, head);
+    for (int k = 0; k < (kTileY - 8) / kDp3Unroll; ++k)
+        dp3_itern<XPL, EDGE, RC>(V, acc, buf, sv, left, t4, rowbase, lane, x0, f, ty, head);
     if (wait_bar) {
         if (wait_acc) {   // profiling aid: cycles this warp spends starved of tiles
             const long long t0 = clock64();
@@ -130,7 +158,9 @@ __device__ __forceinline__ void dp3_block(float (&V)[XPL], uint32_t (&acc)[XPL],
             mbar_wait(wait_bar, wait_parity);
         }
     }
-    dp3_iter8<XPL, EDGE>(V, acc, buf, sv, left, t4, rowbase, lane, x0, f, ty, head);
+#pragma unroll 1
+    for (int k = 0; k < 8 / kDp3Unroll; ++k)
+        dp3_itern<XPL, EDGE, RC>(V, acc, buf, sv, left, t4, rowbase, lane, x0, f, ty, head);
 }
 
 // frame-aligned direction words of chunk c from the previous (already bit-reversed) and the current
@@ -155,57 +185,59 @@ __device__ __forceinline__ void dp3_flush(uint32_t *bits, int xrows, int nch, in
 // Forward pass of one utterance by ONE warp (1 <= t_x <= t_y, XPL == ceil(t_x / 32) <= 8).  Consumes
 // tiles g0 .. g0+ceil(t_y/32)-1 of the ring's lifetime -- whose producers store 0.0 above the diagonal --
 // writes bits[chunk * xrows + x] (natural token order) and returns V[t_x-1, t_y-1] in every lane.
-template <int XPL>
+template <int XPL, int RC = kRing3Cols>
 __device__ __noinline__ float dp3_forward(const Ring3 ring, uint32_t *bits, int xrows, int tx, int ty,
                                           int lane, int g0, long long *wait_acc = nullptr)
 {
+    using G = Ring3Geom<RC>;
     float V[XPL], buf[2][XPL], sv[XPL];
     uint32_t acc[XPL], prev[XPL];
 #pragma unroll
     for (int j = 0; j < XPL; ++j) {
         V[j] = kNeg;
         sv[j] = 0.0f;
+        buf[0][j] = buf[1][j] = 0.0f;
         acc[j] = 0u;
         prev[j] = 0u;
     }
     const int x0 = lane * XPL;
     const int ntiles = (ty + kTileY - 1) / kTileY;   // == nch
     const int nblk = (ty + 31 + kTileY - 1) / kTileY;
-    const uint32_t rowbase = smem_u32(ring.rows) + (uint32_t)(x0 * kRing3Pitch * 4);
-    uint32_t t4 = (uint32_t)((32 * g0 + dp3_shift(lane, XPL) - lane) * 4);   // byte column of iteration 0
+    const uint32_t rowbase = smem_u32(ring.rows) + (uint32_t)(x0 * G::pitch * 4);
+    uint32_t t4 = (uint32_t)(G::wrap(32 * g0 + RC - lane) * 4);   // byte column of iteration 0: frame -lane
     float left = (lane == 0) ? 0.0f : kNeg;     // frame 0: v_prev(x=0) = 0, everything else -1e9
     {
         long long t0 = 0;
         if (wait_acc) t0 = clock64();
-        mbar_wait(&ring.full[g0 & 3], (uint32_t)(g0 >> 2) & 1u);
+        mbar_wait(&ring.full[G::stage(g0)], G::parity(g0));
         if (wait_acc) *wait_acc += clock64() - t0;
     }
-    dp3_load<XPL>(buf[0], rowbase, t4);
-    t4 += 4u;
-    dp3_load<XPL>(buf[1], rowbase, t4);
-    t4 += 4u;
+    dp3_load<XPL, RC>(buf[0], rowbase, t4);
+    t4 = dp3_next<RC>(t4);
+    dp3_load<XPL, RC>(buf[1], rowbase, t4);
+    t4 = dp3_next<RC>(t4);
     for (int g = 0; g < nblk; ++g) {
         const bool head = g == 0;
         const bool tail = 32 * g + 31 >= ty - 1;
         const int gt = g0 + g + 1;
-        uint64_t *wb = (g + 1 < ntiles) ? &ring.full[gt & 3] : nullptr;
-        const uint32_t wp = (uint32_t)(gt >> 2) & 1u;
+        uint64_t *wb = (g + 1 < ntiles) ? &ring.full[G::stage(gt)] : nullptr;
+        const uint32_t wp = G::parity(gt);
         if (head || tail)
-            dp3_block<XPL, true>(V, acc, buf, sv, left, t4, rowbase, lane, x0, 32 * g - lane, ty, head, wb, wp,
-                                 wait_acc);
+            dp3_block<XPL, true, RC>(V, acc, buf, sv, left, t4, rowbase, lane, x0, 32 * g - lane, ty, head, wb, wp,
+                                     wait_acc);
         else
-            dp3_block<XPL, false>(V, acc, buf, sv, left, t4, rowbase, lane, x0, 32 * g - lane, ty, false, wb, wp,
-                                  wait_acc);
+            dp3_block<XPL, false, RC>(V, acc, buf, sv, left, t4, rowbase, lane, x0, 32 * g - lane, ty, false, wb,
+                                      wp, wait_acc);
         dp3_flush<XPL>(bits, xrows, ntiles, g - 1, lane, x0, prev, acc);
         if (g >= 1) {   // every lane is past frame 32g: tile g-1 is free
             __syncwarp();
-            if (lane == 0) mbar_arrive(&ring.empty[(g0 + g - 1) & 3]);
+            if (lane == 0) mbar_arrive(&ring.empty[G::stage(g0 + g - 1)]);
         }
     }
     dp3_flush<XPL>(bits, xrows, ntiles, nblk - 1, lane, x0, prev, acc);   // t_y = 1 (mod 32)
     __syncwarp();
     if (lane == 0)
-        for (int t = max(nblk - 1, 0); t < ntiles; ++t) mbar_arrive(&ring.empty[(g0 + t) & 3]);
+        for (int t = max(nblk - 1, 0); t < ntiles; ++t) mbar_arrive(&ring.empty[G::stage(g0 + t)]);
     const int ql = (tx - 1) / XPL, qj = (tx - 1) - ql * XPL;
     float s = 0.0f;
 #pragma unroll
@@ -214,14 +246,14 @@ __device__ __noinline__ float dp3_forward(const Ring3 ring, uint32_t *bits, int 
     return __shfl_sync(kFull, s, ql);
 }
 
-template <int XPLMAX>
+template <int XPLMAX, int RC = kRing3Cols>
 __device__ __forceinline__ float dp3_forward_dispatch(const Ring3 &ring, uint32_t *bits, int xrows, int tx,
                                                       int ty, int lane, int g0, long long *wacc = nullptr)
 {
     const int xpl = (tx + 31) >> 5;
-#define MAS_CASE3(N)                                                                             \
-    case N:                                                                                      \
-        if constexpr (N <= XPLMAX) return dp3_forward<N>(ring, bits, xrows, tx, ty, lane, g0, wacc); \
+#define MAS_CASE3(N)                                                                                 \
+    case N:                                                                                          \
+        if constexpr (N <= XPLMAX) return dp3_forward<N, RC>(ring, bits, xrows, tx, ty, lane, g0, wacc); \
         break;
     switch (xpl) {
         MAS_CASE3(1) MAS_CASE3(2) MAS_CASE3(3) MAS_CASE3(4) MAS_CASE3(5) MAS_CASE3(6) MAS_CASE3(7) MAS_CASE3(8)

@@ -23,13 +23,6 @@ constexpr int kF3Threads = 160;   // warps 0-3: staging, warp 4: DP
 constexpr int kF3Helpers = 4;
 constexpr int kF3ZeroBytes = 2048;
 
-// x / xpl for x < 512, xpl <= 16
-struct XDiv {
-    uint32_t inv;
-    __device__ __forceinline__ explicit XDiv(int xpl) : inv((65536u + xpl - 1) / xpl) {}
-    __device__ __forceinline__ int operator()(int x) const { return (int)((uint32_t)x * inv >> 16); }
-};
-
 // Tile t -> ring rows, then ONE arrival of this thread on the tile's `full` barrier.  The band of the tile
 // (max(0, t_x + y - t_y) <= x <= min(t_x - 1, y)) is copied from HBM; every cell ABOVE the diagonal
 // (x > frame) is stored as 0.0 -- that is what keeps those cells at exactly -1e9 in the unguarded
@@ -43,8 +36,6 @@ __device__ __forceinline__ void stage3(const InT *__restrict__ vb, const float *
                                        uint64_t *full, int t, int g0, int tx, int ty, int64_t T_y, int htid,
                                        int mode)
 {
-    const int xpl = max(1, (tx + 31) >> 5);
-    const XDiv xdiv(xpl);
     const int lane = htid & 31, hw = htid >> 5;
     const int y0 = t * kTileY;
     const int fl0 = 32 * (g0 + t);               // lifetime frame of the tile's first column
@@ -57,7 +48,7 @@ __device__ __forceinline__ void stage3(const InT *__restrict__ vb, const float *
         const int left = ty - f0;
         const uint32_t bytes = left >= 4 ? 16u : (left > 0 ? 4u * left : 0u);
         for (int x = lo + 4 * hw + rq; x <= hi; x += 4 * kF3Helpers) {
-            float *dst = rows + x * kRing3Pitch + dp3_col(xdiv(x), xpl, fl0 + 4 * c);
+            float *dst = rows + x * kRing3Pitch + dp3_col(fl0 + 4 * c);
             if (x <= f0) {                       // on / below the diagonal: plain copy
                 cp_async16(dst, v32 + (int64_t)x * T_y + (bytes ? f0 : 0), bytes);
             } else if (x > f0 + 3) {             // wholly above: zeros, nothing is read
@@ -76,7 +67,7 @@ __device__ __forceinline__ void stage3(const InT *__restrict__ vb, const float *
         const int y = y0 + lane;
         const bool in = y < ty;
         for (int x = lo + hw; x <= hi; x += kF3Helpers) {
-            float *dst = rows + x * kRing3Pitch + dp3_col(xdiv(x), xpl, fl0 + lane);
+            float *dst = rows + x * kRing3Pitch + dp3_col(fl0 + lane);
             const bool take = in && y >= x;
             if (sizeof(InT) == 4 && mode == 1) {
                 cp_async4(dst, reinterpret_cast<const float *>(vb) + (int64_t)x * T_y + (take ? y : 0), take ? 4u : 0u);
