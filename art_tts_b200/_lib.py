@@ -22,6 +22,11 @@ FLAG_FORCE_TENSOR = 32
 FLAG_LOCKSTEP_DP = 64
 FLAG_SKEWED_DP = 128
 
+
+def flag_utt_per_cta(k: int) -> int:
+    """MAS_FLAG_UTT_PER_CTA(k) of include/mas_b200.h."""
+    return (int(k) & 0xff) << 8
+
 _DTYPES = {
     torch.float32: MAS_F32,
     torch.float16: MAS_F16,

@@ -385,6 +385,7 @@ int from_prior_impl(const float *mu_x, const float *logs, const float *y, const 
         t.T_y = T_y;
         t.path_esize = path ? esize : 4;
         t.one = one_pattern(path_dtype);
+        t.utt_per_cta = (flags >> 8) & 0xff;
         t.npeer = 0;
         if (want_peer) {   // fused all-gather of the durations (and frame index) over peer memory
             t.npeer = peer->n_peers;

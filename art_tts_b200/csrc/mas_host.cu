@@ -75,7 +75,10 @@ extern "C" int mas_from_prior_host_peer_f32(const float *mu_x_host, const float 
     if (score_host && !score) return MAS_ERR_NULL;
     if (B < 0 || F < 1 || T_x < 1 || T_y < 1) return MAS_ERR_SHAPE;
     if (B == 0) return MAS_OK;
-    if (chunk <= 0) chunk = 128;
+    // default chunk: 128 utterances for a chip-filling batch (measured best at B=1024), but at least ~8
+    // chunks per call so that a small length-bucketed shard (batch-sharded steps: 128 utterances) is still
+    // trimmed chunk by chunk instead of as one block padded to its longest utterance
+    if (chunk <= 0) chunk = std::min(128, std::max(16, (B + 7) / 8));
     if ((B + chunk - 1) / chunk > kMaxChunks) chunk = (B + kMaxChunks - 1) / kMaxChunks;
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return MAS_ERR_NO_DEVICE;

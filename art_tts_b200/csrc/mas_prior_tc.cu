@@ -441,14 +441,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) mas_prior_tc_kernel(const Prior
             char *pb = a.path ? static_cast<char *>(a.path) + (int64_t)u * T_x * T_y * a.path_esize : nullptr;
             const int64_t pbytes = a.path ? (int64_t)T_x * T_y * a.path_esize : 0;
             const bool zbulk = bulk_zero_ok(pb, pbytes);
-            if (lp == 0) {   // the even loader also clears the dense output path of the utterance
-                if (zbulk) {
-                    zero_fill_bulk_part(pb, pbytes, 0, 1, zbuf, kTcZeroBytes, lane, 32);
-                    bulk_commit();
-                } else {
-                    zero_fill_part(pb, pbytes, 0, 1, lane, 32);
-                }
-            }
             for (int t = 0; t < ntiles; ++t, ++g) {
                 if ((g & 1) != lp) continue;
                 if (pend >= 0) finish(pend);   // my previous tile: its copy has had a whole trip to land
@@ -477,10 +469,22 @@ __global__ void __launch_bounds__(kTcThreads, 1) mas_prior_tc_kernel(const Prior
                 l_issue.end();
             }
             if (lp == 0) {
-                // the utterance's zeros must be in HBM before the backtrack warp writes its 1-cells; the
-                // tile in flight is finished first so that the wait for the stores delays nobody
+                // The even loader also clears the dense output path of the utterance: a burst of bulk (TMA)
+                // stores that holds it for ~25 k cycles.  It is issued AFTER the utterance's tiles: the
+                // pipeline then has ~9 tiles of this utterance buffered downstream to work through while the
+                // next utterance's even tiles wait, the CTA's first utterance starts without the bubble, and
+                // for its last one the burst runs under the tail of the forward pass.  (With one utterance
+                // per CTA -- batch-sharded over 8 GPUs -- the burst used to be fully exposed: 12.7 us of 69.)
+                // The zeros must be in HBM before the backtrack warp writes its 1-cells (`zdone`); the tile in
+                // flight is finished first so that the burst delays nobody who could run.
                 if (pend >= 0) { finish(pend); pend = -1; }
-                if (zbulk) bulk_wait_all();
+                if (zbulk) {
+                    zero_fill_bulk_part(pb, pbytes, 0, 1, zbuf, kTcZeroBytes, lane, 32);
+                    bulk_commit();
+                    bulk_wait_all();
+                } else {
+                    zero_fill_part(pb, pbytes, 0, 1, lane, 32);
+                }
                 __threadfence_block();
                 __syncwarp();
                 if (lane == 0) *zdone = k + 1;
@@ -801,7 +805,12 @@ cudaError_t launch_from_prior_tc(const PriorTcArgs &a, cudaStream_t st)
     }
     // persistent: one CTA per SM; `sm_limit` (mas_set_sm_limit) leaves SMs free for a concurrent kernel,
     // e.g. the NCCL all-gather of the previous step's durations
-    const int grid = std::min(a.B, std::max(1, sm_count() - sm_reserve()));
+    // `utt_per_cta` (MAS_FLAG_UTT_PER_CTA): a caller that keeps several launches in flight (batch-sharded
+    // steps on several streams) trades latency for throughput -- fewer CTAs, each running >= that many
+    // utterances back to back, so that the pipeline fill/drain, the zero-fill burst and the backtrack of one
+    // utterance overlap the forward pass of the next as they do in the one-launch-fills-the-chip case
+    int grid = std::min(a.B, std::max(1, sm_count() - sm_reserve()));
+    if (a.utt_per_cta > 1) grid = std::min(grid, std::max(1, (a.B + a.utt_per_cta - 1) / a.utt_per_cta));
     k<<<grid, kTcThreads, a.lay.total, st>>>(a);
     count_launch();
     return cudaGetLastError();

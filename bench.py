@@ -12,8 +12,9 @@ by the all-gather of the int32 durations.  cells = 1024*T_text*T_mel (padded).
   --scaling strong (default, what BASELINE config 5 / SURVEY 8e state): the global batch is dealt
       longest-first over the ranks (distributed.length_bucket_order) and every rank runs its
       contiguous shard of 1024/N utterances.  One launch of 128 utterances is one utterance
-      latency on 148 SMs, so at N>1 the steps run back to back on several streams (CUDA graphs of
-      kernel + barrier chains), the peer-memory gather of step i under the kernel of step i+1.
+      latency on 148 SMs, so the steps run back to back on several streams (CUDA graphs of
+      kernel + barrier chains; the same pipeline at every N, N=1 included), the peer-memory
+      gather of step i under the kernels of the steps in flight on the other streams.
       The B=1024-per-GPU (weak) figure is reported beside it under "weak".
   --scaling weak: B=1024 per GPU (round-1 behaviour), global batch 1024*N.
 
@@ -78,8 +79,12 @@ def parse():
                     help="N>1: all-gather of the durations by NCCL in line after the kernel, or done by the fused "
                          "kernel itself over NVLink peer memory (+ a barrier); auto = p2p when every rank can set "
                          "it up (fused op, tensor-core engine, symmetric memory), else serial")
-    ap.add_argument("--streams", type=int, default=3, help="strong scaling, N>1: steps in flight per GPU")
+    ap.add_argument("--streams", type=int, default=6, help="strong scaling: steps in flight per GPU")
     ap.add_argument("--chain", type=int, default=4, help="steps per captured CUDA graph (even)")
+    ap.add_argument("--utt-per-cta", type=int, default=-1,
+                    help="strong scaling: utterances per persistent CTA of the pipelined launches (-1: auto = 4 when "
+                         "the shard has at most 2 x SMs utterances and several steps are in flight, else 1; measured "
+                         "on one GPU: profiles/r2_strong_shard_sweep.txt)")
     ap.add_argument("--no-graphs", action="store_true", help="strong scaling, N>1: eager launches on the streams")
     ap.add_argument("--no-numa", action="store_true", help="do not bind the rank to its GPU's NUMA node")
     ap.add_argument("--engine", default="auto", choices=["auto", "tensor", "cuda"],
@@ -322,6 +327,7 @@ def run_ours(args):
     strong = args.scaling == "strong"
     fused = args.op == "fused"
     eng_flags = {"auto": 0, "tensor": _lib.FLAG_FORCE_TENSOR, "cuda": _lib.FLAG_NO_TENSOR}[args.engine]
+    pipe_flags = [0]      # set below: MAS_FLAG_UTT_PER_CTA for the pipelined (several steps in flight) launches
     tensor_engine = args.engine == "tensor" or (args.engine == "auto" and N_FEATS >= 32)
     want_value = (not fused) or not args.no_dropin
 
@@ -375,7 +381,9 @@ def run_ours(args):
         return peers if int(flag.item()) else None
 
     peers = None
-    nstreams = max(1, args.streams) if (strong and world > 1) else 1
+    # strong scaling: steps in flight on several streams at every N (N=1 included: the same pipeline, so
+    # that the driver's efficiency compares like with like; it hides the persistent kernel's tail)
+    nstreams = max(1, args.streams) if strong else 1
     if world > 1:
         for _ in range(8):   # bring up every NCCL channel/connection before anything is timed
             w = torch.empty(world * 8, dtype=torch.int32, device=dev)
@@ -395,7 +403,7 @@ def run_ours(args):
         if fused:
             pj = peers[j] if peers is not None else None
             path, dur = monotonic_align.maximum_path_from_prior(
-                mu_x, None, y, shard.t_x, shard.t_y, flags=eng_flags,
+                mu_x, None, y, shard.t_x, shard.t_y, flags=eng_flags | pipe_flags[0],
                 peer=pj.desc() if pj is not None else None)
             if pj is not None:
                 return path, dur, pj.finish()     # the kernel wrote every rank's buffer; the ranks only meet here
@@ -438,6 +446,13 @@ def run_ours(args):
 
     pipeline = {"mode": "single stream, eager launches", "streams": 1}
 
+    if strong and nstreams > 1 and fused:
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        upc = args.utt_per_cta if args.utt_per_cta >= 0 else (4 if B <= 2 * sms else 1)
+        if upc > 1:
+            pipe_flags[0] = _lib.flag_utt_per_cta(upc)
+        pipeline["utterances_per_cta"] = max(1, upc)
+
     def timed_pipelined(steps, warmup):
         """Strong scaling, N>1: `nstreams` steps in flight.  Stream j runs chains of kernel -> barrier
         (captured once as a CUDA graph of `chain` steps), so the peer-memory gather + barrier of one
@@ -463,10 +478,12 @@ def run_ours(args):
                       f"eager launches", file=sys.stderr)
                 graphs = []
                 torch.cuda.synchronize()
-        flag = torch.tensor([1 if len(graphs) == nstreams else 0], device=dev)
-        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-        use_graphs = bool(int(flag.item()))
-        pipeline.update({"mode": ("CUDA graphs of %d-step kernel+barrier chains" % chain) if use_graphs
+        use_graphs = len(graphs) == nstreams
+        if world > 1:
+            flag = torch.tensor([1 if use_graphs else 0], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            use_graphs = bool(int(flag.item()))
+        pipeline.update({"mode": ("CUDA graphs of %d-step kernel%s chains" % (chain, "+barrier" if peers is not None else "")) if use_graphs
                          else "eager launches", "streams": nstreams, "chain": chain if use_graphs else 1})
         per_round = nstreams * (chain if use_graphs else 1)
         launches_per_step = [None]
@@ -521,7 +538,7 @@ def run_ours(args):
     clocks = Clocks(local)
     if rank == 0:
         clocks.start()
-    if strong and world > 1 and nstreams > 1:
+    if strong and nstreams > 1:
         ms_step, launches = timed_pipelined(args.steps, max(3, args.warmup))
     else:
         ms_step, launches = timed_serial(lambda i: step(i, 0), args.steps, max(3, args.warmup))

@@ -67,6 +67,10 @@ enum {
     MAS_FLAG_SKEWED_DP = 128    /* mas_maximum_path: the skewed-lane recurrence kernel (mas_fast3.cu,    */
                                 /* T_x <= 256; same results, A/B measurements and tests)                 */
 };
+/* mas_from_prior_f32 (tensor-core engine): run at least k (1..255) utterances per persistent CTA, i.e. at
+ * most ceil(B / k) CTAs.  For callers that keep several launches in flight (batch-sharded steps on several
+ * streams): throughput instead of the latency of one call.  Bits 8..15 of `flags`. */
+#define MAS_FLAG_UTT_PER_CTA(k) (((k) & 0xff) << 8)
 
 int mas_abi_version(void);
 const char *mas_strerror(int code);
@@ -152,7 +156,7 @@ int mas_from_prior_f32(const float *mu_x, const float *logs, const float *y,
  * Host-buffer variant of mas_from_prior_f32: the batch is still in (pinned) HOST memory, as
  * when the reference's training loop hands y to compute_loss (train_v2.py:203 ->
  * tts.py:466 relocate_input, which moves the whole padded batch).  Copies only what MAS can
- * touch -- each chunk of `chunk` consecutive utterances (0 = 128) is trimmed to its longest
+ * touch -- each chunk of `chunk` consecutive utterances (0 = min(128, max(16, B/8))) is trimmed to its longest
  * utterance, so length-bucketed batches move ~35 % fewer bytes -- on an internal copy stream,
  * and launches the chunk's kernel on `stream` as soon as its rows have landed, so transfers
  * and kernels overlap.  Optionally copies durations / score back to host at the end.
