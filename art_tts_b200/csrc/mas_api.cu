@@ -92,7 +92,7 @@ Plan choose_plan(int T_x, int T_y, int flags, FastLayout *lay, size_t extra_smem
     L.nch = (T_y + 31) / 32;
     const size_t stage_bytes = (size_t)L.xrows * 128;
     const size_t bits_bytes = (size_t)L.nch * L.xrows * 4;
-    const size_t misc = (((size_t)T_x * 8 + 15) & ~(size_t)15) + 128 + extra_smem;
+    const size_t misc = (((size_t)T_x * 8 + 15) & ~(size_t)15) + 128 + kFastZeroBytes + extra_smem;
     Plan plan = kPlanGeneral;
     auto total = [&](int S, bool bits_smem) {
         return (size_t)S * stage_bytes + (bits_smem ? bits_bytes : 0) + misc;
@@ -122,7 +122,7 @@ Plan choose_plan(int T_x, int T_y, int flags, FastLayout *lay, size_t extra_smem
     L.off_first = L.off_bits + (L.bits_in_smem ? bits_bytes : 0);
     L.off_dur = L.off_first + (size_t)T_x * 4;
     L.off_bars = (L.off_dur + (size_t)T_x * 4 + 15) & ~(size_t)15;
-    L.total = L.off_bars + 128 + extra_smem;
+    L.total = L.off_bars + 128 + kFastZeroBytes + extra_smem;
     if (lay) *lay = L;
     return plan;
 }

@@ -12,6 +12,7 @@ namespace mas {
 constexpr int kMaxFastTx = 512;            // single-warp DP: 16 tokens per lane
 constexpr int kSmemBudget = 227 * 1024;    // opt-in dynamic shared memory per CTA on sm_100
 constexpr int kFastThreads = 160;          // 1 DP warp + 4 staging warps
+constexpr int kFastZeroBytes = 2048;       // zeroed shared buffer behind the bulk (TMA) zero fill of the fast kernel
 constexpr int kFast2Threads = 192;         // 2 DP warps + 4 staging warps (long utterances)
 constexpr int kGeneralThreads = 256;
 

@@ -206,6 +206,7 @@ __global__ void __launch_bounds__(kFastThreads) mas_fast_kernel(const MasArgs a)
     int *first = reinterpret_cast<int *>(smem + L.off_first);
     int *dur = reinterpret_cast<int *>(smem + L.off_dur);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + L.off_bars);
+    uint32_t *zbuf = reinterpret_cast<uint32_t *>(smem + L.off_bars + 128);   // kFastZeroBytes of zeros (bulk fill)
 
     const int b = blockIdx.x;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -235,6 +236,8 @@ __global__ void __launch_bounds__(kFastThreads) mas_fast_kernel(const MasArgs a)
         }
         mbar_fence_init();
     }
+    for (int i = tid; i < kFastZeroBytes / 4; i += kFastThreads) zbuf[i] = 0u;
+    fence_proxy_async_smem();
     __syncthreads();
 
     const InT *vb = static_cast<const InT *>(a.value) + (int64_t)b * T_x * T_y;
@@ -272,6 +275,10 @@ __global__ void __launch_bounds__(kFastThreads) mas_fast_kernel(const MasArgs a)
         char *pb = a.path ? static_cast<char *>(a.path) + (int64_t)b * T_x * T_y * a.path_esize
                           : nullptr;
         const int64_t pbytes = a.path ? (int64_t)T_x * T_y * a.path_esize : 0;
+        // the dense output is cleared with bulk (TMA) stores from the zeroed shared buffer, a slice per tile:
+        // one instruction per 2 KB instead of one 16-byte store per thread (round 1: the staging warps spent
+        // a third of their issue slots on those stores)
+        const bool zbulk = bulk_zero_ok(pb, pbytes);
         int stage = 0;
         uint32_t phase = 0;
         for (int t = 0; t < ntiles; ++t) {
@@ -299,9 +306,17 @@ __global__ void __launch_bounds__(kFastThreads) mas_fast_kernel(const MasArgs a)
                 stage = 0;
                 phase ^= 1u;
             }
-            zero_fill_part(pb, pbytes, t, ntiles, htid, nht);
+            if (zbulk) zero_fill_bulk_part(pb, pbytes, t, ntiles, zbuf, kFastZeroBytes, htid, nht);
+            else zero_fill_part(pb, pbytes, t, ntiles, htid, nht);
         }
-        if (ntiles == 0) zero_fill_part(pb, pbytes, 0, 1, htid, nht);
+        if (ntiles == 0) {
+            if (zbulk) zero_fill_bulk_part(pb, pbytes, 0, 1, zbuf, kFastZeroBytes, htid, nht);
+            else zero_fill_part(pb, pbytes, 0, 1, htid, nht);
+        }
+        if (zbulk) {   // the zeros must be in memory before anybody writes a 1-cell
+            bulk_commit();
+            bulk_wait_all();
+        }
     }
     __syncthreads();
     write_path_ones(a.path ? static_cast<char *>(a.path) + (int64_t)b * T_x * T_y * a.path_esize
