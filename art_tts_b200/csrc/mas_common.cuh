@@ -8,6 +8,24 @@
 
 #include "../../include/mas_b200.h"
 
+// Index / protocol assertions of the debug build (-DMAS_DEBUG_CHECKS, profiles/debug_checks.sh): every
+// shared-memory and output index the kernels compute is checked against its bound and a violation traps.
+// compute-sanitizer is closed on the build pool (profiles/r2_sanitizer_closed.txt); this is the
+// "bounds checks and asserts of your own" it asks for.  Compiled out of the product.
+#ifdef MAS_DEBUG_CHECKS
+#include <cstdio>
+#define MAS_CHECK(cond)                                                                              \
+    do {                                                                                             \
+        if (!(cond)) {                                                                               \
+            printf("MAS_CHECK failed: %s  (%s:%d, block %d thread %d)\n", #cond, __FILE__, __LINE__, \
+                   (int)blockIdx.x, (int)threadIdx.x);                                               \
+            __trap();                                                                                \
+        }                                                                                            \
+    } while (0)
+#else
+#define MAS_CHECK(cond) ((void)0)
+#endif
+
 namespace mas {
 
 constexpr float kNeg = -1e9f;   // max_neg_val, core.pyx:40 (exactly representable)

@@ -197,6 +197,7 @@ __device__ __noinline__ float dp_forward(const TileRing ring, uint32_t *bits, in
         }
         if (lane == 0) acc[0] = 0u;
         uint32_t *dst = bits + (size_t)t * xrows + lane;
+        MAS_CHECK(((XPL - 1) << 5) + lane < xrows && t < ntiles);
 #pragma unroll
         for (int j = 0; j < XPL; ++j) {
             dst[j << 5] = acc[j];
@@ -264,6 +265,7 @@ __device__ __forceinline__ void backtrack_bits_impl(const uint32_t *bits, int xr
         } else {
             const int p = 31 - __clz(m);
             const int ys = (c << 5) + p;
+            MAS_CHECK(idx > 0 && idx < tx && c >= 0 && ys <= top && row >= 0 && row < xrows);
             first[idx] = ys;
             dur[idx] = top - ys + 1;
             --idx;
@@ -324,6 +326,8 @@ __device__ __forceinline__ void write_path_ones(void *path_b, int32_t *dur_out_b
 {
     for (int x = tid; x < T_x; x += nthr) {
         const int d = dur[x];
+        MAS_CHECK(d >= 0 && d <= T_y);
+        MAS_CHECK(d == 0 || (first[x] >= 0 && (int64_t)first[x] + d <= T_y));
         if (dur_out_b) dur_out_b[x] = d;
         if (path_b && d > 0) {
             const int64_t e0 = (int64_t)x * T_y + first[x];
@@ -340,6 +344,7 @@ __device__ __forceinline__ void write_frame_idx(int32_t *fi, const int *first, c
     for (int y = ty + tid; y < T_y; y += nthr) fi[y] = -1;
     for (int x = tid; x < T_x; x += nthr) {
         const int d = dur[x], f0 = first[x];
+        MAS_CHECK(d == 0 || (f0 >= 0 && f0 + d <= ty));
         for (int k = 0; k < d; ++k) fi[f0 + k] = x;
     }
 }
@@ -490,6 +495,7 @@ __device__ __noinline__ float dp_forward2(const TileRing ring, uint32_t *bits, i
         }
         if (L == 0) acc[0] = 0u;
         uint32_t *dst = bits + (size_t)t * xrows + L;
+        MAS_CHECK(((XPL - 1) << 6) + L < xrows && t < ntiles);
 #pragma unroll
         for (int j = 0; j < XPL; ++j) {
             dst[j << 6] = acc[j];

@@ -90,6 +90,7 @@ __device__ __forceinline__ float lds32(uint32_t addr)
 template <int XPL, int RC>
 __device__ __forceinline__ void dp3_load(float (&v)[XPL], uint32_t rowbase, uint32_t t4)
 {
+    MAS_CHECK(t4 < (uint32_t)(RC * 4) && (t4 & 3u) == 0u);
     const uint32_t a = rowbase + t4;
 #pragma unroll
     for (int j = 0; j < XPL; ++j)
@@ -176,6 +177,7 @@ __device__ __forceinline__ void dp3_flush(uint32_t *bits, int xrows, int nch, in
         const int x = x0 + j;
         if ((x >> 5) == c) w |= 1u << (x & 31);   // x == y always steps down (core.pyx:34 `index == y`)
         if (x == 0) w = 0u;                        // token 0 never does
+        MAS_CHECK(x < xrows);
         if (c >= 0 && c < nch) bits[(size_t)c * xrows + x] = w;
         prev[j] = cur;
         acc[j] = 0u;
@@ -295,6 +297,7 @@ __device__ __forceinline__ void backtrack_nat(const uint32_t *bits, int xrows, i
             continue;
         }
         const int p = 31 - __clz(m);
+        MAS_CHECK(idx > 0 && idx < tx && c >= 0 && (c << 5) + p < ty);
         first[idx] = (c << 5) + p;
         --idx;
         pw -= 4u;

@@ -356,6 +356,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mas_prior_tc_kernel(const Prior
             // fused all-gather (mas_peer_gather): the rows of this utterance go straight into row
             // row0 + u of every rank's buffers over NVLink peer memory (fire-and-forget stores)
             for (int p = 0; p < a.npeer; ++p) {
+                MAS_CHECK(a.peer_stride >= T_x && a.peer_row0 >= 0);
                 int32_t *row = a.peer[p] + (a.peer_row0 + u) * a.peer_stride;
                 for (int x = lane; x < T_x; x += 32) row[x] = dur[x];
                 if (a.peer_fi[p])
@@ -732,6 +733,27 @@ __global__ void __launch_bounds__(kTcThreads, 1) mas_prior_tc_kernel(const Prior
                     if (have[i]) tmem_ld32(lane_base + L.col_d + (b * 2 + i) * 32, acc[i]);
                 }
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                // -0.5|y|^2 of this tile is folded in BEFORE the accumulator is handed back.  Once d_empty is
+                // released the MMA issuer -- and with it the loaders, kTcSlabs tiles further -- may run ahead
+                // while this warp still waits for room in the DP ring below; the ysq ring (kTcYsq entries)
+                // only covers the tiles up to that hand-back.  Reading it after the wait was a latent race:
+                // the MAS_CHECK build, whose slower epilogue waits longer, returned a wrong prior in
+                // test_fused_vs_oracle_configs[F=16] (profiles/r2_debug_checks.txt).
+                {
+                    const float *qs = ysq + (g % kTcYsq) * kTileY;
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        if (!have[i]) continue;
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
+                            const float4 qq = *reinterpret_cast<const float4 *>(qs + 4 * c);
+                            acc[i][4 * c + 0] = __float_as_uint(qq.x + __uint_as_float(acc[i][4 * c + 0]));
+                            acc[i][4 * c + 1] = __float_as_uint(qq.y + __uint_as_float(acc[i][4 * c + 1]));
+                            acc[i][4 * c + 2] = __float_as_uint(qq.z + __uint_as_float(acc[i][4 * c + 2]));
+                            acc[i][4 * c + 3] = __float_as_uint(qq.w + __uint_as_float(acc[i][4 * c + 3]));
+                        }
+                    }
+                }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&d_empty[b]);       // accumulator buffer free again
@@ -740,7 +762,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) mas_prior_tc_kernel(const Prior
                 if (g >= NS) mbar_wait_relaxed(&ring_empty[sidx], ((g / NS) - 1) & 1, 32);  // DP consumed tile g-NS
                 e_re.end();
                 e_w.begin();
-                const float *qs = ysq + (g % kTcYsq) * kTileY;
                 float *tile = stages + (size_t)sidx * ring.stage_floats;
                 const int y0 = t * kTileY;
 #pragma unroll
@@ -750,16 +771,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) mas_prior_tc_kernel(const Prior
                     if (x >= tx) continue;
                     const float ms = msq[x];
                     const int pr = rm.row(x);
+                    MAS_CHECK(pr >= 0 && pr < L.xrows && sidx >= 0 && sidx < NS);
                     float *row = tile + (pr << 5);
 #pragma unroll
                     for (int c = 0; c < 8; ++c) {
-                        const float4 qq = *reinterpret_cast<const float4 *>(qs + 4 * c);
                         float4 o;
-                        // tts.py:495: y_square - y_mu_double + mu_square + const
-                        o.x = ((qq.x + __uint_as_float(acc[i][4 * c + 0])) + ms) + cst;
-                        o.y = ((qq.y + __uint_as_float(acc[i][4 * c + 1])) + ms) + cst;
-                        o.z = ((qq.z + __uint_as_float(acc[i][4 * c + 2])) + ms) + cst;
-                        o.w = ((qq.w + __uint_as_float(acc[i][4 * c + 3])) + ms) + cst;
+                        // tts.py:495: ((y_square - y_mu_double) + mu_square) + const
+                        o.x = (__uint_as_float(acc[i][4 * c + 0]) + ms) + cst;
+                        o.y = (__uint_as_float(acc[i][4 * c + 1]) + ms) + cst;
+                        o.z = (__uint_as_float(acc[i][4 * c + 2]) + ms) + cst;
+                        o.w = (__uint_as_float(acc[i][4 * c + 3]) + ms) + cst;
                         *reinterpret_cast<float4 *>(row + ((c ^ (pr & 7)) << 2)) = o;
                     }
                 }
