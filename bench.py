@@ -596,6 +596,15 @@ def run_ours(args):
 
     kname = (("mas_prior_tc_kernel" if tensor_engine else "mas_prior_kernel") if fused else "mas_fast_kernel")
     roofline = roofline_of(kname, shard.fused_alg_bytes() if fused else shard.dropin_alg_bytes(), k_ms, B)
+    # the same bytes against the steady-state time per step of the pipelined loop (several launches in
+    # flight fill the persistent kernel's tail): what the headline `value` corresponds to
+    step_bytes = torch.tensor([float(shard.fused_alg_bytes() if fused else shard.dropin_alg_bytes())], device=dev,
+                              dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(step_bytes)
+    roofline["frac_steady_state"] = float(step_bytes.item()) / world / (ms_step * 1e-3) / 1e9 / hbm_peak
+    roofline["frac_steady_state_note"] = ("algorithmic bytes of one rank's share of a step / (ms_per_step) / peak: "
+                                          "the pipelined loop, launches overlapping; `frac` is one launch alone")
     if fused and tensor_engine:
         roofline["engine"] = ("tcgen05.mma kind::tf32, 3xTF32 split (fp32-level accuracy), mu_x in TMEM; "
                               "the CUDA-core engine (--engine cuda) is the fp32 FMA variant")
