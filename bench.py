@@ -85,6 +85,8 @@ def parse():
                     help="strong scaling: utterances per persistent CTA of the pipelined launches (-1: auto = 4 when "
                          "the shard has at most 2 x SMs utterances and several steps are in flight, else 1; measured "
                          "on one GPU: profiles/r2_strong_shard_sweep.txt)")
+    ap.add_argument("--kernel-utt-per-cta", type=int, default=0,
+                    help="utterances per CTA for the single-launch measurements as well (0: library default)")
     ap.add_argument("--no-graphs", action="store_true", help="strong scaling, N>1: eager launches on the streams")
     ap.add_argument("--no-numa", action="store_true", help="do not bind the rank to its GPU's NUMA node")
     ap.add_argument("--engine", default="auto", choices=["auto", "tensor", "cuda"],
@@ -327,6 +329,8 @@ def run_ours(args):
     strong = args.scaling == "strong"
     fused = args.op == "fused"
     eng_flags = {"auto": 0, "tensor": _lib.FLAG_FORCE_TENSOR, "cuda": _lib.FLAG_NO_TENSOR}[args.engine]
+    if args.kernel_utt_per_cta > 1:
+        eng_flags |= _lib.flag_utt_per_cta(args.kernel_utt_per_cta)
     pipe_flags = [0]      # set below: MAS_FLAG_UTT_PER_CTA for the pipelined (several steps in flight) launches
     tensor_engine = args.engine == "tensor" or (args.engine == "auto" and N_FEATS >= 32)
     want_value = (not fused) or not args.no_dropin
