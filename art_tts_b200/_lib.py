@@ -21,6 +21,7 @@ FLAG_NO_TENSOR = 16
 FLAG_FORCE_TENSOR = 32
 FLAG_LOCKSTEP_DP = 64
 FLAG_SKEWED_DP = 128
+FLAG_TMA = 1 << 16
 
 
 def flag_utt_per_cta(k: int) -> int:

@@ -7,6 +7,8 @@
 #include <cstdlib>
 #include <initializer_list>
 
+#include <cuda.h>   // CUtensorMap types / enums only: the encoder is fetched with cudaGetDriverEntryPoint, libcuda is not linked
+
 #include "mas_internal.h"
 
 namespace mas {
@@ -61,7 +63,7 @@ static int env_int(const char *name, int dflt)
 // the library, so that plan queries (mas_plan, mas_from_prior_plan, mas_peer_durations_supported)
 // and the launches that follow can never disagree.
 struct Tuning {
-    int prior_tc, prior_tc_min_f, stages, dp2_min_tx, prior_spill, prior_stats, fma_per_smsp, extra_fma, fast3;
+    int prior_tc, prior_tc_min_f, stages, dp2_min_tx, prior_spill, prior_stats, fma_per_smsp, extra_fma, fast3, fast_tma;
 };
 static const Tuning &tuning()
 {
@@ -75,6 +77,7 @@ static const Tuning &tuning()
         v.prior_stats = env_int("MAS_PRIOR_STATS", 0);
         v.fma_per_smsp = env_int("MAS_PRIOR_FMA_PER_SMSP", 2);
         if (v.fma_per_smsp < 1 || v.fma_per_smsp > 4) v.fma_per_smsp = 2;
+        v.fast_tma = env_int("MAS_FAST_TMA", 0);   // TMA tensor-load staging of the drop-in kernel: opt-in (measured: no faster)
         v.fast3 = env_int("MAS_FAST3", 0);   // skewed-lane drop-in kernel: opt-in until its HBM staging beats the lock-step one
         v.extra_fma = env_int("MAS_PRIOR_EXTRA_FMA", 1);
         if (v.extra_fma < 0 || v.extra_fma > 1) v.extra_fma = 1;
@@ -89,8 +92,11 @@ Plan choose_plan(int T_x, int T_y, int flags, FastLayout *lay, size_t extra_smem
 {
     FastLayout L{};
     L.xrows = ((T_x + row_align - 1) / row_align) * row_align;
+    // single-DP-warp kernel: a stage has kTmaBoxRows of slack behind its rows (the last TMA box of a tile
+    // may reach past the band); stage bases stay 1024-byte aligned (SWIZZLE_128B atom)
+    L.srows = L.xrows + ((row_align == 32 && extra_smem == 0) ? kTmaBoxRows : 0);
     L.nch = (T_y + 31) / 32;
-    const size_t stage_bytes = (size_t)L.xrows * 128;
+    const size_t stage_bytes = (size_t)L.srows * 128;
     const size_t bits_bytes = (size_t)L.nch * L.xrows * 4;
     const size_t misc = (((size_t)T_x * 8 + 15) & ~(size_t)15) + 128 + kFastZeroBytes + extra_smem;
     Plan plan = kPlanGeneral;
@@ -125,6 +131,33 @@ Plan choose_plan(int T_x, int T_y, int flags, FastLayout *lay, size_t extra_smem
     L.total = L.off_bars + 128 + kFastZeroBytes + extra_smem;
     if (lay) *lay = L;
     return plan;
+}
+
+// Tensor map of `value` viewed as [B*T_x rows, T_y frames] fp32 for the TMA staging of mas_fast_kernel:
+// boxes of [kTmaBoxRows rows][32 frames] (128-byte rows, SWIZZLE_128B = the XOR pattern of tile_index()).
+// false when the driver entry point is missing or the encoder refuses the shape.
+static bool encode_value_map(TensorMap *out, const void *base, int B, int T_x, int T_y)
+{
+    typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                 const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                 CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return reinterpret_cast<EncodeFn>(p);
+    }();
+    if (!fn) return false;
+    static_assert(sizeof(TensorMap) == sizeof(CUtensorMap) && alignof(TensorMap) >= alignof(CUtensorMap), "CUtensorMap layout");
+    const cuuint64_t dims[2] = {(cuuint64_t)T_y, (cuuint64_t)B * (cuuint64_t)T_x};
+    const cuuint64_t strides[1] = {(cuuint64_t)T_y * 4};
+    const cuuint32_t box[2] = {32u, (cuuint32_t)kTmaBoxRows};   // 32 frames = one tile = one 128-byte swizzle row
+    const cuuint32_t estr[2] = {1, 1};
+    return fn(reinterpret_cast<CUtensorMap *>(out), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void *>(base), dims,
+              strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 static size_t bits_workspace_bytes(int B, int T_x, int T_y)
@@ -316,10 +349,15 @@ int mas_maximum_path(const void *value, int value_dtype, const float *cell_mask,
     a.load_mode = 0;
     if (value_dtype == MAS_F32 && !cell_mask && !(flags & MAS_FLAG_NO_ASYNC))
         a.load_mode = (T_y % 4 == 0 && (uintptr_t)value % 16 == 0) ? 2 : 1;
+    // TMA tensor loads for the single-DP-warp kernel (same conditions as the 16-byte cp.async path)
+    TensorMap tmap{};
+    if (a.load_mode == 2 && plan != kPlanGeneral && !a.skewed && a.dp_warps == 1 && a.lay.srows >= a.lay.xrows + kTmaBoxRows &&
+        (tuning().fast_tma || (flags & MAS_FLAG_TMA)) && encode_value_map(&tmap, value, B, T_x, T_y))
+        a.load_mode = 3;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const cudaError_t e = (plan == kPlanGeneral) ? launch_general(a, value_dtype, st)
                           : a.skewed           ? launch_fast3(a, value_dtype, st)
-                                               : launch_fast(a, value_dtype, st);
+                                               : launch_fast(a, value_dtype, st, a.load_mode == 3 ? &tmap : nullptr);
     return (int)e;
 }
 

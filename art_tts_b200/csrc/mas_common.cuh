@@ -210,6 +210,23 @@ __device__ __forceinline__ void bulk_load(void *dst_smem, const void *src_gmem, 
                  : "memory");
 }
 
+// ---------------------------------------------------------------- TMA tensor loads
+// cp.async.bulk.tensor.2d global -> shared::cta through a tensor map (CUtensorMap, built on the host by
+// cuTensorMapEncodeTiled): ONE instruction moves a whole [rows x 32 frames] box, coordinates may be
+// unaligned and out-of-bounds elements read as zero; completion is reported to the mbarrier as bytes.
+// c0 = innermost coordinate (frame), c1 = row.
+__device__ __forceinline__ void tma_load_2d(void *dst_smem, const void *tmap, int c0, int c1, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const void *tmap)
+{
+    asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
+}
+
 // ---------------------------------------------------------------- bulk (TMA) zero fill
 // cp.async.bulk shared::cta -> global: the copy engine streams a zeroed shared buffer to HBM,
 // so clearing the dense output costs one instruction per `zbytes` instead of one 16-byte

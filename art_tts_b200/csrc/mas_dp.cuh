@@ -96,14 +96,16 @@ __device__ __forceinline__ void dp_step(float (&V)[XPL], uint32_t (&acc)[XPL],
 
 // One staged tile of up to 32 frames (frames y0 .. y0+nsteps-1, y0 % 32 == 0).
 // `stage` is the swizzled [row][32 frames] tile in shared memory (see tile_index()).
-template <int XPL, bool DIAG, bool FULL, bool FMAX = false>
+// NAT: the tile keeps token x in row x (what a TMA box writes, SWIZZLE_128B: chunk ^= row & 7) instead of
+// the permuted row (x % XPL) * 32 + x / XPL of the cp.async / STS staging.
+template <int XPL, bool DIAG, bool FULL, bool FMAX = false, bool NAT = false>
 __device__ __forceinline__ void dp_tile(float (&V)[XPL], uint32_t (&acc)[XPL], float &left,
                                         const float *__restrict__ stage, int lane, int x0, int y0,
                                         int nsteps)
 {
     // explicit shared-space address: `stage` arrives through a struct, and a generic LD would
     // otherwise be emitted for the hottest load of the kernel
-    const uint32_t rowbase = smem_u32(stage + (lane << 5));
+    const uint32_t rowbase = smem_u32(stage + ((NAT ? x0 : lane) << 5));
     const int sw = lane & 7;
 #pragma unroll 1
     for (int g = 0; g < 8; ++g) {
@@ -111,7 +113,9 @@ __device__ __forceinline__ void dp_tile(float (&V)[XPL], uint32_t (&acc)[XPL], f
         if (!FULL && s0 >= nsteps) break;
         float4 vv[XPL];
 #pragma unroll
-        for (int j = 0; j < XPL; ++j) vv[j] = lds128(rowbase + (j << 12) + ((g ^ sw) << 4));
+        for (int j = 0; j < XPL; ++j)
+            vv[j] = NAT ? lds128(rowbase + (j << 7) + ((g ^ ((x0 + j) & 7)) << 4))
+                        : lds128(rowbase + (j << 12) + ((g ^ sw) << 4));
         float v[XPL];
 #pragma unroll
         for (int j = 0; j < XPL; ++j) v[j] = f4_get<0>(vv[j]);
@@ -149,7 +153,7 @@ struct TileRing {
 // returns V[t_x-1, t_y-1].  Requires 1 <= t_x <= t_y and XPL == ceil(t_x/32).
 // `g0` = index (in the ring's lifetime) of this utterance's first tile: a persistent CTA keeps
 // one ring and its barrier phases running across utterances.
-template <int XPL, bool FMAX = false>
+template <int XPL, bool FMAX = false, bool NAT = false>
 __device__ __noinline__ float dp_forward(const TileRing ring, uint32_t *bits, int xrows, int tx,
                                          int ty, int lane, int g0 = 0, long long *wait_acc = nullptr)
 {
@@ -178,10 +182,10 @@ __device__ __noinline__ float dp_forward(const TileRing ring, uint32_t *bits, in
         const int nsteps = min(kTileY, ty - y0);
         const bool diag = y0 < tx;  // some token x > y still exists in this tile
         if (nsteps == kTileY) {
-            if (diag) dp_tile<XPL, true, true, FMAX>(V, acc, left, tile, lane, x0, y0, nsteps);
-            else dp_tile<XPL, false, true, FMAX>(V, acc, left, tile, lane, x0, y0, nsteps);
+            if (diag) dp_tile<XPL, true, true, FMAX, NAT>(V, acc, left, tile, lane, x0, y0, nsteps);
+            else dp_tile<XPL, false, true, FMAX, NAT>(V, acc, left, tile, lane, x0, y0, nsteps);
         } else {
-            dp_tile<XPL, true, false, FMAX>(V, acc, left, tile, lane, x0, y0, nsteps);
+            dp_tile<XPL, true, false, FMAX, NAT>(V, acc, left, tile, lane, x0, y0, nsteps);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&ring.empty[stage]);

@@ -18,8 +18,17 @@ constexpr int kGeneralThreads = 256;
 
 enum Plan { kPlanFastSmemBits = 0, kPlanFastSpillBits = 1, kPlanGeneral = 2 };
 
+constexpr int kTmaBoxRows = 16;            // rows of one TMA box of the drop-in kernel ([16 rows][32 frames] = 2 KB)
+
+// layout-compatible stand-in for CUtensorMap (cuda.h: 64-byte aligned, 16 x 64-bit opaque words), so that
+// the kernels' headers do not need the driver API header
+struct alignas(64) TensorMap {
+    unsigned long long opaque[16];
+};
+
 struct FastLayout {       // dynamic shared memory carve-up of the fast kernels
     int xrows;            // 32 * ceil(T_x / 32)
+    int srows;            // rows of one ring stage: xrows (+ kTmaBoxRows of slack for the last TMA box of a tile)
     int nch;              // ceil(T_y / 32) direction words per token
     int nstages;
     int bits_in_smem;
@@ -42,7 +51,8 @@ struct MasArgs {
     int skewed;            // 1: mas_fast3_kernel (skewed-lane recurrence, ring of mas_dp3.cuh)
     long long *stats;      // optional [B][16] phase cycle counters (profiles/microbench/fast3_phases.cu), else NULL
     int load_mode;         // fast kernel staging: 0 = LDG/STS (any dtype, cell mask), 1 = cp.async 4 B,
-                           // 2 = cp.async 16 B (fp32, rows 16-byte aligned)
+                           // 2 = cp.async 16 B (fp32, rows 16-byte aligned), 3 = TMA tensor boxes (same
+                           // conditions; mas_fast_kernel only; rows in natural token order)
     unsigned long long one;
     FastLayout lay;
 };
@@ -58,7 +68,7 @@ cudaError_t launch_lengths_from_mask(const void *mask, int mask_dtype, int B, in
 cudaError_t launch_seq_lengths(const void *xm, int xdt, int64_t xsb, int64_t xst, const void *ym, int ydt,
                                int64_t ysb, int64_t yst, int B, int T_x, int T_y, int32_t *t_x, int32_t *t_y,
                                cudaStream_t st);
-cudaError_t launch_fast(const MasArgs &a, int value_dtype, cudaStream_t st);
+cudaError_t launch_fast(const MasArgs &a, int value_dtype, cudaStream_t st, const TensorMap *tmap = nullptr);
 cudaError_t launch_general(const MasArgs &a, int value_dtype, cudaStream_t st);
 // mas_fast3.cu: drop-in kernel on the skewed-lane recurrence (T_x <= 256)
 bool fast3_layout(int T_x, int T_y, FastLayout *lay);

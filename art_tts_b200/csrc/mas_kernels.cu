@@ -170,22 +170,23 @@ __device__ __forceinline__ void stage_value_tile_async(const float *__restrict__
     }
 }
 
-template <int XPL>
+template <int XPL, bool NAT>
 __device__ __forceinline__ float run_forward(const TileRing &ring, uint32_t *bits, int xrows, int tx,
                                              int ty, int lane)
 {
-    return dp_forward<XPL>(ring, bits, xrows, tx, ty, lane);
+    return dp_forward<XPL, false, NAT>(ring, bits, xrows, tx, ty, lane);
 }
 
-// dispatch on tokens-per-lane of THIS utterance (warp-uniform), bounded by the launch bucket
-template <int XPLMAX>
+// dispatch on tokens-per-lane of THIS utterance (warp-uniform), bounded by the launch bucket.
+// NAT: tiles in natural row order (TMA boxes), see dp_tile
+template <int XPLMAX, bool NAT = false>
 __device__ __forceinline__ float forward_dispatch(const TileRing &ring, uint32_t *bits, int xrows,
                                                   int tx, int ty, int lane)
 {
     const int xpl = (tx + 31) >> 5;
 #define MAS_CASE(N)                                                               \
     case N:                                                                       \
-        if constexpr (N <= XPLMAX) return run_forward<N>(ring, bits, xrows, tx, ty, lane); \
+        if constexpr (N <= XPLMAX) return run_forward<N, NAT>(ring, bits, xrows, tx, ty, lane); \
         break;
     switch (xpl) {
         MAS_CASE(1) MAS_CASE(2) MAS_CASE(3) MAS_CASE(4) MAS_CASE(5) MAS_CASE(6) MAS_CASE(7)
@@ -198,7 +199,7 @@ __device__ __forceinline__ float forward_dispatch(const TileRing &ring, uint32_t
 }
 
 template <typename InT, int XPLMAX>
-__global__ void __launch_bounds__(kFastThreads) mas_fast_kernel(const MasArgs a)
+__global__ void __launch_bounds__(kFastThreads) mas_fast_kernel(const MasArgs a, const __grid_constant__ TensorMap tmap)
 {
     extern __shared__ __align__(1024) unsigned char smem[];
     const FastLayout &L = a.lay;
@@ -227,14 +228,17 @@ __global__ void __launch_bounds__(kFastThreads) mas_fast_kernel(const MasArgs a)
     ring.full = bars;
     ring.empty = bars + L.nstages;
     ring.nstages = L.nstages;
-    ring.stage_floats = L.xrows * kTileY;
+    ring.stage_floats = L.srows * kTileY;
+    const bool tma = sizeof(InT) == 4 && a.load_mode == 3;
 
     if (tid == 0) {
         for (int s = 0; s < L.nstages; ++s) {
-            mbar_init(&ring.full[s], kHelperWarps * 32);  // every staging thread arrives once
+            // TMA staging: one thread announces the tile's bytes; else every staging thread arrives once
+            mbar_init(&ring.full[s], tma ? 1 : kHelperWarps * 32);
             mbar_init(&ring.empty[s], 1);
         }
         mbar_fence_init();
+        if (tma) tma_prefetch_desc(&tmap);
     }
     for (int i = tid; i < kFastZeroBytes / 4; i += kFastThreads) zbuf[i] = 0u;
     fence_proxy_async_smem();
@@ -250,7 +254,12 @@ __global__ void __launch_bounds__(kFastThreads) mas_fast_kernel(const MasArgs a)
         __syncwarp();
         float score = 0.0f;
         if (active) {
-            score = forward_dispatch<XPLMAX>(ring, bits, L.xrows, tx, ty, lane);
+            if constexpr (sizeof(InT) == 4) {
+                score = tma ? forward_dispatch<XPLMAX, true>(ring, bits, L.xrows, tx, ty, lane)
+                            : forward_dispatch<XPLMAX, false>(ring, bits, L.xrows, tx, ty, lane);
+            } else {
+                score = forward_dispatch<XPLMAX, false>(ring, bits, L.xrows, tx, ty, lane);
+            }
             __syncwarp();
             if (lane == 0) backtrack_bits(bits, L.xrows, tx, ty, first, dur, L.bits_in_smem != 0);
         } else if (degenerate) {
@@ -285,8 +294,29 @@ __global__ void __launch_bounds__(kFastThreads) mas_fast_kernel(const MasArgs a)
             if (t >= L.nstages) mbar_wait(&ring.empty[stage], phase ^ 1u);
             float *dst = stages + stage * ring.stage_floats;
             bool async_done = false;
+            if (tma) {
+                // TMA tensor loads: ONE thread moves the band of the tile as [16 rows x 32 frames] boxes in
+                // natural row order (box k = rows lo8 + 16 k ..; lo8 = band start rounded down to the 8-row
+                // swizzle atom; rows past the band -- at most 15, possibly the next utterance's -- land in the
+                // stage's slack rows and are never read).  Frames beyond T_y read as zero.  No per-thread
+                // copy instruction, no LSU miss-queue entry per 16 bytes: the staging warps only clear the
+                // output, and one CTA keeps whole tiles in flight (profiles/r2_fast3_phases.txt: per-thread
+                // cp.async tops out near 20 GB/s per SM with 128 threads).
+                if (tid == 0) {
+                    const int y0 = t * kTileY;
+                    const int lo8 = max(0, tx + y0 - ty) & ~7;
+                    const int hi = min(tx - 1, y0 + kTileY - 1);
+                    const int nbox = (hi - lo8) / kTmaBoxRows + 1;
+                    mbar_arrive_expect_tx(&ring.full[stage], (uint32_t)nbox * kTmaBoxRows * 128u);
+                    for (int k = 0; k < nbox; ++k)
+                        tma_load_2d(dst + ((lo8 + kTmaBoxRows * k) << 5), &tmap, y0, b * T_x + lo8 + kTmaBoxRows * k,
+                                    &ring.full[stage]);
+                }
+                async_done = true;
+            }
             if constexpr (sizeof(InT) == 4) {
-                if (a.load_mode == 2) {
+                if (tma) {
+                } else if (a.load_mode == 2) {
                     stage_value_tile_async<true>(reinterpret_cast<const float *>(vb), dst, t, tx, ty,
                                                  T_y, hw, kHelperWarps, lane);
                     async_done = true;
@@ -296,7 +326,8 @@ __global__ void __launch_bounds__(kFastThreads) mas_fast_kernel(const MasArgs a)
                     async_done = true;
                 }
             }
-            if (async_done) {
+            if (tma) {
+            } else if (async_done) {
                 cp_async_arrive(&ring.full[stage]);
             } else {
                 stage_value_tile<InT>(vb, mb, dst, t, tx, ty, T_y, hw, kHelperWarps, lane);
@@ -490,10 +521,10 @@ static cudaError_t launch_fast2_typed(const MasArgs &a, cudaStream_t st)
 }
 
 template <typename InT>
-static cudaError_t launch_fast_typed(const MasArgs &a, cudaStream_t st)
+static cudaError_t launch_fast_typed(const MasArgs &a, cudaStream_t st, const TensorMap *tmap)
 {
     const int xplmax = (a.T_x + 31) / 32;
-    void (*k)(const MasArgs) = nullptr;
+    void (*k)(const MasArgs, const TensorMap) = nullptr;
     if constexpr (sizeof(InT) == 4) {  // fp32: register budget sized to the batch's T_x bucket
         if (xplmax <= 2) k = mas_fast_kernel<InT, 2>;
         else if (xplmax <= 4) k = mas_fast_kernel<InT, 4>;
@@ -508,12 +539,13 @@ static cudaError_t launch_fast_typed(const MasArgs &a, cudaStream_t st)
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)a.lay.total);
     if (e != cudaSuccess) return e;
-    k<<<a.B, kFastThreads, a.lay.total, st>>>(a);
+    static const TensorMap no_map{};
+    k<<<a.B, kFastThreads, a.lay.total, st>>>(a, tmap ? *tmap : no_map);
     count_launch();
     return cudaGetLastError();
 }
 
-cudaError_t launch_fast(const MasArgs &a, int value_dtype, cudaStream_t st)
+cudaError_t launch_fast(const MasArgs &a, int value_dtype, cudaStream_t st, const TensorMap *tmap)
 {
     if (a.dp_warps == 2) {
         switch (value_dtype) {
@@ -525,10 +557,10 @@ cudaError_t launch_fast(const MasArgs &a, int value_dtype, cudaStream_t st)
         }
     }
     switch (value_dtype) {
-    case MAS_F32: return launch_fast_typed<float>(a, st);
-    case MAS_F16: return launch_fast_typed<__half>(a, st);
-    case MAS_BF16: return launch_fast_typed<__nv_bfloat16>(a, st);
-    case MAS_F64: return launch_fast_typed<double>(a, st);
+    case MAS_F32: return launch_fast_typed<float>(a, st, tmap);
+    case MAS_F16: return launch_fast_typed<__half>(a, st, tmap);
+    case MAS_BF16: return launch_fast_typed<__nv_bfloat16>(a, st, tmap);
+    case MAS_F64: return launch_fast_typed<double>(a, st, tmap);
     default: return cudaErrorInvalidValue;
     }
 }

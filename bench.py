@@ -458,13 +458,18 @@ def run_ours(args):
         pipeline["utterances_per_cta"] = max(1, upc)
 
     def timed_pipelined(steps, warmup):
-        """Strong scaling, N>1: `nstreams` steps in flight.  Stream j runs chains of kernel -> barrier
+        """Strong scaling: `nstreams` steps in flight.  Stream j runs chains of kernel -> barrier
         (captured once as a CUDA graph of `chain` steps), so the peer-memory gather + barrier of one
-        step run under the kernels of the steps on the other streams."""
+        step run under the kernels of the steps on the other streams.  EXACTLY `steps` steps are
+        timed: they are dealt round-robin over the streams, stream j replays its chain graph
+        n_j // chain times and then a second graph holding the remaining n_j % chain steps (nothing
+        in the timed region runs eagerly: an eager step on a side stream would have to cudaMalloc
+        its 680 MB outputs, torch.cuda.graph() empties the allocator cache)."""
         main = torch.cuda.current_stream()
         streams = [torch.cuda.Stream(device=dev) for _ in range(nstreams)]
         chain = max(2, args.chain // 2 * 2)      # even: the two gather slots keep alternating across replays
-        graphs, keep = [], []
+        per_stream = [steps // nstreams + (1 if j < steps % nstreams else 0) for j in range(nstreams)]
+        graphs, tails, keep = [], [], []
         if not args.no_graphs:
             try:
                 for j, s in enumerate(streams):
@@ -477,6 +482,16 @@ def run_ours(args):
                         for i in range(chain):
                             keep.append(step(j * chain + i, j))
                     graphs.append(g)
+                    rem = per_stream[j] % chain
+                    tg = None
+                    if rem:
+                        tg = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(tg, stream=s):
+                            for i in range(rem):
+                                keep.append(step(j * chain + i, j))
+                        if peers is not None and rem % 2:      # keep the gather slot parity of the chain graphs
+                            peers[j].step += 1
+                    tails.append(tg)
             except Exception as e:
                 print(f"[bench] rank {rank}: CUDA-graph capture of the step chain failed ({type(e).__name__}: {e}); "
                       f"eager launches", file=sys.stderr)
@@ -488,12 +503,11 @@ def run_ours(args):
             dist.all_reduce(flag, op=dist.ReduceOp.MIN)
             use_graphs = bool(int(flag.item()))
         pipeline.update({"mode": ("CUDA graphs of %d-step kernel%s chains" % (chain, "+barrier" if peers is not None else "")) if use_graphs
-                         else "eager launches", "streams": nstreams, "chain": chain if use_graphs else 1})
-        per_round = nstreams * (chain if use_graphs else 1)
+                         else "eager launches", "streams": nstreams, "chain": chain if use_graphs else 1,
+                         "steps_per_stream": per_stream})
         launches_per_step = [None]
 
-        def run(n):
-            rounds, rem = divmod(n, per_round)
+        def run_warm(rounds):
             for _ in range(rounds):
                 for j, s in enumerate(streams):
                     with torch.cuda.stream(s):
@@ -501,9 +515,21 @@ def run_ours(args):
                             graphs[j].replay()
                         else:
                             step(j, j)
-            for i in range(rem):                   # the remainder of K: eager, round-robin
-                with torch.cuda.stream(streams[i % nstreams]):
-                    step(i, i % nstreams)
+
+        def run_timed():
+            if use_graphs:
+                most = max(per_stream) // chain
+                for r in range(most + 1):
+                    for j, s in enumerate(streams):
+                        with torch.cuda.stream(s):
+                            if r < per_stream[j] // chain:
+                                graphs[j].replay()
+                            elif r == per_stream[j] // chain and tails[j] is not None:
+                                tails[j].replay()
+            else:
+                for i in range(steps):
+                    with torch.cuda.stream(streams[i % nstreams]):
+                        step(i, i % nstreams)
 
         def fork():
             ev = torch.cuda.Event()
@@ -515,11 +541,14 @@ def run_ours(args):
             for s in streams:
                 main.wait_stream(s)
 
+        per_round = nstreams * (chain if use_graphs else 1)
         fork()
-        l0 = _lib.launch_count()
-        run(-(-max(per_round, warmup) // per_round) * per_round)    # whole rounds: gather slots keep alternating
+        run_warm(-(-max(per_round, warmup) // per_round))    # whole rounds: gather slots keep alternating
+        if not use_graphs:
+            run_timed()                                       # eager: let the allocator cache every stream's outputs
         join()
         barrier()
+        l0 = _lib.launch_count()
         if use_graphs:   # launches replayed from a graph are not counted by the library: count two eager steps
             with torch.cuda.stream(streams[0]):
                 l1 = _lib.launch_count()
@@ -531,7 +560,7 @@ def run_ours(args):
         e0.record(main)
         fork()
         l0 = _lib.launch_count()
-        run(steps)
+        run_timed()
         join()
         e1.record(main)
         barrier()
@@ -746,8 +775,10 @@ def run_ours(args):
 
 def time_configs(dev, monotonic_align, _lib, iters=20):
     """BASELINE configs 1-4 through both entries: median per-call device time, the 126 MB L2 flushed
-    (a 256 MB write) before every timed call -- these shapes are far smaller than L2."""
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    (a 1 GB write) before every timed call -- these shapes are far smaller than L2."""
+    # 1 GB: the flush also has to outlast the host side of the call that follows it (allocations, ctypes), or
+    # the idle gap before the launch would be timed with the kernel
+    flush = torch.empty(1 << 30, dtype=torch.uint8, device=dev)
     out = {}
     shapes = {
         "cfg1": dict(B=16, T_x=190, T_y=870, F=80, kind="ljs", seed=0),

@@ -67,6 +67,8 @@ enum {
     MAS_FLAG_SKEWED_DP = 128    /* mas_maximum_path: the skewed-lane recurrence kernel (mas_fast3.cu,    */
                                 /* T_x <= 256; same results, A/B measurements and tests)                 */
 };
+#define MAS_FLAG_TMA (1 << 16) /* mas_maximum_path: stage tiles with TMA tensor loads (cp.async.bulk.tensor.2d) instead of
+                                  per-thread cp.async; fp32 value, rows 16-byte aligned, T_x <= 256; same results */
 /* mas_from_prior_f32 (tensor-core engine): run at least k (1..255) utterances per persistent CTA, i.e. at
  * most ceil(B / k) CTAs.  For callers that keep several launches in flight (batch-sharded steps on several
  * streams): throughput instead of the latency of one call.  Bits 8..15 of `flags`. */

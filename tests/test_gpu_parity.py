@@ -46,9 +46,12 @@ def test_small_goldens_bit_exact(cuda, golden_small):
             assert fast.dtype == got.dtype and torch.equal(fast, got), name
         skew = run_mas(value, mask, cuda, flags=128)  # skewed-lane kernel (every dtype / staging mode)
         assert skew.dtype == got.dtype and torch.equal(skew, got), name
+        if name != "holes":
+            tma = run_mas(value, mask, cuda, strict_mask=False, flags=1 << 16)   # TMA tensor-load staging (fp32, aligned rows)
+            assert tma.dtype == got.dtype and torch.equal(tma, got), name
 
 
-@pytest.mark.parametrize("flags", [0, 128, 1], ids=["lockstep", "skewed", "general"])
+@pytest.mark.parametrize("flags", [0, 1 << 16, 128, 1], ids=["lockstep", "lockstep_tma", "skewed", "general"])
 def test_seeded_goldens_bit_exact(cuda, golden_seeded, flags):
     g = golden_seeded
     for name in g["names"]:
@@ -65,7 +68,7 @@ def test_seeded_goldens_bit_exact(cuda, golden_seeded, flags):
 
 
 # ------------------------------------------------------------------ oracle on random inputs
-@pytest.mark.parametrize("flags", [0, 128, 1], ids=["lockstep", "skewed", "general"])
+@pytest.mark.parametrize("flags", [0, 1 << 16, 128, 1], ids=["lockstep", "lockstep_tma", "skewed", "general"])
 def test_random_ragged_vs_oracle(cuda, flags):
     rng = np.random.default_rng(2024 + flags)
     for it in range(30):
