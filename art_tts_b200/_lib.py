@@ -22,6 +22,7 @@ FLAG_FORCE_TENSOR = 32
 FLAG_LOCKSTEP_DP = 64
 FLAG_SKEWED_DP = 128
 FLAG_TMA = 1 << 16
+FLAG_CLUSTER2 = 1 << 17
 
 
 def flag_utt_per_cta(k: int) -> int:

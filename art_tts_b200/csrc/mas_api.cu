@@ -63,7 +63,7 @@ static int env_int(const char *name, int dflt)
 // the library, so that plan queries (mas_plan, mas_from_prior_plan, mas_peer_durations_supported)
 // and the launches that follow can never disagree.
 struct Tuning {
-    int prior_tc, prior_tc_min_f, stages, dp2_min_tx, prior_spill, prior_stats, fma_per_smsp, extra_fma, fast3, fast_tma;
+    int prior_tc, prior_tc_min_f, stages, dp2_min_tx, prior_spill, prior_stats, fma_per_smsp, extra_fma, fast3, fast_tma, tc_cluster;
 };
 static const Tuning &tuning()
 {
@@ -77,6 +77,7 @@ static const Tuning &tuning()
         v.prior_stats = env_int("MAS_PRIOR_STATS", 0);
         v.fma_per_smsp = env_int("MAS_PRIOR_FMA_PER_SMSP", 2);
         if (v.fma_per_smsp < 1 || v.fma_per_smsp > 4) v.fma_per_smsp = 2;
+        v.tc_cluster = env_int("MAS_TC_CLUSTER", 4);   // CTAs per utterance of the tensor-core kernel when T_x > 256: 4 (default), 2, 0 = off
         v.fast_tma = env_int("MAS_FAST_TMA", 0);   // TMA tensor-load staging of the drop-in kernel: opt-in (measured: no faster)
         v.fast3 = env_int("MAS_FAST3", 0);   // skewed-lane drop-in kernel: opt-in until its HBM staging beats the lock-step one
         v.extra_fma = env_int("MAS_PRIOR_EXTRA_FMA", 1);
@@ -196,7 +197,8 @@ uint64_t mas_launch_count(void) { return g_launches.load(std::memory_order_relax
 static bool tc_engine_selected(int F, int T_x, int T_y, int flags, mas::TcLayout *lay)
 {
     if (!tuning().prior_tc || (flags & (MAS_FLAG_FORCE_GENERAL | MAS_FLAG_SPILL_BITS | MAS_FLAG_NO_TENSOR))) return false;
-    const mas::TcLayout l = mas::tc_layout(F, T_x, T_y);
+    if (T_x > 256 && tuning().tc_cluster != 2 && tuning().tc_cluster != 4) return false;
+    const mas::TcLayout l = mas::tc_layout(F, T_x, T_y, (flags & MAS_FLAG_CLUSTER2) ? 2 : tuning().tc_cluster);
     if (lay) *lay = l;
     // measured (profiles/config_sweep.py): below ~32 features the FMA work is so small that the
     // CUDA-core kernel is as fast or faster (F=16: 0.157 vs 0.166 ms at B=1024, 160x512)
@@ -365,6 +367,7 @@ int mas_from_prior_plan(int B, int F, int T_x, int T_y, int flags)
 {
     (void)B;
     if (T_x < 1 || T_y < 1 || F < 1) return MAS_ERR_SHAPE;
+    if (tc_engine_selected(F, T_x, T_y, flags, nullptr)) return 0;   // tensor-core engine (cluster of CTAs when T_x > 256)
     FastLayout lay;
     const Plan plan = choose_plan(T_x, T_y, flags, &lay, prior_extra_smem(F, T_x, T_y, false), 3);
     return plan == kPlanGeneral ? 1 : 0;
@@ -410,6 +413,12 @@ int from_prior_impl(const float *mu_x, const float *logs, const float *y, const 
         t.frame_idx = frame_idx;
         t.score = score;
         t.lp_out = log_prior_out;
+        t.bits_ws = nullptr;
+        if (t.lay.cluster > 1) {   // direction words of the cluster kernel live in the workspace
+            if (!workspace || workspace_bytes < mas_workspace_bytes(B, T_x, T_y)) return MAS_ERR_WORKSPACE;
+            if ((uintptr_t)workspace % 16) return MAS_ERR_ALIGN;
+            t.bits_ws = static_cast<uint32_t *>(workspace);
+        }
         t.stats = nullptr;
         if (tuning().prior_stats) {  // profiling aid: counters at the tail of an over-sized workspace
             const size_t need = mas_workspace_bytes(B, T_x, T_y), sbytes = (size_t)1024 * 32 * 8;

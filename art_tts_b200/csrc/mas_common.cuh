@@ -80,6 +80,57 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t *bar, uint32_t parity
     while (!mbar_try_wait(bar, parity)) __nanosleep(ns);
 }
 
+// ---------------------------------------------------------------- thread-block clusters (distributed shared memory)
+// A shared::cta address is also a valid shared::cluster address of the executing CTA; map_to_cta gives the
+// address of the same variable in CTA `rank` of the cluster.  The cluster-scope arrive/wait pair orders the
+// remote st.shared::cluster stores issued before the arrive (same thread) before the loads after the wait.
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t saddr, uint32_t rank)
+{
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr)
+{
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity, unsigned ns = 0)
+{
+    while (!mbar_try_wait_cluster(bar, parity))
+        if (ns) __nanosleep(ns);
+}
+__device__ __forceinline__ void st_cluster_f4(uint32_t cluster_addr, float x, float y, float z, float w)
+{
+    asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(cluster_addr), "f"(x), "f"(y), "f"(z), "f"(w)
+                 : "memory");
+}
+__device__ __forceinline__ void st_cluster_u32(uint32_t cluster_addr, uint32_t v)
+{
+    asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(cluster_addr), "r"(v) : "memory");
+}
+
 __device__ __forceinline__ float4 lds128(uint32_t addr)
 {
     float4 v;

@@ -537,6 +537,258 @@ __device__ __forceinline__ float prior_forward2_dispatch(const TileRing &ring, u
     return 0.0f;
 }
 
+// ------------------------------------------------------------------------------------
+// Chain of DP warps across the CTAs of a thread-block cluster (long token axes: T_x > 256).
+// CTA h of the cluster owns the tokens [xlo, xlo + xs) of the utterance (xs = 128 or 256) and runs them
+// on two DP warps exactly like dp_forward2; the chain position of a warp is 2h + w.  Inside a CTA the
+// boundary value travels through the `edge` ring as before.  Across CTAs it travels through
+// DISTRIBUTED SHARED MEMORY: warp 1 of CTA h stores its last token's 32 values of a tile straight into
+// a ring in CTA h+1's shared memory (st.shared::cluster) and arrives on that CTA's mbarrier; warp 0 of
+// CTA h+1 runs behind it and hands the slot back with a remote arrive (kXRing tiles of slack).
+// Tiles are counted globally (tile tt = frames 32 tt ..): CTA h only works on the tiles that hold band
+// cells of its tokens, [t_lo, t_lo + ntiles), t_lo = xlo / 32.  Its first token needs V[xlo-1, 32 t_lo - 1],
+// i.e. the LAST value of the left CTA's tile t_lo - 1: the exchange on a link covers the tiles
+// t_lo - 1 .. in_last (in_last = last tile of the left CTA), the first one only seeds `left`.
+// Direction words go to global memory (bits[tt * bstride + row], row local to the CTA).
+// ------------------------------------------------------------------------------------
+constexpr int kXRing = 8;   // tiles of boundary values in flight on a cluster link
+
+struct ChainCtx {
+    uint32_t in_ring;       // shared::cta address: [kXRing][32] floats written by the left CTA's warp 1
+    uint64_t *in_full;      // [kXRing] count 1, arrived by the left CTA
+    uint32_t left_empty;    // shared::cluster address of the left CTA's out_empty[0]
+    uint32_t right_ring;    // shared::cluster address of the right CTA's in_ring
+    uint32_t right_full;    // shared::cluster address of the right CTA's in_full[0]
+    uint64_t *out_empty;    // [kXRing] count 1, arrived by the right CTA
+    int n_in, n_out;        // boundary tiles received / sent so far (CTA lifetime)
+};
+
+template <int XPL, bool DIAG, bool FULL, bool FMAX>
+__device__ __forceinline__ void dp_tile_chain(float (&V)[XPL], uint32_t (&acc)[XPL], float &left,
+                                              const float *__restrict__ stage, uint32_t in_addr, uint32_t out_addr,
+                                              int L, int lane, int x0, int y0, int nsteps)
+{
+    const uint32_t rowbase = smem_u32(stage + (L << 5));
+    const int sw = lane & 7;
+#pragma unroll 1
+    for (int g = 0; g < 8; ++g) {
+        const int s0 = g << 2;
+        if (!FULL && s0 >= nsteps) break;
+        float4 vv[XPL];
+#pragma unroll
+        for (int j = 0; j < XPL; ++j) vv[j] = lds128(rowbase + (j << 13) + ((g ^ sw) << 4));   // rows j*64 + L
+        const float4 ev = in_addr ? lds128(in_addr + (g << 4)) : make_float4(kNeg, kNeg, kNeg, kNeg);
+        float4 out;
+        float v[XPL];
+#pragma unroll
+        for (int j = 0; j < XPL; ++j) v[j] = f4_get<0>(vv[j]);
+        out.x = dp_step2<XPL, DIAG, FMAX>(V, acc, v, left, lane, x0, y0 + s0, 1u << s0, ev.x);
+        out.y = out.z = out.w = 0.0f;
+        if (FULL || s0 + 1 < nsteps) {
+#pragma unroll
+            for (int j = 0; j < XPL; ++j) v[j] = f4_get<1>(vv[j]);
+            out.y = dp_step2<XPL, DIAG, FMAX>(V, acc, v, left, lane, x0, y0 + s0 + 1, 2u << s0, ev.y);
+        }
+        if (FULL || s0 + 2 < nsteps) {
+#pragma unroll
+            for (int j = 0; j < XPL; ++j) v[j] = f4_get<2>(vv[j]);
+            out.z = dp_step2<XPL, DIAG, FMAX>(V, acc, v, left, lane, x0, y0 + s0 + 2, 4u << s0, ev.z);
+        }
+        if (FULL || s0 + 3 < nsteps) {
+#pragma unroll
+            for (int j = 0; j < XPL; ++j) v[j] = f4_get<3>(vv[j]);
+            out.w = dp_step2<XPL, DIAG, FMAX>(V, acc, v, left, lane, x0, y0 + s0 + 3, 8u << s0, ev.w);
+        }
+        if (out_addr && lane == 31) st_cluster_f4(out_addr + (g << 4), out.x, out.y, out.z, out.w);
+    }
+}
+
+// Forward pass of the tokens [xlo, xlo + 64 XPL) of one utterance by DP warp `w` (0/1) of this CTA.
+// `in_last`  (warp 0): last tile for which the left CTA publishes a boundary (< t_lo - 1: no left neighbour);
+// `out_first` (warp 1): first tile whose boundary the right CTA wants (> last tile: no right neighbour).
+// Returns V[t_x-1, t_y-1] when this warp owns token t_x-1 (`*owns`).
+template <int XPL, bool FMAX = false>
+__device__ __noinline__ float dp_forward_chain(const TileRing ring, uint32_t *bits, int bstride, int tx, int ty,
+                                               int lane, int w, int g0, float *edge, uint64_t *edge_full,
+                                               int xlo, int t_lo, int ntiles, int in_last, int out_first,
+                                               ChainCtx &cx, int *owns)
+{
+    float V[XPL];
+    uint32_t acc[XPL];
+#pragma unroll
+    for (int j = 0; j < XPL; ++j) {
+        V[j] = kNeg;
+        acc[j] = 0u;
+    }
+    const int L = 32 * w + lane;
+    const int x0 = xlo + L * XPL;               // this lane's first token (global index)
+    float left = (x0 == 0) ? 0.0f : kNeg;       // frame 0: v_prev(x=0) = 0, everything else -1e9
+    if (w == 0 && in_last >= t_lo - 1) {
+        // V[xlo-1, 32 t_lo - 1]: the last value of the left CTA's tile t_lo - 1
+        const int slot = cx.n_in % kXRing;
+        mbar_wait_cluster(&cx.in_full[slot], (uint32_t)(cx.n_in / kXRing) & 1u);
+        float e;
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(e) : "r"(cx.in_ring + (uint32_t)slot * 128u + 124u));
+        if (lane == 0) left = e;
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(cx.left_empty + (uint32_t)slot * 8u);
+        ++cx.n_in;
+    }
+    int stage = g0 % ring.nstages;
+    uint32_t phase = (uint32_t)(g0 / ring.nstages) & 1u;
+    for (int t = 0; t < ntiles; ++t) {
+        const int gt = g0 + t, tt = t_lo + t;
+        mbar_wait(&ring.full[stage], phase);
+        uint32_t in_addr = 0u, out_addr = 0u;
+        int in_slot = -1, out_slot = -1;
+        if (w == 1) {
+            mbar_wait(&edge_full[gt & 3], (uint32_t)(gt >> 2) & 1u);   // warp 0 finished this tile
+            in_addr = smem_u32(edge + ((gt & 3) << 5));
+            if (tt >= out_first) {
+                out_slot = cx.n_out % kXRing;
+                if (cx.n_out >= kXRing)
+                    mbar_wait_cluster(&cx.out_empty[out_slot], (uint32_t)(cx.n_out / kXRing - 1) & 1u);
+                out_addr = cx.right_ring + (uint32_t)out_slot * 128u;
+                ++cx.n_out;
+            }
+        } else {
+            out_addr = smem_u32(edge + ((gt & 3) << 5));
+            if (tt <= in_last) {
+                in_slot = cx.n_in % kXRing;
+                mbar_wait_cluster(&cx.in_full[in_slot], (uint32_t)(cx.n_in / kXRing) & 1u);
+                in_addr = cx.in_ring + (uint32_t)in_slot * 128u;
+                ++cx.n_in;
+            }
+        }
+        const float *tile = ring.stages + stage * ring.stage_floats;
+        const int y0 = tt * kTileY;
+        const int nsteps = min(kTileY, ty - y0);
+        const bool diag = y0 < tx;  // some token x > y may still exist in this tile
+        if (nsteps == kTileY) {
+            if (diag) dp_tile_chain<XPL, true, true, FMAX>(V, acc, left, tile, in_addr, out_addr, L, lane, x0, y0, nsteps);
+            else dp_tile_chain<XPL, false, true, FMAX>(V, acc, left, tile, in_addr, out_addr, L, lane, x0, y0, nsteps);
+        } else {
+            dp_tile_chain<XPL, true, false, FMAX>(V, acc, left, tile, in_addr, out_addr, L, lane, x0, y0, nsteps);
+        }
+        __syncwarp();
+        if (lane == 0) {
+            mbar_arrive(&ring.empty[stage]);
+            if (w == 0) mbar_arrive(&edge_full[gt & 3]);
+            if (in_slot >= 0) mbar_arrive_cluster(cx.left_empty + (uint32_t)in_slot * 8u);   // slot read: hand it back
+        }
+        // the thread that stored the boundary values publishes them (release at cluster scope)
+        if (out_slot >= 0 && lane == 31) mbar_arrive_cluster(cx.right_full + (uint32_t)out_slot * 8u);
+        if (++stage == ring.nstages) {
+            stage = 0;
+            phase ^= 1u;
+        }
+        // x == y always steps down (core.pyx:34 `index == y`), token 0 never does.
+        if (diag) {
+#pragma unroll
+            for (int j = 0; j < XPL; ++j)
+                if (((x0 + j) >> 5) == tt) acc[j] |= 1u << ((x0 + j) & 31);
+        }
+        if (x0 == 0) acc[0] = 0u;
+        uint32_t *dst = bits + (size_t)tt * bstride + L;
+#pragma unroll
+        for (int j = 0; j < XPL; ++j) {
+            dst[j << 6] = acc[j];
+            acc[j] = 0u;
+        }
+    }
+    // total alignment score: token tx-1 = local lane (tx-1-xlo)/XPL, slot (tx-1-xlo)%XPL
+    const int xl = tx - 1 - xlo;
+    const int ql = xl / XPL, qj = xl - ql * XPL;
+    *owns = (xl >= 0 && xl < 64 * XPL && (ql >> 5) == w) ? 1 : 0;
+    float s = 0.0f;
+#pragma unroll
+    for (int j = 0; j < XPL; ++j)
+        if (j == qj) s = V[j];
+    return __shfl_sync(kFull, s, ql & 31);
+}
+
+template <int XPLMAX, bool FMAX = false>
+__device__ __forceinline__ float chain_forward_dispatch(const TileRing &ring, uint32_t *bits, int bstride, int tx,
+                                                        int ty, int txl, int lane, int w, int g0, float *edge,
+                                                        uint64_t *edge_full, int xlo, int t_lo, int ntiles,
+                                                        int in_last, int out_first, ChainCtx &cx, int *owns)
+{
+    const int xpl = (txl + 63) >> 6;
+#define MAS_CASEC(N)                                                                                              \
+    case N:                                                                                                       \
+        if constexpr (N <= XPLMAX)                                                                                \
+            return dp_forward_chain<N, FMAX>(ring, bits, bstride, tx, ty, lane, w, g0, edge, edge_full, xlo, t_lo, \
+                                             ntiles, in_last, out_first, cx, owns);                               \
+        break;
+    switch (xpl) {
+        MAS_CASEC(1) MAS_CASEC(2) MAS_CASEC(3) MAS_CASEC(4)
+    default: break;
+    }
+#undef MAS_CASEC
+    *owns = 0;
+    return 0.0f;
+}
+
+// Backtrack over direction words kept in GLOBAL memory, by a whole warp.  One dependent load per word from
+// L2 (~700 cycles) would dominate a long utterance, so the warp keeps a WINDOW in registers -- lane i holds
+// the words of token wx - i for the NC chunks wc, wc-1, .. -- loaded with all lanes' requests in flight at
+// once, and walks inside it with shuffles (every lane follows the same walk).  Tokens are the CTA's local
+// ones (global token idx = xlo + local), rows by RowMap(txl, 6).  Starts on token `idx` at frame `y`
+// (the last frame of that token); returns the last frame of token xlo - 1 when the walk leaves the CTA's
+// tokens downwards (the left CTA continues there), or -1 when it ended on token 0.
+template <int NC = 4>
+__device__ __forceinline__ int backtrack_bits_window(const uint32_t *bits, int bstride, int txl, int xlo, int idx,
+                                                     int y, int *first, int *dur, int lane)
+{
+    const RowMap rm(txl, 6);
+    int top = y, c = y >> 5;
+    int wx = -1, wc = -1;
+    uint32_t W[NC];
+#pragma unroll
+    for (int n = 0; n < NC; ++n) W[n] = 0u;
+    while (y >= 0 && idx != 0) {
+        const int xl = idx - xlo;
+        if (wx < 0 || xl < wx - 31 || c < wc - (NC - 1)) {
+            wx = xl;
+            wc = c;
+            const int mx = wx - lane;
+            const int row = mx >= 0 ? rm.row(mx) : 0;
+#pragma unroll
+            for (int n = 0; n < NC; ++n)
+                W[n] = (mx >= 0 && wc - n >= 0) ? __ldcg(bits + (size_t)(wc - n) * bstride + row) : 0u;
+        }
+        const int n = wc - c;
+        uint32_t mine = W[0];
+#pragma unroll
+        for (int q = 1; q < NC; ++q) mine = (n == q) ? W[q] : mine;
+        const uint32_t w = __shfl_sync(kFull, mine, wx - xl);
+        const int s = y & 31;
+        const uint32_t m = w & (0xffffffffu >> (31 - s));
+        if (m == 0u) {  // stays on this token down to the chunk start
+            y = (c << 5) - 1;
+            --c;
+            continue;
+        }
+        const int p = 31 - __clz(m);
+        const int ys = (c << 5) + p;
+        MAS_CHECK(xl >= 0 && xl < txl && ys <= top);
+        if (lane == 0) {
+            first[idx] = ys;
+            dur[idx] = top - ys + 1;
+        }
+        --idx;
+        y = ys - 1;
+        top = y;
+        if (idx < xlo) return y;
+        if (p == 0) --c;   // crossed into the previous chunk
+    }
+    if (top >= 0 && lane == 0) {
+        first[idx] = 0;
+        dur[idx] = top + 1;
+    }
+    return -1;
+}
+
 // one cell of the prior, same operation order as the producers / log_prior_kernel
 __device__ __forceinline__ float lp_cell(const float *mub, const float *yb, int F, int T_x,
                                          int64_t T_y, int x, int y, float cst)

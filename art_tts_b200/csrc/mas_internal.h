@@ -131,7 +131,10 @@ struct TcLayout {
     int xrows, nch, nstages, bits_slots;
     int nb;                // accumulator buffers in TMEM
     int col_ahi, col_alo, col_d;   // TMEM column map
-    size_t off_stages, off_slabs, off_staging, off_bits, off_ysq, off_musq, off_first, off_dur, off_zero, off_bars, total;
+    int cluster;           // CTAs per utterance: 1, or a thread-block cluster of 2 / 4 splitting the token axis (T_x > 256)
+    int xs;                // tokens per CTA (cluster mode: 256 / 128; else xrows)
+    int xr_tot;            // cluster mode: row stride of the direction words in the workspace (T_x rounded up to 64)
+    size_t off_stages, off_slabs, off_staging, off_bits, off_ysq, off_musq, off_first, off_dur, off_zero, off_bars, off_cl, total;
 };
 constexpr int kMaxPeers = 16;
 struct PriorTcArgs {
@@ -145,6 +148,7 @@ struct PriorTcArgs {
     float *score;
     long long *stats;      // optional [grid][32] cycle counters (MAS_PRIOR_STATS=1), else NULL
     float *lp_out;         // optional parity tap [B,T_x,T_y]: the prior exactly as the DP consumed it
+    uint32_t *bits_ws;     // cluster mode: direction words [B][nch][xr_tot] in the caller's workspace
     int32_t *peer[kMaxPeers];      // mas_peer_gather: every rank's durations buffer, or npeer == 0
     int32_t *peer_fi[kMaxPeers];   // and (optionally, else NULL) every rank's frame-index buffer
     int npeer;
@@ -155,7 +159,7 @@ struct PriorTcArgs {
     unsigned long long one;
     TcLayout lay;
 };
-TcLayout tc_layout(int F, int T_x, int T_y);
+TcLayout tc_layout(int F, int T_x, int T_y, int cluster = 4);
 cudaError_t launch_from_prior_tc(const PriorTcArgs &a, cudaStream_t st);
 
 int from_prior_impl(const float *mu_x, const float *logs, const float *y, const int32_t *t_x,

@@ -53,6 +53,9 @@ constexpr int kTcStage = 2;        // staging buffers [F][32 frames] behind the 
 constexpr int kTcMsq = 4;         // ring of per-utterance -0.5|mu|^2 vectors (> utterances an accumulator lags)
 constexpr int kTcZeroBytes = 4096;
 constexpr int kTcTmemCols = 512;
+// cluster mode: inbound boundary ring [kXRing][32] floats (1 KB), then in_full[kXRing], out_empty[kXRing],
+// bt_full[4] mbarriers and bt_in[4] ints (hand-over of the backtrack between CTAs)
+constexpr int kTcClBytes = 2048;
 
 // ---------------------------------------------------------------- tcgen05 wrappers
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -150,24 +153,36 @@ struct TcStat {
 // Shared-memory carve-up and TMEM column map of the tensor-core kernel, or ok == 0 when the
 // shape does not qualify (T_x > 256, F > 96, or the buffers do not fit): the CUDA-core kernel
 // of mas_prior.cu takes those.
-TcLayout tc_layout(int F, int T_x, int T_y)
+TcLayout tc_layout(int F, int T_x, int T_y, int cluster)
 {
     TcLayout L{};
     L.ok = 0;
     L.Fp = (F + 7) / 8 * 8;
     L.xrows = (T_x + 63) / 64 * 64;            // two DP warps: 64 lanes share the token axis
     L.nch = (T_y + 31) / 32;
-    if (T_x > 256 || L.Fp > 96) return L;
-    const int mt = (T_x + 127) / 128;          // M tiles of 128 tokens
+    L.cluster = 1;
+    L.xs = L.xrows;
+    L.xr_tot = L.xrows;
+    if (T_x > 512 || L.Fp > 96) return L;
+    if (T_x > 256) {
+        // Long token axis: a thread-block cluster per utterance, CTA h owns the tokens [h xs, (h+1) xs) -- its own
+        // M tiles of mu_x in its own tensor memory, its own tile ring and DP warps; the recurrence crosses the CTA
+        // boundary through distributed shared memory (mas_dp.cuh dp_forward_chain).  Direction words go to the
+        // workspace (L2): 4096 frames x 256 tokens of them would not fit next to the rings.
+        L.cluster = (cluster == 2) ? 2 : 4;
+        L.xs = 512 / L.cluster;
+        L.xrows = L.xs;
+    }
+    const int mt = ((L.cluster > 1 ? L.xs : T_x) + 127) / 128;   // M tiles of 128 tokens per CTA
     L.col_ahi = 0;
     L.col_alo = mt * L.Fp;
     L.col_d = 2 * mt * L.Fp;
     L.nb = std::min(4, (kTcTmemCols - L.col_d) / 64);   // accumulator buffers of 2 x 32 columns
     if (L.nb < 2) return L;
-    const size_t stage = (size_t)L.xrows * 128, bits = (size_t)L.nch * L.xrows * 4;
+    const size_t stage = (size_t)L.xrows * 128, bits = L.cluster > 1 ? 0 : (size_t)L.nch * L.xrows * 4;
     const size_t slabs = (size_t)kTcSlabs * 2 * L.Fp * 128;   // hi + lo, K-major: 1 KB per k step of 8 features
     const size_t misc = (size_t)kTcYsq * 128 + (size_t)kTcMsq * 256 * 4 + (((size_t)T_x * 8 + 15) & ~(size_t)15) + 16 +
-                        kTcZeroBytes + 1024 + (size_t)kTcStage * L.Fp * 128;
+                        kTcZeroBytes + 1024 + (size_t)kTcStage * L.Fp * 128 + (L.cluster > 1 ? kTcClBytes : 0);
     for (int slots = 2; slots >= 1 && !L.ok; --slots)
         for (int ns = 4; ns >= 2; --ns)
             if ((size_t)ns * stage + slots * bits + slabs + misc <= (size_t)kSmemBudget) {
@@ -187,17 +202,25 @@ TcLayout tc_layout(int F, int T_x, int T_y)
     L.off_dur = L.off_first + (size_t)T_x * 4;
     L.off_zero = (L.off_dur + (size_t)T_x * 4 + 15) & ~(size_t)15;
     L.off_bars = L.off_zero + kTcZeroBytes;
-    L.total = L.off_bars + 1024;
+    L.off_cl = L.off_bars + 1024;
+    L.total = L.off_cl + (L.cluster > 1 ? kTcClBytes : 0);
     // one CTA per SM: each CTA allocates all 512 TMEM columns
     L.total = std::max(L.total, (size_t)(kSmemBudget / 2 + 1024));
     return L;
 }
 
-template <int XPLMAX>
+// CS = CTAs per utterance: 1, or a thread-block cluster of 2 / 4 (launched with the cluster attribute) that
+// splits the token axis (T_x > 256); everything cluster-specific is compiled out of the CS == 1 kernel.
+template <int XPLMAX, int CS>
 __global__ void __launch_bounds__(kTcThreads, 1) mas_prior_tc_kernel(const PriorTcArgs a)
 {
     extern __shared__ __align__(1024) unsigned char smem[];
+    constexpr bool CL = CS > 1;
     const TcLayout &L = a.lay;
+    const int crank = CL ? (int)cluster_ctarank() : 0;            // CTA h of the cluster
+    const int cid = CL ? (int)blockIdx.x / CS : (int)blockIdx.x;  // persistent worker index
+    const int ncl = CL ? (int)gridDim.x / CS : (int)gridDim.x;
+    const int xs = CL ? L.xs : 0, xlo = crank * xs;               // this CTA's tokens: [xlo, xlo + xs)
     const int F = a.F, Fp = L.Fp, T_x = a.T_x, NS = L.nstages, NB = L.nb;
     const int64_t T_y = a.T_y;
     float *stages = reinterpret_cast<float *>(smem + L.off_stages);
@@ -266,23 +289,53 @@ __global__ void __launch_bounds__(kTcThreads, 1) mas_prior_tc_kernel(const Prior
     tc_fence_after();
     const uint32_t tbase = __shfl_sync(kFull, *tslot, 0);
 
-    auto geometry = [&](int u, int &tx, int &ty, int &ntiles, bool &degenerate) {
+    // ntiles = tiles this CTA works on, the first of them global tile t_lo (frames 32 t_lo ..).  One CTA per
+    // utterance: all of them.  Cluster: the tiles that hold band cells of the CTA's tokens (mas_dp.cuh).
+    auto geometry = [&](int u, int &tx, int &ty, int &ntiles, bool &degenerate, int &t_lo) {
         tx = min(max(a.t_x[u], 0), T_x);
         ty = min(max(a.t_y[u], 0), a.T_y);
         degenerate = tx > ty && ty >= 1;
         const bool active = tx >= 1 && ty >= 1 && !degenerate;
         ntiles = active ? (ty + kTileY - 1) / kTileY : 0;
+        t_lo = 0;
+        if constexpr (CL) {
+            if (ntiles > 0) {
+                if (tx <= xlo) {
+                    ntiles = 0;
+                } else {
+                    t_lo = xlo >> 5;
+                    ntiles = min(ntiles - 1, (min(tx, xlo + xs) - 1 - tx + ty) >> 5) - t_lo + 1;
+                }
+            }
+        }
     };
-    // which 128-token M tiles of tile t hold band cells (all of them when the parity tap is on)
+    // which of the CTA's 128-token M tiles hold band cells of (global) tile t (all of them when the parity tap is on)
     auto tile_mask = [&](int tx, int ty, int t) -> int {
-        const int mt = (tx + 127) >> 7;
+        const int mt = CL ? (min(tx, xlo + xs) - xlo + 127) >> 7 : (tx + 127) >> 7;
         if (a.lp_out) return (1 << mt) - 1;
         const int lo = max(0, tx + t * kTileY - ty), hi = min(tx - 1, t * kTileY + kTileY - 1);
         int m = 0;
         for (int i = 0; i < mt; ++i)
-            if (128 * i <= hi && 128 * i + 127 >= lo) m |= 1 << i;
+            if (xlo + 128 * i <= hi && xlo + 128 * i + 127 >= lo) m |= 1 << i;
         return m;
     };
+    // cluster mode: boundary ring and hand-over slots (kTcClBytes at off_cl)
+    unsigned char *clb = smem + L.off_cl;
+    uint64_t *x_in_full = reinterpret_cast<uint64_t *>(clb + 1024), *x_out_empty = x_in_full + kXRing;
+    uint64_t *bt_full = x_out_empty + kXRing;
+    int *bt_in = reinterpret_cast<int *>(bt_full + 4);
+    if constexpr (CL) {
+        if (tid == 0) {
+            for (int s = 0; s < kXRing; ++s) {
+                mbar_init(&x_in_full[s], 1);
+                mbar_init(&x_out_empty[s], 1);
+            }
+            for (int s = 0; s < 4; ++s) mbar_init(&bt_full[s], 1);
+            mbar_fence_init();
+        }
+        __syncwarp();
+        cluster_sync_all();   // every CTA's barriers exist before anybody arrives on them remotely
+    }
     volatile int *zdone = ctrl, *fwd_done = ctrl + 1, *bt_done = ctrl + 2, *fwd_done2 = ctrl + 3;
     const bool son = a.stats != nullptr;
     long long *so = son ? a.stats + (size_t)blockIdx.x * 32 : nullptr;
@@ -295,22 +348,46 @@ __global__ void __launch_bounds__(kTcThreads, 1) mas_prior_tc_kernel(const Prior
         int g = 0, k = 0;
         TcStat s_all(son);
         long long dp_wait = 0;
+        ChainCtx cx{};
+        if constexpr (CL) {
+            cx.in_ring = smem_u32(clb);
+            cx.in_full = x_in_full;
+            cx.out_empty = x_out_empty;
+            cx.left_empty = map_to_cta(smem_u32(x_out_empty), (uint32_t)max(crank - 1, 0));
+            cx.right_ring = map_to_cta(smem_u32(clb), (uint32_t)min(crank + 1, CS - 1));
+            cx.right_full = map_to_cta(smem_u32(x_in_full), (uint32_t)min(crank + 1, CS - 1));
+        }
         s_all.begin();
-        for (int u = blockIdx.x; u < a.B; u += gridDim.x, ++k) {
-            int tx, ty, ntiles;
+        for (int u = cid; u < a.B; u += ncl, ++k) {
+            int tx, ty, ntiles, t_lo;
             bool degenerate;
-            geometry(u, tx, ty, ntiles, degenerate);
+            geometry(u, tx, ty, ntiles, degenerate, t_lo);
             if (ntiles > 0) {
+                // cluster mode: the direction words live in the workspace (one region per utterance), the wait
+                // only bounds how far the forward passes run ahead of the backtrack hand-overs (4 slots)
                 while (*bt_done < k - bslots + 1) __nanosleep(32);
                 __threadfence_block();
                 int owns = 0;
-                const float score = prior_forward2_dispatch<XPLMAX, true>(ring, bits_of(k), L.xrows, tx, ty, lane, w, g,
-                                                                    edge, edge_full, &owns,
-                                                                    son ? &dp_wait : nullptr);
+                float score;
+                if constexpr (CL) {
+                    const int nt = (ty + kTileY - 1) / kTileY;
+                    // warp 0: last tile the left CTA publishes a boundary for; warp 1: first tile the right CTA wants
+                    const int in_last = (w == 0 && crank > 0) ? min(nt - 1, (xlo - 1 - tx + ty) >> 5) : t_lo - 2;
+                    const int out_first = (w == 1 && crank < CS - 1 && tx > xlo + xs) ? ((xlo + xs) >> 5) - 1 : (1 << 30);
+                    uint32_t *gbits = a.bits_ws + (size_t)u * L.nch * L.xr_tot + xlo;
+                    score = chain_forward_dispatch<XPLMAX, true>(ring, gbits, L.xr_tot, tx, ty, min(tx, xlo + xs) - xlo,
+                                                                 lane, w, g, edge, edge_full, xlo, t_lo, ntiles, in_last,
+                                                                 out_first, cx, &owns);
+                } else {
+                    score = prior_forward2_dispatch<XPLMAX, true>(ring, bits_of(k), L.xrows, tx, ty, lane, w, g,
+                                                                  edge, edge_full, &owns,
+                                                                  son ? &dp_wait : nullptr);
+                }
                 g += ntiles;
                 if (owns && lane == 0 && a.score) a.score[u] = score;
             }
-            __threadfence_block();
+            if constexpr (CL) __threadfence();   // direction words in the workspace: read back through L2 (ld.cg)
+            else __threadfence_block();
             __syncwarp();
             if (lane == 0) *(w == 0 ? fwd_done : fwd_done2) = k + 1;
         }
@@ -319,16 +396,68 @@ __global__ void __launch_bounds__(kTcThreads, 1) mas_prior_tc_kernel(const Prior
         if (son && lane == 0 && w == 1) { so[26] = s_all.acc; so[27] = dp_wait; }
     } else if (warp == kTcBack) {
         // ======================= backtrack warp =======================
-        int k = 0;
-        for (int u = blockIdx.x; u < a.B; u += gridDim.x, ++k) {
-            int tx, ty, ntiles;
+        int k = 0, n_bt_in = 0, n_bt_out = 0;
+        const uint32_t left_bt_in = CL ? map_to_cta(smem_u32(bt_in), (uint32_t)max(crank - 1, 0)) : 0u;
+        const uint32_t left_bt_full = CL ? map_to_cta(smem_u32(bt_full), (uint32_t)max(crank - 1, 0)) : 0u;
+        // cluster mode: this CTA's rows of the outputs
+        const int x_beg = CL ? min(xlo, T_x) : 0, x_end = CL ? min(xlo + xs, T_x) : T_x;
+        for (int u = cid; u < a.B; u += ncl, ++k) {
+            int tx, ty, ntiles, t_lo;
             bool degenerate;
-            geometry(u, tx, ty, ntiles, degenerate);
+            geometry(u, tx, ty, ntiles, degenerate, t_lo);
+            char *pb = a.path ? static_cast<char *>(a.path) + (int64_t)u * T_x * T_y * a.path_esize : nullptr;
+            if constexpr (CL) {
+                // Cluster mode: THIS warp clears the CTA's rows of the dense path (bulk stores), while the forward
+                // pass of the utterance runs -- it has nothing else to do until then, and an utterance of 512 x 4096
+                // is 8 MB of zeros: issued by a loader it would stall the tile pipeline for ~40 tiles.
+                if (pb && x_end > x_beg) {
+                    char *zb = pb + (int64_t)x_beg * T_y * a.path_esize;
+                    const int64_t zbytes = (int64_t)(x_end - x_beg) * T_y * a.path_esize;
+                    if (bulk_zero_ok(zb, zbytes)) {
+                        zero_fill_bulk_part(zb, zbytes, 0, 1, zbuf, kTcZeroBytes, lane, 32);
+                        bulk_commit();
+                    } else {
+                        zero_fill_part(zb, zbytes, 0, 1, lane, 32);
+                    }
+                }
+            }
             for (int x = lane; x < T_x; x += 32) dur[x] = 0;
             while (*fwd_done <= k || *fwd_done2 <= k) __nanosleep(32);
             __threadfence_block();
             __syncwarp();
-            if (ntiles > 0) {
+            if constexpr (CL) {
+                if (ntiles > 0) {
+                    // the CTA that owns token t_x - 1 starts; every other one takes over where its right
+                    // neighbour left its tokens (frame handed over through distributed shared memory)
+                    int y = ty - 1;
+                    if (tx > xlo + xs) {
+                        const int slot = n_bt_in & 3;
+                        mbar_wait_cluster(&bt_full[slot], (uint32_t)(n_bt_in >> 2) & 1u, 64);
+                        y = bt_in[slot];
+                        ++n_bt_in;
+                    }
+                    const uint32_t *gbits = a.bits_ws + (size_t)u * L.nch * L.xr_tot + xlo;
+                    const int yl = backtrack_bits_window(gbits, L.xr_tot, min(tx, xlo + xs) - xlo, xlo,
+                                                         min(tx, xlo + xs) - 1, y, first, dur, lane);
+                    if (crank > 0 && lane == 0) {
+                        const int slot = n_bt_out & 3;
+                        st_cluster_u32(left_bt_in + 4u * slot, (uint32_t)yl);
+                        mbar_arrive_cluster(left_bt_full + 8u * slot);
+                    }
+                    if (crank > 0) ++n_bt_out;
+                } else if (degenerate) {
+                    // t_x > t_y (rare): every CTA walks the whole utterance and keeps its own rows
+                    if (lane == 0) {
+                        const float *mub = a.mu_x + (int64_t)u * F * T_x;
+                        const float *yb = a.y + (int64_t)u * F * T_y;
+                        auto val = [&](int x, int y) { return lp_cell(mub, yb, F, T_x, T_y, x, y, cst); };
+                        backtrack_degenerate(val, tx, ty, first, dur);
+                        if (a.score && crank == 0) a.score[u] = val(tx - 1, ty - 1);
+                    }
+                } else if (lane == 0 && a.score && crank == 0 && !(tx >= 1 && ty >= 1)) {
+                    a.score[u] = 0.0f;
+                }
+            } else if (ntiles > 0) {
                 if (lane == 0) backtrack_bits(bits_of(k), L.xrows, tx, ty, first, dur, true, 6);
             } else if (degenerate) {
                 if (lane == 0) {  // reference semantics for t_x > t_y: raw prior values (mas_dp.cuh)
@@ -344,11 +473,48 @@ __global__ void __launch_bounds__(kTcThreads, 1) mas_prior_tc_kernel(const Prior
             __threadfence_block();
             __syncwarp();
             if (lane == 0) *bt_done = k + 1;
-            if (a.path) {
+            if constexpr (CL) {
+                bulk_wait_all();          // my zeros are in memory before my 1-cells
+                __syncwarp();
+            } else if (a.path) {
                 while (*zdone <= k) __nanosleep(64);
                 __threadfence_block();
             }
-            char *pb = a.path ? static_cast<char *>(a.path) + (int64_t)u * T_x * T_y * a.path_esize : nullptr;
+            if constexpr (CL) {
+                // rows [x_beg, x_end) only
+                for (int x = x_beg + lane; x < x_end; x += 32) {
+                    const int d = dur[x];
+                    if (a.durations) a.durations[(int64_t)u * T_x + x] = d;
+                    if (pb && d > 0) {
+                        const int64_t e0 = (int64_t)x * T_y + first[x];
+                        for (int kk = 0; kk < d; ++kk) st_one(pb, e0 + kk, a.path_esize, a.one);
+                    }
+                }
+                if (a.frame_idx) {
+                    int32_t *fi = a.frame_idx + (int64_t)u * T_y;
+                    if (crank == 0)
+                        for (int y = ty + lane; y < a.T_y; y += 32) fi[y] = -1;
+                    for (int x = x_beg + lane; x < x_end; x += 32) {
+                        const int d = dur[x], f0 = first[x];
+                        for (int kk = 0; kk < d; ++kk) fi[f0 + kk] = x;
+                    }
+                }
+                for (int p = 0; p < a.npeer; ++p) {
+                    int32_t *row = a.peer[p] + (a.peer_row0 + u) * a.peer_stride;
+                    for (int x = x_beg + lane; x < x_end; x += 32) row[x] = dur[x];
+                    if (a.peer_fi[p]) {
+                        int32_t *fi = a.peer_fi[p] + (a.peer_row0 + u) * a.peer_fi_stride;
+                        if (crank == 0)
+                            for (int y = ty + lane; y < a.T_y; y += 32) fi[y] = -1;
+                        for (int x = x_beg + lane; x < x_end; x += 32) {
+                            const int d = dur[x], f0 = first[x];
+                            for (int kk = 0; kk < d; ++kk) fi[f0 + kk] = x;
+                        }
+                    }
+                }
+                __syncwarp();
+                continue;
+            }
             write_path_ones(pb, a.durations ? a.durations + (int64_t)u * T_x : nullptr, first, dur, T_x, T_y,
                             a.path_esize, a.one, lane, 32);
             write_frame_idx(a.frame_idx ? a.frame_idx + (int64_t)u * T_y : nullptr, first, dur, T_x, ty, a.T_y,
@@ -434,10 +600,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) mas_prior_tc_kernel(const Prior
         // staging buffer: copy of its tile g in flight -> (at its next tile) transpose pass -> next copy.
         const int lp = (warp == kTcLoader) ? 0 : 1;
         int g = 0, pend = -1, k = 0;
-        for (int u = blockIdx.x; u < a.B; u += gridDim.x, ++k) {
-            int tx, ty, ntiles;
+        for (int u = cid; u < a.B; u += ncl, ++k) {
+            int tx, ty, ntiles, t_lo;
             bool degenerate;
-            geometry(u, tx, ty, ntiles, degenerate);
+            geometry(u, tx, ty, ntiles, degenerate, t_lo);
             const float *yb = a.y + (int64_t)u * F * T_y;
             char *pb = a.path ? static_cast<char *>(a.path) + (int64_t)u * T_x * T_y * a.path_esize : nullptr;
             const int64_t pbytes = a.path ? (int64_t)T_x * T_y * a.path_esize : 0;
@@ -450,7 +616,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mas_prior_tc_kernel(const Prior
                 if (g >= kTcSlabs) mbar_wait_relaxed(&slab_free[s], ((g / kTcSlabs) - 1) & 1);  // MMAs of tile g-kTcSlabs done
                 l_free.end();
                 float *dst = staging + (size_t)lp * Fp * kTileY;
-                const int y0 = t * kTileY;
+                const int y0 = (t_lo + t) * kTileY;
                 l_issue.begin();
                 if (vec16) {
                     const int left = ty - (y0 + 4 * c);
@@ -469,7 +635,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mas_prior_tc_kernel(const Prior
                 pend = g;
                 l_issue.end();
             }
-            if (lp == 0) {
+            if (!CL && lp == 0) {
                 // The even loader also clears the dense output path of the utterance: a burst of bulk (TMA)
                 // stores that holds it for ~25 k cycles.  It is issued AFTER the utterance's tiles: the
                 // pipeline then has ~9 tiles of this utterance buffered downstream to work through while the
@@ -507,17 +673,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) mas_prior_tc_kernel(const Prior
             int g = 0, ka = 0;
             TcStat m_all(son), m_a(son), m_s(son), m_d(son), m_i(son);
             m_all.begin();
-            for (int u = blockIdx.x; u < a.B; u += gridDim.x) {
-                int tx, ty, ntiles;
+            for (int u = cid; u < a.B; u += ncl) {
+                int tx, ty, ntiles, t_lo;
                 bool degenerate;
-                geometry(u, tx, ty, ntiles, degenerate);
+                geometry(u, tx, ty, ntiles, degenerate, t_lo);
                 if (ntiles == 0) continue;
                 // A operand readiness / release is tracked per M tile: the first ~4 tiles of an utterance
                 // only touch tokens < 128, and its last tiles only tokens >= 128, so the movers can
                 // refill one half of TMEM while the other is still (or already) being multiplied
                 bool a_ok[2] = {false, false}, a_rel[2] = {false, false};
                 // last tile whose band still reaches into M tile 0 (tokens < 128)
-                const int t0_last = a.lp_out ? ntiles - 1 : min(ntiles - 1, (127 - tx + ty) >> 5);   // tap: every tile
+                const int t0_last = a.lp_out ? ntiles - 1 : min(ntiles - 1, ((xlo + 127 - tx + ty) >> 5) - t_lo);   // tap: every tile
                 for (int t = 0; t < ntiles;) {
                     // a pair of tiles (g, g+1): up to four independent accumulators in flight
                     // (accumulator c = 2*e + i: tile e of the pair, M tile i); everything the issue
@@ -539,7 +705,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mas_prior_tc_kernel(const Prior
                         const uint32_t sb = smem_u32(slabs + (size_t)s * slab_floats);
                         bh[e] = tc_bdesc(sb);
                         bl[e] = tc_bdesc(sb + (uint32_t)part_floats * 4u);
-                        am |= tile_mask(tx, ty, t + e) << (2 * e);
+                        am |= tile_mask(tx, ty, t_lo + t + e) << (2 * e);
                         dcol[2 * e] = tbase + L.col_d + (b * 2) * 32;
                         dcol[2 * e + 1] = dcol[2 * e] + 32;
                     }
@@ -646,17 +812,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) mas_prior_tc_kernel(const Prior
         TcStat a_all(aon), a_ld(aon), a_w(aon), a_st(aon);
         a_all.begin();
         int ka = 0;
-        for (int u = blockIdx.x; u < a.B; u += gridDim.x) {
-            int tx, ty, ntiles;
+        for (int u = cid; u < a.B; u += ncl) {
+            int tx, ty, ntiles, t_lo;
             bool degenerate;
-            geometry(u, tx, ty, ntiles, degenerate);
+            geometry(u, tx, ty, ntiles, degenerate, t_lo);
             if (ntiles == 0) continue;
-            const int mt = (tx + 127) >> 7;
+            const int mt = CL ? (min(tx, xlo + xs) - xlo + 127) >> 7 : (tx + 127) >> 7;   // this CTA's M tiles
             const float *mub = a.mu_x + (int64_t)u * F * T_x;
             float *msq = musq + (ka % kTcMsq) * 256;
             for (int i = 0; i < 2; ++i) {
-                const bool any = i < mt && 128 * i + 32 * q < tx;   // some of this warp's tokens exist
-                const int x = 128 * i + 32 * q + lane;
+                const bool any = i < mt && xlo + 128 * i + 32 * q < tx;   // some of this warp's tokens exist
+                const int x = xlo + 128 * i + 32 * q + lane;
                 const bool xv = x < tx;
                 // every feature of "my" token into registers: all loads in flight at once, issued
                 // while the previous utterance is still being multiplied
@@ -690,7 +856,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mas_prior_tc_kernel(const Prior
                         tmem_st8(lane_base + L.col_ahi + i * Fp + f0, rh);
                         tmem_st8(lane_base + L.col_alo + i * Fp + f0, rl);
                     }
-                    msq[x] = -0.5f * s;   // tts.py:494  mu_square
+                    msq[x - xlo] = -0.5f * s;   // tts.py:494  mu_square
                 }
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 tc_fence_before();
@@ -710,16 +876,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) mas_prior_tc_kernel(const Prior
         const bool eon = son && q == 0;
         TcStat e_all(eon), e_df(eon), e_re(eon), e_w(eon);
         e_all.begin();
-        for (int u = blockIdx.x; u < a.B; u += gridDim.x) {
-            int tx, ty, ntiles;
+        for (int u = cid; u < a.B; u += ncl) {
+            int tx, ty, ntiles, t_lo;
             bool degenerate;
-            geometry(u, tx, ty, ntiles, degenerate);
+            geometry(u, tx, ty, ntiles, degenerate, t_lo);
             if (ntiles == 0) continue;
-            const RowMap rm(tx, 6);
+            const RowMap rm(CL ? min(tx, xlo + xs) - xlo : tx, 6);
             const float *msq = musq + (ka % kTcMsq) * 256;
             for (int t = 0; t < ntiles; ++t, ++g) {
                 const int b = g % NB, sidx = g % NS;
-                const int mask = tile_mask(tx, ty, t);
+                const int mask = tile_mask(tx, ty, t_lo + t);
                 e_df.begin();
                 mbar_wait_relaxed(&d_full[b], (g / NB) & 1, 32);
                 e_df.end();
@@ -729,7 +895,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mas_prior_tc_kernel(const Prior
                 bool have[2];
 #pragma unroll
                 for (int i = 0; i < 2; ++i) {
-                    have[i] = (mask >> i & 1) && (128 * i + 32 * q < tx);
+                    have[i] = (mask >> i & 1) && (xlo + 128 * i + 32 * q < tx);
                     if (have[i]) tmem_ld32(lane_base + L.col_d + (b * 2 + i) * 32, acc[i]);
                 }
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -763,14 +929,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) mas_prior_tc_kernel(const Prior
                 e_re.end();
                 e_w.begin();
                 float *tile = stages + (size_t)sidx * ring.stage_floats;
-                const int y0 = t * kTileY;
+                const int y0 = (t_lo + t) * kTileY;
 #pragma unroll
                 for (int i = 0; i < 2; ++i) {
                     if (!have[i]) continue;
-                    const int x = 128 * i + 32 * q + lane;
+                    const int x = xlo + 128 * i + 32 * q + lane;
                     if (x >= tx) continue;
-                    const float ms = msq[x];
-                    const int pr = rm.row(x);
+                    const float ms = msq[x - xlo];
+                    const int pr = rm.row(x - xlo);
                     MAS_CHECK(pr >= 0 && pr < L.xrows && sidx >= 0 && sidx < NS);
                     float *row = tile + (pr << 5);
 #pragma unroll
@@ -787,9 +953,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) mas_prior_tc_kernel(const Prior
                 if (a.lp_out) {   // parity tap (cold path): copy this warp's rows of the tile to HBM
                     __syncwarp();
                     for (int i = 0; i < 2; ++i) {
-                        const int x = 128 * i + 32 * q + lane;
+                        const int x = xlo + 128 * i + 32 * q + lane;
                         if (!have[i] || x >= tx) continue;
-                        const int pr = rm.row(x);
+                        const int pr = rm.row(x - xlo);
                         const float *row = tile + (pr << 5);
                         float *tap = a.lp_out + ((int64_t)u * T_x + x) * T_y + y0;
                         for (int e = 0; e < kTileY && y0 + e < ty; ++e) tap[e] = row[(((e >> 2) ^ (pr & 7)) << 2) + (e & 3)];
@@ -806,16 +972,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) mas_prior_tc_kernel(const Prior
     }
     tc_fence_before();
     __syncthreads();
+    if constexpr (CL) cluster_sync_all();   // nobody leaves while a neighbour may still arrive on its barriers
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tbase), "r"(kTcTmemCols));
 }
 
 cudaError_t launch_from_prior_tc(const PriorTcArgs &a, cudaStream_t st)
 {
-    const int xplmax = (a.T_x + 63) / 64;   // tokens per lane of the two DP warps
+    const int cs = a.lay.cluster;
+    const int xplmax = ((cs > 1 ? a.lay.xs : a.T_x) + 63) / 64;   // tokens per lane of the two DP warps
     void (*k)(const PriorTcArgs) = nullptr;
-    if (xplmax <= 2) k = mas_prior_tc_kernel<2>;
-    else if (xplmax <= 3) k = mas_prior_tc_kernel<3>;
-    else k = mas_prior_tc_kernel<4>;
+    if (cs == 4) k = mas_prior_tc_kernel<2, 4>;
+    else if (cs == 2) k = mas_prior_tc_kernel<4, 2>;
+    else if (xplmax <= 2) k = mas_prior_tc_kernel<2, 1>;
+    else if (xplmax <= 3) k = mas_prior_tc_kernel<3, 1>;
+    else k = mas_prior_tc_kernel<4, 1>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a.lay.total);
     if (e != cudaSuccess) return e;
     if (a.lp_out) {
@@ -834,6 +1004,33 @@ cudaError_t launch_from_prior_tc(const PriorTcArgs &a, cudaStream_t st)
     // never more CTAs than SMs: measured at B=1024, 256..512 CTAs of 2..4 utterances cost 12-30 % (0.37-0.44 ms
     // against 0.333) -- CTA start-up and the loss of the lock-step between the SMs' write bursts
     if (a.utt_per_cta > 1) grid = std::min(grid, std::max(1, (a.B + a.utt_per_cta - 1) / a.utt_per_cta));
+    if (cs > 1) {
+        // one cluster per utterance in flight: as many clusters as the device can hold at once (the GPC
+        // structure decides: not every SM can be part of a 4-cluster), each running its utterances back to back
+        cudaLaunchConfig_t cfg{};
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)cs;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.blockDim = dim3(kTcThreads);
+        cfg.dynamicSmemBytes = a.lay.total;
+        cfg.stream = st;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        cfg.gridDim = dim3((unsigned)cs);
+        int ncl = 0;
+        e = cudaOccupancyMaxActiveClusters(&ncl, k, &cfg);
+        if (e != cudaSuccess) return e;
+        if (ncl < 1) return cudaErrorLaunchOutOfResources;
+        ncl = std::min(ncl, std::max(1, (sm_count() - sm_reserve()) / cs));
+        ncl = std::min(ncl, a.B);
+        if (a.utt_per_cta > 1) ncl = std::min(ncl, std::max(1, (a.B + a.utt_per_cta - 1) / a.utt_per_cta));
+        cfg.gridDim = dim3((unsigned)(ncl * cs));
+        e = cudaLaunchKernelEx(&cfg, k, a);
+        count_launch();
+        return e != cudaSuccess ? e : cudaGetLastError();
+    }
     k<<<grid, kTcThreads, a.lay.total, st>>>(a);
     count_launch();
     return cudaGetLastError();

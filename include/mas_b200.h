@@ -69,6 +69,10 @@ enum {
 };
 #define MAS_FLAG_TMA (1 << 16) /* mas_maximum_path: stage tiles with TMA tensor loads (cp.async.bulk.tensor.2d) instead of
                                   per-thread cp.async; fp32 value, rows 16-byte aligned, T_x <= 256; same results */
+/* mas_from_prior_f32, 256 < T_x <= 512 (one thread-block cluster per utterance, the token axis split over its CTAs,
+ * the recurrence crossing CTAs through distributed shared memory): clusters of 2 CTAs x 256 tokens instead of the
+ * default 4 CTAs x 128 tokens.  Same results. */
+#define MAS_FLAG_CLUSTER2 (1 << 17)
 /* mas_from_prior_f32 (tensor-core engine): run at least k (1..255) utterances per persistent CTA, i.e. at
  * most ceil(B / k) CTAs.  For callers that keep several launches in flight (batch-sharded steps on several
  * streams): throughput instead of the latency of one call.  Bits 8..15 of `flags`. */

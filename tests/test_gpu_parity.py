@@ -449,17 +449,94 @@ def test_fused_engines_agree_at_b1024(cuda):
 
 
 def test_fused_unfused_plan_for_long_text(cuda):
-    """T_x=512 at F=80: mu_x does not fit beside the ring -> prior to HBM once, then drop-in."""
+    """T_x=512 at F=80 on the CUDA-core engine: mu_x does not fit beside the ring -> prior to HBM once, then
+    drop-in (the tensor-core engine runs this shape on a cluster of CTAs, see below)."""
+    from art_tts_b200 import _lib
     rng = np.random.default_rng(6)
     B, F, T_x, T_y = 2, 80, 512, 1200
+    assert _lib.load().mas_from_prior_plan(B, F, T_x, T_y, ENGINES["cuda_core"]) == 1
+    assert _lib.load().mas_from_prior_plan(B, F, T_x, T_y, 0) == 0
     mu_x = rng.standard_normal((B, F, T_x)).astype(np.float32)
     y = rng.standard_normal((B, F, T_y)).astype(np.float32)
     x_len = np.array([512, 300], np.int32)
     y_len = np.array([1200, 1000], np.int32)
     mask = rect_mask(x_len, y_len, T_x, T_y)
-    path, dur, lp = fused(mu_x, y, x_len, y_len, cuda, return_log_prior=True)
+    path, dur, lp = fused(mu_x, y, x_len, y_len, cuda, return_log_prior=True, flags=ENGINES["cuda_core"])
     self_path = oracle.maximum_path(lp.cpu().numpy(), mask, n_threads=2)
     assert np.array_equal(path.cpu().numpy(), self_path)
+
+
+CLUSTERS = {"cluster4": 0, "cluster2": 1 << 17}
+
+
+@pytest.mark.parametrize("cl", list(CLUSTERS))
+@pytest.mark.parametrize("T_x", [257, 300, 384, 385, 449, 512])
+def test_fused_cluster_token_axis_edges(cuda, T_x, cl):
+    """256 < T_x <= 512: one thread-block cluster per utterance, the token axis split over its CTAs (4 x 128
+    or 2 x 256 tokens), the recurrence and the backtrack crossing CTAs through distributed shared memory.
+    Utterances that end in every CTA of the cluster, t_x == t_y, empty and degenerate ones in one batch."""
+    rng = np.random.default_rng(500 + T_x)
+    F = 24
+    T_y = 3 * T_x // 2 + 37
+    x_len = np.array([T_x, T_x - 1, 128, 129, 256, min(T_x, 257), 1, 200, 0, T_x, 60, max(1, T_x - 130)], np.int32)
+    y_len = np.array([T_y, T_y - 7, 128, T_y, 300, T_y - 1, 33, T_y, 50, T_x - 5, 61, T_y - 64], np.int32)
+    B = len(x_len)
+    mu_x = rng.standard_normal((B, F, T_x)).astype(np.float32)
+    y = rng.standard_normal((B, F, T_y)).astype(np.float32)
+    mask = rect_mask(x_len, y_len, T_x, T_y)
+    from art_tts_b200 import _lib
+    assert _lib.load().mas_from_prior_plan(B, F, T_x, T_y, ENGINES["tensor_core"] | CLUSTERS[cl]) == 0
+    path, dur, score, fidx, lp = fused(mu_x, y, x_len, y_len, cuda, return_score=True,
+                                       return_frame_idx=True, return_log_prior=True,
+                                       flags=ENGINES["tensor_core"] | CLUSTERS[cl])
+    lp_np = lp.cpu().numpy()
+    ref_lp = oracle.log_prior(mu_x, y, method="c")
+    m = mask.astype(bool)
+    assert np.allclose(lp_np[m], ref_lp[m], rtol=1e-5, atol=1e-4)
+    # the degenerate utterance (t_x > t_y) is decided by raw values computed with the CUDA-core formula
+    lp_for_oracle = lp_np.copy()
+    lp_for_oracle[9] = ref_lp[9]
+    want = oracle.maximum_path(lp_for_oracle, mask, n_threads=8)
+    assert np.array_equal(path.cpu().numpy(), want)
+    assert np.array_equal(dur.cpu().numpy(), want.sum(-1).astype(np.int32))
+    fi = fidx.cpu().numpy()
+    for b in range(B):
+        if 1 <= x_len[b] <= y_len[b]:
+            assert np.array_equal(fi[b, :y_len[b]], want[b].argmax(0)[:y_len[b]]), b
+            assert (fi[b, y_len[b]:] == -1).all(), b
+    ok = (x_len >= 1) & (x_len <= y_len)
+    ll = (lp_np.astype(np.float64) * want).sum((1, 2))
+    assert np.allclose(score.cpu().numpy()[ok], ll[ok], rtol=1e-4)
+    # without the tap (band-only production of the prior) nothing changes; nor with several utterances per cluster
+    for fl in (0, 3 << 8):
+        p2, d2 = fused(mu_x, y, x_len, y_len, cuda, flags=ENGINES["tensor_core"] | CLUSTERS[cl] | fl)
+        assert torch.equal(p2, path) and torch.equal(d2, dur), fl
+
+
+@pytest.mark.parametrize("cl", list(CLUSTERS))
+def test_config4_fused_on_clusters(cuda, cl):
+    """BASELINE config 4 (T_text=512, T_mel=4096, F=80) through the fused entry: the prior is never written to
+    HBM (plan 0), direction words go through the workspace, result equal to the oracle on the kernel's own prior."""
+    from art_tts_b200 import _lib
+    rng = np.random.default_rng(44)
+    B, F, T_x, T_y = 6, 80, 512, 4096
+    assert _lib.load().mas_from_prior_plan(32, F, T_x, T_y, 0) == 0
+    x_len = np.array([512, 512, 400, 511, 130, 300], np.int32)
+    y_len = np.array([4096, 3000, 4096, 2047, 4001, 1111], np.int32)
+    mu_x = rng.standard_normal((B, F, T_x)).astype(np.float32)
+    y = rng.standard_normal((B, F, T_y)).astype(np.float32)
+    mask = rect_mask(x_len, y_len, T_x, T_y)
+    path, dur, lp = fused(mu_x, y, x_len, y_len, cuda, return_log_prior=True, flags=CLUSTERS[cl])
+    lp_np = lp.cpu().numpy()
+    ref_lp = oracle.log_prior(mu_x, y, method="c")
+    m = mask.astype(bool)
+    assert np.allclose(lp_np[m], ref_lp[m], rtol=1e-5, atol=1e-4)
+    want = oracle.maximum_path(lp_np, mask, n_threads=8)
+    assert np.array_equal(path.cpu().numpy(), want)
+    assert np.array_equal(dur.cpu().numpy(), want.sum(-1).astype(np.int32))
+    p2, d2 = fused(mu_x, y, x_len, y_len, cuda, flags=CLUSTERS[cl])
+    assert torch.equal(p2, path) and torch.equal(d2, dur)
+    check_path_invariants(path, dur, x_len, y_len)
 
 
 @pytest.mark.parametrize("chunk,trim", [(0, True), (5, True), (64, False)])
