@@ -63,7 +63,7 @@ static int env_int(const char *name, int dflt)
 // the library, so that plan queries (mas_plan, mas_from_prior_plan, mas_peer_durations_supported)
 // and the launches that follow can never disagree.
 struct Tuning {
-    int prior_tc, prior_tc_min_f, stages, dp2_min_tx, prior_spill, prior_stats, fma_per_smsp, extra_fma, fast3, fast_tma, tc_cluster;
+    int prior_tc, prior_tc_min_f, stages, dp2_min_tx, dp2_min_tx_one_wave, prior_spill, prior_stats, fma_per_smsp, extra_fma, fast3, fast_tma, tc_cluster;
 };
 static const Tuning &tuning()
 {
@@ -73,6 +73,7 @@ static const Tuning &tuning()
         v.prior_tc_min_f = env_int("MAS_PRIOR_TC_MIN_F", 32);
         v.stages = env_int("MAS_STAGES", 0);
         v.dp2_min_tx = env_int("MAS_DP2_MIN_TX", 256);
+        v.dp2_min_tx_one_wave = env_int("MAS_DP2_MIN_TX_ONE_WAVE", 64);
         v.prior_spill = env_int("MAS_PRIOR_SPILL", 0);
         v.prior_stats = env_int("MAS_PRIOR_STATS", 0);
         v.fma_per_smsp = env_int("MAS_PRIOR_FMA_PER_SMSP", 2);
@@ -89,7 +90,8 @@ static const Tuning &tuning()
 
 // Shared-memory carve-up of the fast kernels and the plan that follows from it.
 // `extra_smem` = bytes the caller needs besides ring + bits (the fused kernel's operands).
-Plan choose_plan(int T_x, int T_y, int flags, FastLayout *lay, size_t extra_smem, int max_stages, int row_align)
+Plan choose_plan(int T_x, int T_y, int flags, FastLayout *lay, size_t extra_smem, int max_stages, int row_align,
+                 bool one_wave)
 {
     FastLayout L{};
     L.xrows = ((T_x + row_align - 1) / row_align) * row_align;
@@ -114,7 +116,7 @@ Plan choose_plan(int T_x, int T_y, int flags, FastLayout *lay, size_t extra_smem
         const int forced = tuning().stages;
         auto occ = [&](int s) { return (int)((size_t)(kSmemBudget + 1024) / (total(s, fits) + 1024)); };
         for (int s = 3; s <= max_stages; ++s)
-            if (total(s, fits) <= (size_t)kSmemBudget && (occ(s) >= occ(2) || occ(s) >= 3)) S = s;
+            if (total(s, fits) <= (size_t)kSmemBudget && (one_wave || occ(s) >= occ(2) || occ(s) >= 3)) S = s;
         if (forced >= 2 && forced <= (extra_smem ? max_stages : 6) &&
             total(forced, fits) <= (size_t)kSmemBudget)
             S = forced;
@@ -240,20 +242,22 @@ size_t mas_workspace_bytes(int B, int T_x, int T_y)
     return bits_workspace_bytes(B, T_x, T_y) + 256;
 }
 
-static Plan plan_fast(int T_x, int T_y, int flags, MasArgs *a);
+static Plan plan_fast(int B, int T_x, int T_y, int flags, MasArgs *a);
 
 int mas_plan(int B, int T_x, int T_y, int flags)
 {
     (void)B;
     if (T_x < 1 || T_y < 1) return MAS_ERR_SHAPE;
     MasArgs a{};
-    return (int)plan_fast(T_x, T_y, flags, &a);
+    return (int)plan_fast(B, T_x, T_y, flags, &a);
 }
 
 // Layout + DP-warp count of the drop-in kernel.  Long token axis (config 4: 512 x 4096): the
 // frame-sequential recurrence is the whole run time, so two DP warps split the tokens (mas_dp.cuh
 // dp_forward2); that needs a third ring stage and 64-row alignment of the tiles.
-static Plan plan_fast(int T_x, int T_y, int flags, MasArgs *a)
+// A batch that fits the SMs in one wave (B <= SM count: BASELINE configs 1-3) is bound by the latency of ONE
+// utterance's recurrence, not by HBM or occupancy: two DP warps from 64 tokens on.
+static Plan plan_fast(int B, int T_x, int T_y, int flags, MasArgs *a)
 {
     a->skewed = 0;
     if ((tuning().fast3 || (flags & MAS_FLAG_SKEWED_DP)) &&
@@ -265,9 +269,10 @@ static Plan plan_fast(int T_x, int T_y, int flags, MasArgs *a)
     }
     Plan plan = choose_plan(T_x, T_y, flags, &a->lay);
     a->dp_warps = 1;
-    if (plan != kPlanGeneral && T_x > tuning().dp2_min_tx) {
+    const bool one_wave = B >= 1 && B <= sm_count() && !(flags & (MAS_FLAG_ONE_DP_WARP | MAS_FLAG_TMA));
+    if (plan != kPlanGeneral && (T_x > tuning().dp2_min_tx || (one_wave && T_x > tuning().dp2_min_tx_one_wave))) {
         FastLayout l2;
-        const Plan p2 = choose_plan(T_x, T_y, flags, &l2, 512, 3, 64);
+        const Plan p2 = choose_plan(T_x, T_y, flags, &l2, 512, 3, 64, one_wave);
         if (p2 != kPlanGeneral && l2.nstages >= 3) {
             a->lay = l2;
             plan = p2;
@@ -329,7 +334,7 @@ int mas_maximum_path(const void *value, int value_dtype, const float *cell_mask,
     if (B == 0) return MAS_OK;
 
     MasArgs a{};
-    const Plan plan = plan_fast(T_x, T_y, flags, &a);
+    const Plan plan = plan_fast(B, T_x, T_y, flags, &a);
     if (plan != kPlanFastSmemBits) {
         if (!workspace || workspace_bytes < mas_workspace_bytes(B, T_x, T_y)) return MAS_ERR_WORKSPACE;
         if ((uintptr_t)workspace % 16) return MAS_ERR_ALIGN;
@@ -350,7 +355,8 @@ int mas_maximum_path(const void *value, int value_dtype, const float *cell_mask,
     a.one = one_pattern(path_dtype);
     a.load_mode = 0;
     if (value_dtype == MAS_F32 && !cell_mask && !(flags & MAS_FLAG_NO_ASYNC))
-        a.load_mode = (T_y % 4 == 0 && (uintptr_t)value % 16 == 0) ? 2 : 1;
+        a.load_mode = (T_y % 4 == 0 && (uintptr_t)value % 16 == 0) ? 2
+                      : (T_y % 2 == 0 && (uintptr_t)value % 8 == 0 && !a.skewed) ? 4 : 1;
     // TMA tensor loads for the single-DP-warp kernel (same conditions as the 16-byte cp.async path)
     TensorMap tmap{};
     if (a.load_mode == 2 && plan != kPlanGeneral && !a.skewed && a.dp_warps == 1 && a.lay.srows >= a.lay.xrows + kTmaBoxRows &&
@@ -473,7 +479,7 @@ int from_prior_impl(const float *mu_x, const float *logs, const float *y, const 
     if (!fused) {
         // operands do not fit next to the tile ring: prior to HBM once, then the drop-in kernel
         MasArgs m{};
-        const Plan p2 = plan_fast(T_x, T_y, flags, &m);
+        const Plan p2 = plan_fast(B, T_x, T_y, flags, &m);
         if (p2 == kPlanGeneral && (size_t)T_x * 16 > (size_t)kSmemBudget) return MAS_ERR_SHAPE;
         m.value = log_prior_out;
         m.t_x = t_x;
@@ -488,7 +494,8 @@ int from_prior_impl(const float *mu_x, const float *logs, const float *y, const 
         m.T_y = T_y;
         m.path_esize = path ? esize : 4;
         m.one = one_pattern(path_dtype);
-        m.load_mode = (T_y % 4 == 0 && (uintptr_t)log_prior_out % 16 == 0) ? 2 : 1;
+        m.load_mode = (T_y % 4 == 0 && (uintptr_t)log_prior_out % 16 == 0) ? 2
+                      : (T_y % 2 == 0 && (uintptr_t)log_prior_out % 8 == 0 && !m.skewed) ? 4 : 1;
         return (int)((p2 == kPlanGeneral) ? launch_general(m, MAS_F32, st)
                      : m.skewed           ? launch_fast3(m, MAS_F32, st)
                                           : launch_fast(m, MAS_F32, st));

@@ -164,6 +164,12 @@ __device__ __forceinline__ void cp_async4(void *dst_smem, const void *src, uint3
                  "r"(bytes)
                  : "memory");
 }
+__device__ __forceinline__ void cp_async8(void *dst_smem, const void *src, uint32_t bytes)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(smem_u32(dst_smem)), "l"(src),
+                 "r"(bytes)
+                 : "memory");
+}
 __device__ __forceinline__ void cp_async16(void *dst_smem, const void *src, uint32_t bytes)
 {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst_smem)), "l"(src),

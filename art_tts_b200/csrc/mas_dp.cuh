@@ -563,7 +563,7 @@ struct ChainCtx {
     int n_in, n_out;        // boundary tiles received / sent so far (CTA lifetime)
 };
 
-template <int XPL, bool DIAG, bool FULL, bool FMAX>
+template <int XPL, bool DIAG, bool FULL, bool FMAX, bool OUT_LOCAL>
 __device__ __forceinline__ void dp_tile_chain(float (&V)[XPL], uint32_t (&acc)[XPL], float &left,
                                               const float *__restrict__ stage, uint32_t in_addr, uint32_t out_addr,
                                               int L, int lane, int x0, int y0, int nsteps)
@@ -599,7 +599,14 @@ __device__ __forceinline__ void dp_tile_chain(float (&V)[XPL], uint32_t (&acc)[X
             for (int j = 0; j < XPL; ++j) v[j] = f4_get<3>(vv[j]);
             out.w = dp_step2<XPL, DIAG, FMAX>(V, acc, v, left, lane, x0, y0 + s0 + 3, 8u << s0, ev.w);
         }
-        if (out_addr && lane == 31) st_cluster_f4(out_addr + (g << 4), out.x, out.y, out.z, out.w);
+        if (out_addr && lane == 31) {
+            if (OUT_LOCAL)   // the boundary stays in this CTA (warp 0 -> warp 1)
+                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(out_addr + (g << 4)), "f"(out.x), "f"(out.y),
+                             "f"(out.z), "f"(out.w)
+                             : "memory");
+            else
+                st_cluster_f4(out_addr + (g << 4), out.x, out.y, out.z, out.w);
+        }
     }
 }
 
@@ -611,7 +618,7 @@ template <int XPL, bool FMAX = false>
 __device__ __noinline__ float dp_forward_chain(const TileRing ring, uint32_t *bits, int bstride, int tx, int ty,
                                                int lane, int w, int g0, float *edge, uint64_t *edge_full,
                                                int xlo, int t_lo, int ntiles, int in_last, int out_first,
-                                               ChainCtx &cx, int *owns)
+                                               ChainCtx &cx, int *owns, long long *wacc = nullptr)
 {
     float V[XPL];
     uint32_t acc[XPL];
@@ -638,7 +645,10 @@ __device__ __noinline__ float dp_forward_chain(const TileRing ring, uint32_t *bi
     uint32_t phase = (uint32_t)(g0 / ring.nstages) & 1u;
     for (int t = 0; t < ntiles; ++t) {
         const int gt = g0 + t, tt = t_lo + t;
+        long long c0 = 0, c1 = 0;
+        if (wacc) c0 = clock64();
         mbar_wait(&ring.full[stage], phase);
+        if (wacc) c1 = clock64();
         uint32_t in_addr = 0u, out_addr = 0u;
         int in_slot = -1, out_slot = -1;
         if (w == 1) {
@@ -660,15 +670,28 @@ __device__ __noinline__ float dp_forward_chain(const TileRing ring, uint32_t *bi
                 ++cx.n_in;
             }
         }
+        if (wacc) {   // profiling aid: starved of tiles / waiting for a boundary (neighbour warp or CTA)
+            wacc[0] += c1 - c0;
+            wacc[1] += clock64() - c1;
+        }
         const float *tile = ring.stages + stage * ring.stage_floats;
         const int y0 = tt * kTileY;
         const int nsteps = min(kTileY, ty - y0);
         const bool diag = y0 < tx;  // some token x > y may still exist in this tile
-        if (nsteps == kTileY) {
-            if (diag) dp_tile_chain<XPL, true, true, FMAX>(V, acc, left, tile, in_addr, out_addr, L, lane, x0, y0, nsteps);
-            else dp_tile_chain<XPL, false, true, FMAX>(V, acc, left, tile, in_addr, out_addr, L, lane, x0, y0, nsteps);
+        if (w == 0) {
+            if (nsteps == kTileY) {
+                if (diag) dp_tile_chain<XPL, true, true, FMAX, true>(V, acc, left, tile, in_addr, out_addr, L, lane, x0, y0, nsteps);
+                else dp_tile_chain<XPL, false, true, FMAX, true>(V, acc, left, tile, in_addr, out_addr, L, lane, x0, y0, nsteps);
+            } else {
+                dp_tile_chain<XPL, true, false, FMAX, true>(V, acc, left, tile, in_addr, out_addr, L, lane, x0, y0, nsteps);
+            }
         } else {
-            dp_tile_chain<XPL, true, false, FMAX>(V, acc, left, tile, in_addr, out_addr, L, lane, x0, y0, nsteps);
+            if (nsteps == kTileY) {
+                if (diag) dp_tile_chain<XPL, true, true, FMAX, false>(V, acc, left, tile, in_addr, out_addr, L, lane, x0, y0, nsteps);
+                else dp_tile_chain<XPL, false, true, FMAX, false>(V, acc, left, tile, in_addr, out_addr, L, lane, x0, y0, nsteps);
+            } else {
+                dp_tile_chain<XPL, true, false, FMAX, false>(V, acc, left, tile, in_addr, out_addr, L, lane, x0, y0, nsteps);
+            }
         }
         __syncwarp();
         if (lane == 0) {
@@ -711,14 +734,15 @@ template <int XPLMAX, bool FMAX = false>
 __device__ __forceinline__ float chain_forward_dispatch(const TileRing &ring, uint32_t *bits, int bstride, int tx,
                                                         int ty, int txl, int lane, int w, int g0, float *edge,
                                                         uint64_t *edge_full, int xlo, int t_lo, int ntiles,
-                                                        int in_last, int out_first, ChainCtx &cx, int *owns)
+                                                        int in_last, int out_first, ChainCtx &cx, int *owns,
+                                                        long long *wacc = nullptr)
 {
     const int xpl = (txl + 63) >> 6;
 #define MAS_CASEC(N)                                                                                              \
     case N:                                                                                                       \
         if constexpr (N <= XPLMAX)                                                                                \
             return dp_forward_chain<N, FMAX>(ring, bits, bstride, tx, ty, lane, w, g0, edge, edge_full, xlo, t_lo, \
-                                             ntiles, in_last, out_first, cx, owns);                               \
+                                             ntiles, in_last, out_first, cx, owns, wacc);                         \
         break;
     switch (xpl) {
         MAS_CASEC(1) MAS_CASEC(2) MAS_CASEC(3) MAS_CASEC(4)
@@ -730,38 +754,39 @@ __device__ __forceinline__ float chain_forward_dispatch(const TileRing &ring, ui
 }
 
 // Backtrack over direction words kept in GLOBAL memory, by a whole warp.  One dependent load per word from
-// L2 (~700 cycles) would dominate a long utterance, so the warp keeps a WINDOW in registers -- lane i holds
-// the words of token wx - i for the NC chunks wc, wc-1, .. -- loaded with all lanes' requests in flight at
-// once, and walks inside it with shuffles (every lane follows the same walk).  Tokens are the CTA's local
-// ones (global token idx = xlo + local), rows by RowMap(txl, 6).  Starts on token `idx` at frame `y`
-// (the last frame of that token); returns the last frame of token xlo - 1 when the walk leaves the CTA's
-// tokens downwards (the left CTA continues there), or -1 when it ended on token 0.
-template <int NC = 4>
+// L2 (~700 cycles) would dominate a long utterance, so the warp keeps a WINDOW of kBtWinC chunks x 32 tokens
+// in shared memory (`win`, 32 * kBtWinC words): the 32 lanes fetch it with cp.async, all requests in flight at
+// once (one L2 latency per window), and the walk then costs one broadcast LDS per step; every lane follows
+// the same walk.  Tokens are the CTA's local ones (global token idx = xlo + local), rows by RowMap(txl, 6).
+// Starts on token `idx` at frame `y` (the last frame of that token); returns the last frame of token
+// xlo - 1 when the walk leaves the CTA's tokens downwards (the left CTA continues there), or -1 when it
+// ended on token 0.
+constexpr int kBtWinC = 8;
 __device__ __forceinline__ int backtrack_bits_window(const uint32_t *bits, int bstride, int txl, int xlo, int idx,
-                                                     int y, int *first, int *dur, int lane)
+                                                     int y, int *first, int *dur, uint32_t *win, int lane)
 {
     const RowMap rm(txl, 6);
+    const uint32_t swin = smem_u32(win);
     int top = y, c = y >> 5;
     int wx = -1, wc = -1;
-    uint32_t W[NC];
-#pragma unroll
-    for (int n = 0; n < NC; ++n) W[n] = 0u;
     while (y >= 0 && idx != 0) {
         const int xl = idx - xlo;
-        if (wx < 0 || xl < wx - 31 || c < wc - (NC - 1)) {
+        if (wx < 0 || xl < wx - 31 || c < wc - (kBtWinC - 1)) {
+            __syncwarp();          // every lane is done reading the old window
             wx = xl;
             wc = c;
             const int mx = wx - lane;
             const int row = mx >= 0 ? rm.row(mx) : 0;
 #pragma unroll
-            for (int n = 0; n < NC; ++n)
-                W[n] = (mx >= 0 && wc - n >= 0) ? __ldcg(bits + (size_t)(wc - n) * bstride + row) : 0u;
+            for (int n = 0; n < kBtWinC; ++n) {
+                const bool ok = mx >= 0 && wc - n >= 0;
+                cp_async4(win + lane * kBtWinC + n, ok ? bits + (size_t)(wc - n) * bstride + row : bits, ok ? 4u : 0u);
+            }
+            asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+            __syncwarp();
         }
-        const int n = wc - c;
-        uint32_t mine = W[0];
-#pragma unroll
-        for (int q = 1; q < NC; ++q) mine = (n == q) ? W[q] : mine;
-        const uint32_t w = __shfl_sync(kFull, mine, wx - xl);
+        uint32_t w;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(swin + 4u * (uint32_t)((wx - xl) * kBtWinC + (wc - c))));
         const int s = y & 31;
         const uint32_t m = w & (0xffffffffu >> (31 - s));
         if (m == 0u) {  // stays on this token down to the chunk start

@@ -52,7 +52,8 @@ struct MasArgs {
     long long *stats;      // optional [B][16] phase cycle counters (profiles/microbench/fast3_phases.cu), else NULL
     int load_mode;         // fast kernel staging: 0 = LDG/STS (any dtype, cell mask), 1 = cp.async 4 B,
                            // 2 = cp.async 16 B (fp32, rows 16-byte aligned), 3 = TMA tensor boxes (same
-                           // conditions; mas_fast_kernel only; rows in natural token order)
+                           // conditions; mas_fast_kernel only; rows in natural token order),
+                           // 4 = cp.async 8 B (fp32, T_y even: rows 8-byte aligned)
     unsigned long long one;
     FastLayout lay;
 };
@@ -60,7 +61,7 @@ struct MasArgs {
 int element_size(int dtype);
 unsigned long long one_pattern(int dtype);
 Plan choose_plan(int T_x, int T_y, int flags, FastLayout *lay, size_t extra_smem = 0,
-                 int max_stages = 3, int row_align = 32);
+                 int max_stages = 3, int row_align = 32, bool one_wave = false);
 
 cudaError_t launch_lengths_from_mask(const void *mask, int mask_dtype, int B, int T_x, int T_y,
                                      int64_t sb, int64_t sx, int64_t sy, int32_t *t_x, int32_t *t_y,

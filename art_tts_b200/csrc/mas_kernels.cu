@@ -142,17 +142,27 @@ __device__ __forceinline__ void stage_value_tile(const InT *__restrict__ vb,
 
 // fp32, unmasked: the same band through cp.async -- nothing waits on a register, so a staging
 // thread can have every row of several tiles in flight (HBM latency is hidden by depth, not
-// by occupancy).  VEC16: rows are 16-byte aligned (T_y % 4 == 0), one request moves 4 frames.
-template <bool VEC16>
+// by occupancy).  VEC = frames per request: 4 when rows are 16-byte aligned (T_y % 4 == 0), 2 when they are
+// 8-byte aligned (T_y even: the reference's un-padded 870-frame batches), else 1.
+template <int VEC, int LSH = 5>
 __device__ __forceinline__ void stage_value_tile_async(const float *__restrict__ vb, float *stage,
                                                        int t, int tx, int ty, int64_t T_y, int hw,
                                                        int nhw, int lane)
 {
-    const RowMap rm(tx);
+    const RowMap rm(tx, LSH);
     const int y0 = t * kTileY;
     const int lo = max(0, tx + y0 - ty);
     const int hi = min(tx - 1, y0 + kTileY - 1);
-    if constexpr (VEC16) {
+    if constexpr (VEC == 2) {
+        const int c = lane & 15, r = lane >> 4;  // 8-byte chunk of the row, row within a group of 2
+        const int left = ty - (y0 + 2 * c);
+        const uint32_t bytes = left >= 2 ? 8u : (left > 0 ? 4u : 0u);
+        const int yo = bytes ? y0 + 2 * c : 0;
+        for (int x = lo + 2 * hw + r; x <= hi; x += 2 * nhw) {
+            const int row = rm.row(x);
+            cp_async8(stage + (row << 5) + (((c >> 1) ^ (row & 7)) << 2) + ((c & 1) << 1), vb + (int64_t)x * T_y + yo, bytes);
+        }
+    } else if constexpr (VEC == 4) {
         const int c = lane & 7, r = lane >> 3;   // 16-byte chunk of the row, row within a group of 4
         const int left = ty - (y0 + 4 * c);      // valid frames from this chunk on
         const uint32_t bytes = left >= 4 ? 16u : (left > 0 ? 4u * left : 0u);
@@ -317,12 +327,16 @@ __global__ void __launch_bounds__(kFastThreads) mas_fast_kernel(const MasArgs a,
             if constexpr (sizeof(InT) == 4) {
                 if (tma) {
                 } else if (a.load_mode == 2) {
-                    stage_value_tile_async<true>(reinterpret_cast<const float *>(vb), dst, t, tx, ty,
-                                                 T_y, hw, kHelperWarps, lane);
+                    stage_value_tile_async<4>(reinterpret_cast<const float *>(vb), dst, t, tx, ty,
+                                              T_y, hw, kHelperWarps, lane);
+                    async_done = true;
+                } else if (a.load_mode == 4) {
+                    stage_value_tile_async<2>(reinterpret_cast<const float *>(vb), dst, t, tx, ty,
+                                              T_y, hw, kHelperWarps, lane);
                     async_done = true;
                 } else if (a.load_mode == 1) {
-                    stage_value_tile_async<false>(reinterpret_cast<const float *>(vb), dst, t, tx, ty,
-                                                  T_y, hw, kHelperWarps, lane);
+                    stage_value_tile_async<1>(reinterpret_cast<const float *>(vb), dst, t, tx, ty,
+                                              T_y, hw, kHelperWarps, lane);
                     async_done = true;
                 }
             }
@@ -489,7 +503,10 @@ __global__ void __launch_bounds__(kFast2Threads) mas_fast2_kernel(const MasArgs 
         for (int t = 0; t < ntiles; ++t) {
             if (t >= L.nstages) mbar_wait(&ring.empty[stage], phase ^ 1u);
             float *dst = stages + stage * ring.stage_floats;
-            stage_value_tile2<InT>(vb, mb, dst, t, tx, ty, T_y, hw, kHelperWarps, lane, async, a.load_mode == 2);
+            if (async && a.load_mode == 4)
+                stage_value_tile_async<2, 6>(reinterpret_cast<const float *>(vb), dst, t, tx, ty, T_y, hw, kHelperWarps, lane);
+            else
+                stage_value_tile2<InT>(vb, mb, dst, t, tx, ty, T_y, hw, kHelperWarps, lane, async, a.load_mode == 2);
             if (async) cp_async_arrive(&ring.full[stage]);
             else mbar_arrive(&ring.full[stage]);
             if (++stage == L.nstages) {

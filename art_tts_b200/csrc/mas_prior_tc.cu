@@ -54,8 +54,9 @@ constexpr int kTcMsq = 4;         // ring of per-utterance -0.5|mu|^2 vectors (>
 constexpr int kTcZeroBytes = 4096;
 constexpr int kTcTmemCols = 512;
 // cluster mode: inbound boundary ring [kXRing][32] floats (1 KB), then in_full[kXRing], out_empty[kXRing],
-// bt_full[4] mbarriers and bt_in[4] ints (hand-over of the backtrack between CTAs)
-constexpr int kTcClBytes = 2048;
+// bt_full[4] mbarriers and bt_in[4] ints (hand-over of the backtrack between CTAs); at +2048 the backtrack's
+// window of direction words (32 tokens x kBtWinC chunks)
+constexpr int kTcClBytes = 4096;
 
 // ---------------------------------------------------------------- tcgen05 wrappers
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -347,7 +348,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mas_prior_tc_kernel(const Prior
         const int w = (warp == kTcDp) ? 0 : 1;
         int g = 0, k = 0;
         TcStat s_all(son);
-        long long dp_wait = 0;
+        long long dp_wait = 0, ch_wait[2] = {0, 0};
         ChainCtx cx{};
         if constexpr (CL) {
             cx.in_ring = smem_u32(clb);
@@ -377,7 +378,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mas_prior_tc_kernel(const Prior
                     uint32_t *gbits = a.bits_ws + (size_t)u * L.nch * L.xr_tot + xlo;
                     score = chain_forward_dispatch<XPLMAX, true>(ring, gbits, L.xr_tot, tx, ty, min(tx, xlo + xs) - xlo,
                                                                  lane, w, g, edge, edge_full, xlo, t_lo, ntiles, in_last,
-                                                                 out_first, cx, &owns);
+                                                                 out_first, cx, &owns, son ? ch_wait : nullptr);
                 } else {
                     score = prior_forward2_dispatch<XPLMAX, true>(ring, bits_of(k), L.xrows, tx, ty, lane, w, g,
                                                                   edge, edge_full, &owns,
@@ -392,11 +393,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) mas_prior_tc_kernel(const Prior
             if (lane == 0) *(w == 0 ? fwd_done : fwd_done2) = k + 1;
         }
         s_all.end();
-        if (son && lane == 0 && w == 0) { so[0] = s_all.acc; so[1] = dp_wait; so[2] = g; so[3] = k; }
-        if (son && lane == 0 && w == 1) { so[26] = s_all.acc; so[27] = dp_wait; }
+        if (son && lane == 0 && w == 0) { so[0] = s_all.acc; so[1] = CL ? ch_wait[0] : dp_wait; so[2] = g; so[3] = k; so[14] = ch_wait[1]; }
+        if (son && lane == 0 && w == 1) { so[26] = s_all.acc; so[27] = CL ? ch_wait[0] : dp_wait; so[15] = ch_wait[1]; }
     } else if (warp == kTcBack) {
         // ======================= backtrack warp =======================
         int k = 0, n_bt_in = 0, n_bt_out = 0;
+        TcStat b_fwd(son), b_hand(son), b_walk(son), b_out(son);
         const uint32_t left_bt_in = CL ? map_to_cta(smem_u32(bt_in), (uint32_t)max(crank - 1, 0)) : 0u;
         const uint32_t left_bt_full = CL ? map_to_cta(smem_u32(bt_full), (uint32_t)max(crank - 1, 0)) : 0u;
         // cluster mode: this CTA's rows of the outputs
@@ -422,7 +424,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) mas_prior_tc_kernel(const Prior
                 }
             }
             for (int x = lane; x < T_x; x += 32) dur[x] = 0;
+            b_fwd.begin();
             while (*fwd_done <= k || *fwd_done2 <= k) __nanosleep(32);
+            b_fwd.end();
             __threadfence_block();
             __syncwarp();
             if constexpr (CL) {
@@ -432,13 +436,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) mas_prior_tc_kernel(const Prior
                     int y = ty - 1;
                     if (tx > xlo + xs) {
                         const int slot = n_bt_in & 3;
+                        b_hand.begin();
                         mbar_wait_cluster(&bt_full[slot], (uint32_t)(n_bt_in >> 2) & 1u, 64);
+                        b_hand.end();
                         y = bt_in[slot];
                         ++n_bt_in;
                     }
                     const uint32_t *gbits = a.bits_ws + (size_t)u * L.nch * L.xr_tot + xlo;
+                    b_walk.begin();
                     const int yl = backtrack_bits_window(gbits, L.xr_tot, min(tx, xlo + xs) - xlo, xlo,
-                                                         min(tx, xlo + xs) - 1, y, first, dur, lane);
+                                                         min(tx, xlo + xs) - 1, y, first, dur,
+                                                         reinterpret_cast<uint32_t *>(clb + 2048), lane);
+                    b_walk.end();
                     if (crank > 0 && lane == 0) {
                         const int slot = n_bt_out & 3;
                         st_cluster_u32(left_bt_in + 4u * slot, (uint32_t)yl);
@@ -474,6 +483,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mas_prior_tc_kernel(const Prior
             __syncwarp();
             if (lane == 0) *bt_done = k + 1;
             if constexpr (CL) {
+                b_out.begin();
                 bulk_wait_all();          // my zeros are in memory before my 1-cells
                 __syncwarp();
             } else if (a.path) {
@@ -513,6 +523,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mas_prior_tc_kernel(const Prior
                     }
                 }
                 __syncwarp();
+                b_out.end();
                 continue;
             }
             write_path_ones(pb, a.durations ? a.durations + (int64_t)u * T_x : nullptr, first, dur, T_x, T_y,
@@ -531,6 +542,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mas_prior_tc_kernel(const Prior
             }
             __syncwarp();
         }
+        if (son && CL && lane == 0) { so[28] = b_hand.acc; so[29] = b_walk.acc; so[30] = b_fwd.acc; so[31] = b_out.acc; }
     } else if (warp == kTcLoader || warp == kTcLoader2) {
         // ======================= slab loader =======================
         // y[:, 32t..32t+31] -> staging buffer in shared memory (cp.async, 16-byte pieces, the natural

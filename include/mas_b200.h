@@ -69,6 +69,10 @@ enum {
 };
 #define MAS_FLAG_TMA (1 << 16) /* mas_maximum_path: stage tiles with TMA tensor loads (cp.async.bulk.tensor.2d) instead of
                                   per-thread cp.async; fp32 value, rows 16-byte aligned, T_x <= 256; same results */
+/* mas_maximum_path: keep ONE DP warp per utterance also when the batch fits the SMs in one wave (B <= SM count),
+ * where the default splits the token axis of each utterance over two DP warps from 64 tokens on (latency of one
+ * utterance instead of throughput).  Same results; A/B measurements and tests. */
+#define MAS_FLAG_ONE_DP_WARP (1 << 18)
 /* mas_from_prior_f32, 256 < T_x <= 512 (one thread-block cluster per utterance, the token axis split over its CTAs,
  * the recurrence crossing CTAs through distributed shared memory): clusters of 2 CTAs x 256 tokens instead of the
  * default 4 CTAs x 128 tokens.  Same results. */

@@ -19,9 +19,16 @@ import bench
 from art_tts_b200 import _lib
 
 dev = torch.device("cuda:0")
-B = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
-T_X, T_Y, F = bench.T_X, bench.T_Y, bench.N_FEATS
-t_x_np, t_y_np = bench.make_lengths(B, 1000)
+CFG4 = "--cfg4" in sys.argv      # BASELINE config 4: B=32, 512 x 4096, full lengths (cluster kernel)
+if CFG4:
+    sys.argv.remove("--cfg4")
+B = int(sys.argv[1]) if len(sys.argv) > 1 else (32 if CFG4 else 1024)
+T_X, T_Y, F = (512, 4096, 80) if CFG4 else (bench.T_X, bench.T_Y, bench.N_FEATS)
+if CFG4:
+    t_x_np, t_y_np = np.full(B, T_X, np.int32), np.full(B, T_Y, np.int32)
+else:
+    t_x_np, t_y_np = bench.make_lengths(B, 1000)
+FLAGS = int(os.environ.get("MAS_STATS_FLAGS", "0"))
 t_x, t_y = torch.from_numpy(t_x_np).to(dev), torch.from_numpy(t_y_np).to(dev)
 mu_x = torch.randn(B, F, T_X, device=dev)
 y = torch.randn(B, F, T_Y, device=dev)
@@ -34,7 +41,7 @@ dur = torch.empty(B, T_X, dtype=torch.int32, device=dev)
 for _ in range(3):
     code = lib.mas_from_prior_f32(_lib.ptr(mu_x), None, _lib.ptr(y), _lib.ptr(t_x), _lib.ptr(t_y),
                                   _lib.ptr(path) if path is not None else None, 0, _lib.ptr(dur), None, None, None, B, F, T_X, T_Y,
-                                  _lib.ptr(ws), nws, 0, _lib.stream_ptr(dev))
+                                  _lib.ptr(ws), nws, FLAGS, _lib.stream_ptr(dev))
     assert code == 0, code
 torch.cuda.synchronize()
 off = (nws - sbytes) & ~15
@@ -48,6 +55,9 @@ names = {0: "DP warp 0 total", 1: "  starved of tiles", 28: "  waiting for a fre
          8: "MMA lane total", 9: "  wait A ready (mu_x -> TMEM)", 10: "  wait slab full", 11: "  wait D buffer empty", 12: "  issue + commit",
          13: "epilogue warp0 total", 16: "  wait D full", 17: "  wait ring stage empty", 18: "  ld + adds + store",
          19: "mu_x mover warp0 total", 20: "  global loads (issue)", 21: "  wait A free (prev MMAs done)", 22: "  split + tcgen05.st", 14: "  zero fill of the dense path (a quarter)"}
+if CFG4:
+    names.update({1: "  starved of tiles", 14: "  waiting for the boundary (left CTA)", 27: "  starved of tiles", 15: "  waiting for warp 0 / room in the right CTA's ring",
+                  28: "backtrack warp: waiting for the right CTA's hand-over", 29: "backtrack warp: windowed walk", 30: "backtrack warp: waiting for forward (incl. zero-fill issue)", 31: "backtrack warp: outputs (+ wait zero fill)"})
 if os.environ.get("MAS_LIB_PATH"):
     names.update({13: "DP warp 0: first tcgen05.ld of a tile", 14: "DP warp 0: edge wait (tc2) / zero fill issue", 15: "DP warp 0: later tcgen05.ld waits (tc2) / zero fill wait",
                   16: "DP warp 3: first tcgen05.ld of a tile", 17: "DP warp 3: edge wait", 18: "DP warp 3: later tcgen05.ld waits"})

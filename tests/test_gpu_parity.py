@@ -49,9 +49,11 @@ def test_small_goldens_bit_exact(cuda, golden_small):
         if name != "holes":
             tma = run_mas(value, mask, cuda, strict_mask=False, flags=1 << 16)   # TMA tensor-load staging (fp32, aligned rows)
             assert tma.dtype == got.dtype and torch.equal(tma, got), name
+        one = run_mas(value, mask, cuda, flags=1 << 18)   # one DP warp per utterance (what batches beyond one wave run)
+        assert one.dtype == got.dtype and torch.equal(one, got), name
 
 
-@pytest.mark.parametrize("flags", [0, 1 << 16, 128, 1], ids=["lockstep", "lockstep_tma", "skewed", "general"])
+@pytest.mark.parametrize("flags", [0, 1 << 18, 1 << 16, 128, 1], ids=["lockstep", "lockstep_one_dp_warp", "lockstep_tma", "skewed", "general"])
 def test_seeded_goldens_bit_exact(cuda, golden_seeded, flags):
     g = golden_seeded
     for name in g["names"]:
@@ -68,7 +70,7 @@ def test_seeded_goldens_bit_exact(cuda, golden_seeded, flags):
 
 
 # ------------------------------------------------------------------ oracle on random inputs
-@pytest.mark.parametrize("flags", [0, 1 << 16, 128, 1], ids=["lockstep", "lockstep_tma", "skewed", "general"])
+@pytest.mark.parametrize("flags", [0, 1 << 18, 1 << 16, 128, 1], ids=["lockstep", "lockstep_one_dp_warp", "lockstep_tma", "skewed", "general"])
 def test_random_ragged_vs_oracle(cuda, flags):
     rng = np.random.default_rng(2024 + flags)
     for it in range(30):
@@ -90,8 +92,9 @@ def test_random_ragged_vs_oracle(cuda, flags):
         assert np.array_equal(dur.cpu().numpy(), want.sum(-1).astype(np.int32))
 
 
+@pytest.mark.parametrize("flags", [0, 1 << 18], ids=["auto", "one_dp_warp"])
 @pytest.mark.parametrize("T_x", [1, 31, 32, 33, 64, 65, 190, 256, 257, 511, 512])
-def test_token_axis_edges_vs_oracle(cuda, T_x):
+def test_token_axis_edges_vs_oracle(cuda, T_x, flags):
     rng = np.random.default_rng(T_x)
     T_y = T_x + int(rng.integers(0, 300))
     B = 3
@@ -100,7 +103,7 @@ def test_token_axis_edges_vs_oracle(cuda, T_x):
     value = (rng.standard_normal((B, T_x, T_y)) * 3 - 20).astype(np.float32)
     mask = rect_mask(t_x, t_y, T_x, T_y)
     want, wsc = oracle.maximum_path(value, mask, return_scores=True)
-    path, dur, score = run_lengths(value, t_x, t_y, cuda, return_durations=True, return_score=True)
+    path, dur, score = run_lengths(value, t_x, t_y, cuda, return_durations=True, return_score=True, flags=flags)
     assert np.array_equal(path.cpu().numpy(), want)
     assert np.array_equal(score.cpu().numpy(), wsc)
 
