@@ -836,40 +836,55 @@ __global__ void __launch_bounds__(kTcThreads, 1) mas_prior_tc_kernel(const Prior
                 const bool any = i < mt && xlo + 128 * i + 32 * q < tx;   // some of this warp's tokens exist
                 const int x = xlo + 128 * i + 32 * q + lane;
                 const bool xv = x < tx;
-                // every feature of "my" token into registers: all loads in flight at once, issued
-                // while the previous utterance is still being multiplied
-                float v[96];
-                a_ld.begin();
-                if (any) {
+                // the features of "my" token go through registers in two halves of 48 (all loads of a half in
+                // flight at once; the first half is issued while the previous utterance is still being multiplied,
+                // the second one is prefetched into L2 meanwhile).  Holding all 96 at once put the kernel over its
+                // 128-register budget: the spilled values serialised the loads (15 k cycles to issue them).
+                float s = 0.0f;
+#pragma unroll 1
+                for (int h = 0; h < 2; ++h) {
+                    const int fb = 48 * h;
+                    float v[48];
+                    a_ld.begin();
+                    if (any && fb < Fp) {
 #pragma unroll
-                    for (int f = 0; f < 96; ++f)
-                        v[f] = (xv && f < F) ? __ldg(mub + (int64_t)f * T_x + x) : 0.0f;
-                }
-                a_ld.end();
-                a_w.begin();
-                if (ka > 0) mbar_wait_relaxed(&a_free[i], (ka - 1) & 1, 128);  // previous utterance's MMAs have read this half
-                a_w.end();
-                tc_fence_after();
-                a_st.begin();
-                if (any) {
-                    float s = 0.0f;
-#pragma unroll
-                    for (int f0 = 0; f0 < 96; f0 += 8) {
-                        if (f0 >= Fp) break;
-                        uint32_t rh[8], rl[8];
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) {
-                            const float m = v[f0 + e];
-                            s = __fmaf_rn(m, m, s);
-                            const float h = tf32_rn(m);
-                            rh[e] = __float_as_uint(h);
-                            rl[e] = __float_as_uint(tf32_rn(m - h));
+                        for (int f = 0; f < 48; ++f)
+                            v[f] = (xv && fb + f < F) ? __ldg(mub + (int64_t)(fb + f) * T_x + x) : 0.0f;
+                        if (h == 0 && xv) {
+#pragma unroll 4
+                            for (int f = 48; f < F; ++f)
+                                asm volatile("prefetch.global.L2 [%0];" ::"l"(mub + (int64_t)f * T_x + x));
                         }
-                        tmem_st8(lane_base + L.col_ahi + i * Fp + f0, rh);
-                        tmem_st8(lane_base + L.col_alo + i * Fp + f0, rl);
                     }
-                    msq[x - xlo] = -0.5f * s;   // tts.py:494  mu_square
+                    a_ld.end();
+                    if (h == 0) {
+                        a_w.begin();
+                        if (ka > 0) mbar_wait_relaxed(&a_free[i], (ka - 1) & 1, 128);  // previous utterance's MMAs have read this half
+                        a_w.end();
+                        tc_fence_after();
+                    }
+                    a_st.begin();
+                    if (any && fb < Fp) {
+#pragma unroll
+                        for (int f0 = 0; f0 < 48; f0 += 8) {
+                            if (fb + f0 >= Fp) break;
+                            uint32_t rh[8], rl[8];
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) {
+                                const float m = v[f0 + e];
+                                s = __fmaf_rn(m, m, s);
+                                const float hh = tf32_rn(m);
+                                rh[e] = __float_as_uint(hh);
+                                rl[e] = __float_as_uint(tf32_rn(m - hh));
+                            }
+                            tmem_st8(lane_base + L.col_ahi + i * Fp + fb + f0, rh);
+                            tmem_st8(lane_base + L.col_alo + i * Fp + fb + f0, rl);
+                        }
+                    }
+                    a_st.end();
                 }
+                a_st.begin();
+                if (any) msq[x - xlo] = -0.5f * s;   // tts.py:494  mu_square
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 tc_fence_before();
                 __syncwarp();
