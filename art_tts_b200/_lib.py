@@ -24,6 +24,7 @@ FLAG_SKEWED_DP = 128
 FLAG_TMA = 1 << 16
 FLAG_CLUSTER2 = 1 << 17
 FLAG_ONE_DP_WARP = 1 << 18
+FLAG_PATH_ZEROED = 1 << 19
 
 
 def flag_utt_per_cta(k: int) -> int:

@@ -439,6 +439,7 @@ int from_prior_impl(const float *mu_x, const float *logs, const float *y, const 
         t.path_esize = path ? esize : 4;
         t.one = one_pattern(path_dtype);
         t.utt_per_cta = (flags >> 8) & 0xff;
+        t.path_zeroed = (flags & MAS_FLAG_PATH_ZEROED) ? 1 : 0;
         t.npeer = 0;
         if (want_peer) {   // fused all-gather of the durations (and frame index) over peer memory
             t.npeer = peer->n_peers;

@@ -412,7 +412,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mas_prior_tc_kernel(const Prior
                 // Cluster mode: THIS warp clears the CTA's rows of the dense path (bulk stores), while the forward
                 // pass of the utterance runs -- it has nothing else to do until then, and an utterance of 512 x 4096
                 // is 8 MB of zeros: issued by a loader it would stall the tile pipeline for ~40 tiles.
-                if (pb && x_end > x_beg) {
+                if (pb && x_end > x_beg && !a.path_zeroed) {
                     char *zb = pb + (int64_t)x_beg * T_y * a.path_esize;
                     const int64_t zbytes = (int64_t)(x_end - x_beg) * T_y * a.path_esize;
                     if (bulk_zero_ok(zb, zbytes)) {
@@ -657,7 +657,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) mas_prior_tc_kernel(const Prior
                 // The zeros must be in HBM before the backtrack warp writes its 1-cells (`zdone`); the tile in
                 // flight is finished first so that the burst delays nobody who could run.
                 if (pend >= 0) { finish(pend); pend = -1; }
-                if (zbulk) {
+                if (a.path_zeroed) {
+                    // MAS_FLAG_PATH_ZEROED: the caller cleared the dense path (copy engine, under the previous step)
+                } else if (zbulk) {
                     zero_fill_bulk_part(pb, pbytes, 0, 1, zbuf, kTcZeroBytes, lane, 32);
                     bulk_commit();
                     bulk_wait_all();

@@ -167,13 +167,15 @@ def maximum_path_from_prior(mu_x: torch.Tensor, logs: Optional[torch.Tensor], y:
                             x_mask: torch.Tensor, y_mask: torch.Tensor, *,
                             return_score: bool = False, return_frame_idx: bool = False,
                             return_log_prior: bool = False, want_path: bool = True,
-                            flags: int = 0, peer=None):
+                            flags: int = 0, peer=None, path_out: Optional[torch.Tensor] = None):
     """Fused Gaussian log-prior + MAS + durations (replaces tts.py:483-505).
 
     mu_x [B,F,T_x], y [B,F,T_y] fp32;  x_mask [B,1,T_x], y_mask [B,1,T_y] 0/1 sequence masks
     (or int lengths [B]).  `logs` must be None: the reference's prior has unit variance.
     `peer`: a `_lib.PeerGatherDesc` (see distributed.PeerDurationGather) -- the kernel also stores
     the durations rows into every rank's peer-mapped buffer.
+    `path_out`: write the path into this [B,T_x,T_y] tensor of mu_x.dtype instead of a new one; with
+    `flags | FLAG_PATH_ZEROED` the caller guarantees it is all zeros already (see `ZeroedPathPool`).
     Returns (path [B,T_x,T_y] in mu_x.dtype, durations [B,T_x] int32), followed by the
     optional extras in the order score [B] fp32, frame_idx [B,T_y] int32, log_prior."""
     if logs is not None:
@@ -198,7 +200,14 @@ def maximum_path_from_prior(mu_x: torch.Tensor, logs: Optional[torch.Tensor], y:
         raise ValueError("pass either two masks or two length vectors")
     else:                                              # sequence masks: one kernel, no eager torch ops
         t_x, t_y = lengths_from_seq_masks(x_mask.to(dev), y_mask.to(dev), T_x, T_y)
-    path = torch.empty((B, T_x, T_y), dtype=out_dtype, device=dev) if want_path else None
+    if path_out is not None:
+        if (not want_path or tuple(path_out.shape) != (B, T_x, T_y) or path_out.dtype != out_dtype
+                or path_out.device != dev or not path_out.is_contiguous()):
+            raise ValueError("path_out must be a contiguous [B,T_x,T_y] tensor of mu_x's dtype on mu_x's device")
+        path = path_out
+    else:
+        flags &= ~_lib.FLAG_PATH_ZEROED
+        path = torch.empty((B, T_x, T_y), dtype=out_dtype, device=dev) if want_path else None
     dur = torch.empty((B, T_x), dtype=torch.int32, device=dev)
     score = torch.empty((B,), dtype=torch.float32, device=dev) if return_score else None
     fidx = torch.empty((B, T_y), dtype=torch.int32, device=dev) if return_frame_idx else None

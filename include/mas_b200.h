@@ -73,6 +73,11 @@ enum {
  * where the default splits the token axis of each utterance over two DP warps from 64 tokens on (latency of one
  * utterance instead of throughput).  Same results; A/B measurements and tests. */
 #define MAS_FLAG_ONE_DP_WARP (1 << 18)
+/* mas_from_prior_f32 (tensor-core engine; the others ignore it and clear the path themselves): `path` already holds
+ * zeros in every element -- the caller cleared it, e.g. with cudaMemsetAsync on another stream while the previous
+ * step's kernel was running (copy engine, no SM time) -- so the kernel only writes the 1-cells.  Clearing is 2/3 of
+ * the kernel's algorithmic bytes and, done by the SMs, stalls the tile pipeline of every utterance. */
+#define MAS_FLAG_PATH_ZEROED (1 << 19)
 /* mas_from_prior_f32, 256 < T_x <= 512 (one thread-block cluster per utterance, the token axis split over its CTAs,
  * the recurrence crossing CTAs through distributed shared memory): clusters of 2 CTAs x 256 tokens instead of the
  * default 4 CTAs x 128 tokens.  Same results. */

@@ -122,7 +122,10 @@ def test_peer_gather_description_validated_without_gpu(maslib):
     assert b"peer" in lib.mas_strerror(-7)
     assert lib.mas_peer_durations_supported(1024, 80, 190, 872, 0) == 1    # tensor-core engine
     assert lib.mas_peer_durations_supported(1024, 16, 160, 512, 0) == 0    # CUDA-core engine (F < 32)
-    assert lib.mas_peer_durations_supported(32, 80, 512, 4096, 0) == 0     # beyond 256 tokens
+    assert lib.mas_peer_durations_supported(32, 80, 512, 4096, 0) == 1     # 257..512 tokens: the cluster kernel
+    assert lib.mas_peer_durations_supported(32, 80, 513, 4096, 0) == 0     # beyond 512 tokens
+    assert lib.mas_from_prior_plan(32, 80, 512, 4096, 0) == 0              # config 4 stays fused (prior never in HBM)
+    assert lib.mas_from_prior_plan(32, 80, 512, 4096, 16) == 1             # MAS_FLAG_NO_TENSOR: prior to HBM + drop-in
     assert lib.mas_peer_durations_supported(1024, 80, 190, 872, 16) == 0   # MAS_FLAG_NO_TENSOR
     # sequence-mask lengths entry
     lm = lib.mas_lengths_from_seq_masks

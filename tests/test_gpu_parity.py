@@ -642,7 +642,8 @@ def test_fused_degenerate_and_empty_utterances(cuda, engine, monkeypatch):
     assert np.allclose(lp_np[m], ref_lp[m], rtol=1e-5, atol=1e-4)
 
 
-def test_peer_gather_single_rank_and_refusal(cuda):
+@pytest.mark.parametrize("T_x,T_y", [(70, 300), (300, 700)], ids=["one_cta", "cluster"])
+def test_peer_gather_single_rank_and_refusal(cuda, T_x, T_y):
     """mas_peer_gather with this GPU's own buffers as the only peer (the multi-GPU form is
     tests/test_gpu_multi.py): the tensor-core engine writes durations and frame index at row0 + b
     through the row strides, the CUDA-core engine refuses the call instead of leaving the buffers
@@ -651,9 +652,10 @@ def test_peer_gather_single_rank_and_refusal(cuda):
     import ctypes
     from art_tts_b200 import _lib
     rng = np.random.default_rng(5)
-    B, F, T_x, T_y = 40, 80, 70, 300
+    B, F = 40, 80
     x_len = rng.integers(5, T_x + 1, B).astype(np.int32)
-    y_len = np.minimum(T_y, 4 * x_len + rng.integers(0, 20, B)).astype(np.int32)
+    y_len = np.minimum(T_y, (4 if T_x < 256 else 2) * x_len + rng.integers(0, 20, B)).astype(np.int32)
+    x_len = np.minimum(x_len, y_len)
     mu_x = rng.standard_normal((B, F, T_x)).astype(np.float32)
     y = rng.standard_normal((B, F, T_y)).astype(np.float32)
     row0, stride, fstride = 3, T_x + 9, T_y + 4        # buffers padded to a larger T_x / T_y
