@@ -849,13 +849,26 @@ __global__ void __launch_bounds__(kTcThreads, 1) mas_prior_tc_kernel(const Prior
                     float v[48];
                     a_ld.begin();
                     if (any && fb < Fp) {
+                        // running pointer + a stride pinned in a register: with the address formed from the kernel
+                        // parameters per load, ptxas re-read them from the constant bank before every LDG (two LDC
+                        // + their scoreboard wait per load: 80 cycles per load, 15 k cycles to issue them all)
+                        // (32-bit element offsets off a uniform base: one IMAD.WIDE per address, no carry chains)
+                        uint32_t stride = (uint32_t)T_x;
+                        const float *mb = mub;
+                        asm volatile("" : "+r"(stride), "+l"(mb));
+                        uint32_t off = (uint32_t)fb * stride + (uint32_t)x;
+                        const int nf = xv ? min(48, F - fb) : 0;
 #pragma unroll
-                        for (int f = 0; f < 48; ++f)
-                            v[f] = (xv && fb + f < F) ? __ldg(mub + (int64_t)(fb + f) * T_x + x) : 0.0f;
+                        for (int f = 0; f < 48; ++f) {
+                            v[f] = (f < nf) ? __ldg(mb + off) : 0.0f;
+                            off += stride;
+                        }
                         if (h == 0 && xv) {
 #pragma unroll 4
-                            for (int f = 48; f < F; ++f)
-                                asm volatile("prefetch.global.L2 [%0];" ::"l"(mub + (int64_t)f * T_x + x));
+                            for (int f = 48; f < F; ++f) {
+                                asm volatile("prefetch.global.L2 [%0];" ::"l"(mb + off));
+                                off += stride;
+                            }
                         }
                     }
                     a_ld.end();

@@ -516,6 +516,36 @@ def test_fused_cluster_token_axis_edges(cuda, T_x, cl):
         assert torch.equal(p2, path) and torch.equal(d2, dur), fl
 
 
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("cl", list(CLUSTERS))
+def test_fused_cluster_random_batches(cuda, cl):
+    """Random ragged batches on the cluster kernel: utterances of every length class in random order (so the
+    links between neighbouring CTAs switch on and off from one utterance to the next), several utterances per
+    cluster, small and large frame counts; equal to the oracle on the kernel's own prior every time."""
+    rng = np.random.default_rng(77 if cl == "cluster4" else 78)
+    for it in range(12):
+        T_x = int(rng.integers(257, 513))
+        T_y = int(rng.integers(T_x, 3 * T_x))
+        B = int(rng.integers(1, 48))
+        F = int(rng.choice([32, 40, 80]))
+        x_len = rng.integers(1, T_x + 1, B).astype(np.int32)
+        x_len[rng.integers(0, B)] = T_x
+        y_len = np.minimum(T_y, x_len + rng.integers(0, 2 * T_x, B)).astype(np.int32)
+        mu_x = rng.standard_normal((B, F, T_x)).astype(np.float32)
+        y = rng.standard_normal((B, F, T_y)).astype(np.float32)
+        mask = rect_mask(x_len, y_len, T_x, T_y)
+        upc = int(rng.choice([0, 2, 5]))
+        path, dur, score, lp = fused(mu_x, y, x_len, y_len, cuda, return_score=True, return_log_prior=True,
+                                     flags=CLUSTERS[cl] | (upc << 8))
+        lp_np = lp.cpu().numpy()
+        want, wsc = oracle.maximum_path(lp_np, mask, n_threads=8, return_scores=True)
+        assert np.array_equal(path.cpu().numpy(), want), (it, T_x, T_y, B, F, upc)
+        assert np.array_equal(dur.cpu().numpy(), want.sum(-1).astype(np.int32)), (it, T_x, T_y, B, F, upc)
+        assert np.allclose(score.cpu().numpy(), wsc, rtol=1e-5), (it, T_x, T_y, B, F, upc)
+        p2, d2 = fused(mu_x, y, x_len, y_len, cuda, flags=CLUSTERS[cl] | (upc << 8))
+        assert torch.equal(p2, path) and torch.equal(d2, dur), (it, T_x, T_y, B, F, upc)
+
+
 @pytest.mark.parametrize("cl", list(CLUSTERS))
 def test_config4_fused_on_clusters(cuda, cl):
     """BASELINE config 4 (T_text=512, T_mel=4096, F=80) through the fused entry: the prior is never written to
