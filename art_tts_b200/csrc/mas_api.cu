@@ -97,7 +97,9 @@ Plan choose_plan(int T_x, int T_y, int flags, FastLayout *lay, size_t extra_smem
     L.xrows = ((T_x + row_align - 1) / row_align) * row_align;
     // single-DP-warp kernel: a stage has kTmaBoxRows of slack behind its rows (the last TMA box of a tile
     // may reach past the band); stage bases stay 1024-byte aligned (SWIZZLE_128B atom)
-    L.srows = L.xrows + ((row_align == 32 && extra_smem == 0) ? kTmaBoxRows : 0);
+    // (only when TMA staging is asked for: the 2 KB per stage cost the 190 x 872 shape its third resident CTA)
+    const bool tma_slack = row_align == 32 && extra_smem == 0 && (tuning().fast_tma || (flags & MAS_FLAG_TMA));
+    L.srows = L.xrows + (tma_slack ? kTmaBoxRows : 0);
     L.nch = (T_y + 31) / 32;
     const size_t stage_bytes = (size_t)L.srows * 128;
     const size_t bits_bytes = (size_t)L.nch * L.xrows * 4;
