@@ -713,12 +713,14 @@ __device__ __noinline__ float dp_forward_chain(const TileRing ring, uint32_t *bi
         }
         if (x0 == 0) acc[0] = 0u;
         uint32_t *dst = bits + (size_t)tt * bstride + L;
+        MAS_CHECK(tt >= 0 && tt * kTileY < ty && xlo + ((XPL - 1) << 6) + L < bstride);
 #pragma unroll
         for (int j = 0; j < XPL; ++j) {
             dst[j << 6] = acc[j];
             acc[j] = 0u;
         }
     }
+    MAS_CHECK(cx.n_in >= 0 && cx.n_out >= 0);
     // total alignment score: token tx-1 = local lane (tx-1-xlo)/XPL, slot (tx-1-xlo)%XPL
     const int xl = tx - 1 - xlo;
     const int ql = xl / XPL, qj = xl - ql * XPL;

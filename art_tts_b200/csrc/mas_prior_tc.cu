@@ -440,6 +440,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mas_prior_tc_kernel(const Prior
                         mbar_wait_cluster(&bt_full[slot], (uint32_t)(n_bt_in >> 2) & 1u, 64);
                         b_hand.end();
                         y = bt_in[slot];
+                        MAS_CHECK(y >= xlo + xs - 1 && y < ty);   // token xlo + xs - 1 ends at frame y >= its own index
                         ++n_bt_in;
                     }
                     const uint32_t *gbits = a.bits_ws + (size_t)u * L.nch * L.xr_tot + xlo;
