@@ -186,5 +186,25 @@ def workspace(device, nbytes: int) -> torch.Tensor:
     return buf
 
 
+_NVTX = os.environ.get("MAS_NVTX", "0") not in ("", "0")
+
+
+def traced(fn):
+    """NVTX range around a public entry point when MAS_NVTX=1 (read at import): the ranges show up in
+    Nsight Systems / `ncu --nvtx` timelines as mas.<function>; a plain passthrough otherwise."""
+    if not _NVTX:
+        return fn
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kw):
+        torch.cuda.nvtx.range_push("mas." + fn.__name__)
+        try:
+            return fn(*args, **kw)
+        finally:
+            torch.cuda.nvtx.range_pop()
+    return wrapper
+
+
 def launch_count() -> int:
     return int(load().mas_launch_count())

@@ -42,6 +42,7 @@ def _i32(t, dev, n=None):
     return t
 
 
+@_lib.traced
 def frame_index(durations: torch.Tensor, x_lengths, y_lengths, T_y: int) -> torch.Tensor:
     """durations [B,T_x] int32 -> token index of every frame [B,T_y] int32 (-1 on padding)."""
     _lib.require_cuda(durations, "durations")
@@ -100,6 +101,7 @@ class _DurationLoss(torch.autograd.Function):
         return (g * grad).reshape(ctx.shape).to(ctx.dtype), None, None
 
 
+@_lib.traced
 def duration_loss_from_durations(logw: torch.Tensor, durations: torch.Tensor, x_lengths) -> torch.Tensor:
     """duration_loss(logw, log(1e-8 + durations) * x_mask, x_lengths) (tts.py:503-506,
     model/utils.py:46-48) as one kernel; differentiable w.r.t. logw ([B,1,T_x] or [B,T_x])."""
@@ -260,6 +262,7 @@ class AlignmentLosses(NamedTuple):
     out_offset: Optional[torch.Tensor]
 
 
+@_lib.traced
 def alignment_losses(mu_x: torch.Tensor, logw: torch.Tensor, x_lengths, y: torch.Tensor, y_lengths,
                      out_size: Optional[int] = None, *, y_lengths_host=None, out_offset=None,
                      rng=_random, return_attn: bool = False) -> AlignmentLosses:

@@ -56,6 +56,7 @@ def lengths_from_mask(mask: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
     return t_x, t_y
 
 
+@_lib.traced
 def maximum_path_lengths(value: torch.Tensor, t_x: torch.Tensor, t_y: torch.Tensor, *,
                          out_dtype: Optional[torch.dtype] = None,
                          cell_mask: Optional[torch.Tensor] = None,
@@ -104,6 +105,7 @@ def maximum_path_lengths(value: torch.Tensor, t_x: torch.Tensor, t_y: torch.Tens
     return out[0] if len(out) == 1 else tuple(out)
 
 
+@_lib.traced
 def maximum_path(value: torch.Tensor, mask: torch.Tensor, *, strict_mask: bool = True, flags: int = 0):
     """Drop-in for the reference's `maximum_path(value, mask)` (__init__.py:8-23).
 
@@ -163,6 +165,7 @@ def lengths_from_seq_masks(x_mask: torch.Tensor, y_mask: torch.Tensor,
     return t_x, t_y
 
 
+@_lib.traced
 def maximum_path_from_prior(mu_x: torch.Tensor, logs: Optional[torch.Tensor], y: torch.Tensor,
                             x_mask: torch.Tensor, y_mask: torch.Tensor, *,
                             return_score: bool = False, return_frame_idx: bool = False,
@@ -257,6 +260,7 @@ def _host_staging(dev, B, F, T_x, T_y):
             buf[o2:o2 + B].view(torch.int32), buf[o3:o3 + B].view(torch.int32))
 
 
+@_lib.traced
 def maximum_path_from_prior_host(mu_x: torch.Tensor, y: torch.Tensor, x_lengths: torch.Tensor,
                                  y_lengths: torch.Tensor, device=None, *, want_path: bool = True,
                                  out_dtype: torch.dtype = torch.float32, chunk: int = 0,

@@ -30,6 +30,7 @@ def fix_len_compatibility(length, num_downsamplings_in_unet=2):
         length += 1
 
 
+@_lib.traced
 def generate_path_lengths(duration, t_x, t_y, T_y, out_dtype=torch.float32):
     """durations [B,T_x] (int32 or fp32) + lengths -> dense path [B,T_x,T_y] in out_dtype."""
     _lib.require_cuda(duration, "duration")
