@@ -54,6 +54,19 @@ def cfg3_inputs(n_vocab=149, B=64, T_x=190, T_y=872, n_feats=80, seed=3):
     return x, x_lengths, y, y_lengths
 
 
+def long_text_inputs(n_vocab=149, n_feats=80, seed=44):
+    """Same recipe as tests/golden/make_golden.py::long_text_inputs (keep in sync)."""
+    rng = np.random.default_rng(seed)
+    T_x, T_y = 420, 1320
+    x_lengths = np.array([420, 257, 129, 300, 64, 385], np.int64)
+    y_lengths = np.minimum(T_y, 3 * x_lengths + rng.integers(0, 61, len(x_lengths))).astype(np.int64)
+    y_lengths[0] = T_y
+    x = rng.integers(0, n_vocab, (len(x_lengths), T_x)).astype(np.int64)
+    y = rng.standard_normal((len(x_lengths), n_feats, T_y), dtype=np.float32)
+    y *= (np.arange(T_y)[None, None, :] < y_lengths[:, None, None])
+    return x, x_lengths, y, y_lengths
+
+
 def rect_mask(t_x, t_y, T_x, T_y, dtype=np.float32):
     m = (np.arange(T_x)[None, :, None] < np.asarray(t_x)[:, None, None]) & \
         (np.arange(T_y)[None, None, :] < np.asarray(t_y)[:, None, None])

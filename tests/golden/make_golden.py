@@ -19,6 +19,8 @@ Outputs (committed):
 
   generate_path.npz  the reference's own model.utils.generate_path (utils.py:26-43) on the inference
                      call site's inputs (tts.py:130-147): int64 / fp32 durations, length_scale 1.0 / 1.3
+  long_text_gradtts.npz  token axis of 257..420 (add-blank text; what BASELINE config 4 stands for) through the same
+                     GradTTS(params_v2) compute_loss: mu_x, durations, path hash, prior rows, losses
   cfg3_gradtts.npz   BASELINE config 3 at its stated size: GradTTS(params_v2) compute_loss, B=64,
                      T_x<=190, T_y<=872, out_size=172 -- inputs by seeded recipe (+ sha256), reference
                      durations, losses, sha256 of log_prior and of the path
@@ -27,6 +29,7 @@ Run:  python tests/golden/make_golden.py            (everything)
       python tests/golden/make_golden.py --only loss  (just loss_block_gradtts.npz)
       python tests/golden/make_golden.py --only gp    (just generate_path.npz)
       python tests/golden/make_golden.py --only cfg3  (just cfg3_gradtts.npz)
+      python tests/golden/make_golden.py --only long  (just long_text_gradtts.npz)
 """
 from __future__ import annotations
 
@@ -227,7 +230,26 @@ def cfg3_inputs(n_vocab=149, B=64, T_x=190, T_y=872, n_feats=80, seed=3):
     return x, x_lengths, y, y_lengths
 
 
-def cfg3_golden():
+def long_text_inputs(n_vocab=149, n_feats=80, seed=44):
+    """Seeded inputs of the long-token-axis capture (shared with tests/conftest.py::long_text_inputs, keep in
+    sync): add-blank phoneme text of 257..420 tokens next to short utterances, t_y = 3 t_x + U{0..60}."""
+    rng = np.random.default_rng(seed)
+    T_x, T_y = 420, 1320
+    x_lengths = np.array([420, 257, 129, 300, 64, 385], np.int64)
+    y_lengths = np.minimum(T_y, 3 * x_lengths + rng.integers(0, 61, len(x_lengths))).astype(np.int64)
+    y_lengths[0] = T_y
+    x = rng.integers(0, n_vocab, (len(x_lengths), T_x)).astype(np.int64)
+    y = rng.standard_normal((len(x_lengths), n_feats, T_y), dtype=np.float32)
+    y *= (np.arange(T_y)[None, None, :] < y_lengths[:, None, None])
+    return x, x_lengths, y, y_lengths
+
+
+def long_text_golden():
+    """Token axis beyond 256 (what BASELINE config 4 stands for) through the reference's own compute_loss."""
+    cfg3_golden(inputs=long_text_inputs, fname="long_text_gradtts.npz", recipe=[6, 420, 1320, 80, 44], row_step=7)
+
+
+def cfg3_golden(inputs=None, fname="cfg3_gradtts.npz", recipe=(64, 190, 872, 80, 3), row_step=19):
     """BASELINE config 3 at its stated size (tts.py:450-563, params_v2.py:57,61)."""
     import importlib
     import random
@@ -242,7 +264,7 @@ def cfg3_golden():
                 p2.filter_channels_dp, p2.n_heads, p2.n_enc_layers, p2.enc_kernel, p2.enc_dropout,
                 p2.window_size, p2.n_feats, p2.dec_dim, p2.beta_min, p2.beta_max, p2.pe_scale)
     g.eval()
-    x, x_lengths, y, y_lengths = cfg3_inputs(n_vocab=n_vocab, n_feats=p2.n_feats)
+    x, x_lengths, y, y_lengths = (inputs or cfg3_inputs)(n_vocab=n_vocab, n_feats=p2.n_feats)
     enc, dec, mas = {}, {}, {}
     h = g.encoder.register_forward_hook(lambda m, i, o: enc.update(mu_x=o[0], logw=o[1], x_mask=o[2]))
 
@@ -275,8 +297,8 @@ def cfg3_golden():
     for b in range(len(tx)):
         score[b] = float((lp[b].astype(np.float64) * attn[b]).sum())
     np.savez_compressed(
-        os.path.join(HERE, "cfg3_gradtts.npz"),
-        recipe=np.array([64, 190, 872, 80, 3], np.int64), out_size=np.int32(p2.out_size),
+        os.path.join(HERE, fname),
+        recipe=np.array(list(recipe), np.int64), out_size=np.int32(p2.out_size),
         random_seed=np.int32(seed), x_sha256=np.array(sha(x)), y_sha256=np.array(sha(y)),
         # mu_x is an encoder output (conv/attention stack): stored, fp16-exact storage is not enough
         mu_x=enc["mu_x"].detach().numpy(), logw=enc["logw"].detach().numpy(),
@@ -284,7 +306,7 @@ def cfg3_golden():
         durations=attn.sum(-1).astype(np.int32), path_sha256=np.array(sha(attn.astype(np.uint8))),
         log_prior_sha256=np.array(sha(lp)), log_prior_absmax=np.float32(np.abs(lp).max()),
         # a thin sample of the prior for the 1e-5 bar without storing 42 MB: every 19th token row
-        log_prior_rows=lp[:, ::19, :].astype(np.float32),
+        log_prior_rows=lp[:, ::row_step, :].astype(np.float32), row_step=np.int32(row_step),
         score=score, dur_loss=np.float32(dur_loss.item()), prior_loss=np.float32(prior_loss.item()),
         mu_y_sha256=np.array(sha(dec["mu_y"].numpy())), y_cut_sha256=np.array(sha(dec["y"].numpy())),
         y_cut_mask_sum=dec["y_mask"].numpy().sum(-1).astype(np.int32).reshape(-1))
@@ -298,7 +320,8 @@ def main():
 
     if "--only" in sys.argv:
         which = sys.argv[sys.argv.index("--only") + 1]
-        {"loss": lambda: loss_block(shim), "gp": generate_path_golden, "cfg3": cfg3_golden}[which]()
+        {"loss": lambda: loss_block(shim), "gp": generate_path_golden, "cfg3": cfg3_golden,
+         "long": long_text_golden}[which]()
         shutil.rmtree(shim, ignore_errors=True)
         return
 
@@ -449,6 +472,7 @@ def main():
     loss_block(shim)
     generate_path_golden()
     cfg3_golden()
+    long_text_golden()
     shutil.rmtree(shim, ignore_errors=True)
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):

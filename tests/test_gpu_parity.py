@@ -10,7 +10,7 @@ import pytest
 import torch
 
 import oracle
-from conftest import GOLDEN, cfg3_inputs, path_from_durations, rect_mask, seeded_case
+from conftest import GOLDEN, cfg3_inputs, long_text_inputs, path_from_durations, rect_mask, seeded_case
 
 pytestmark = pytest.mark.gpu
 
@@ -313,6 +313,41 @@ def test_config3_size_reference_capture(cuda):
     d = torch.from_numpy(g["durations"]).to(cuda)
     logw = torch.from_numpy(g["logw"]).to(cuda)
     loss = alignment.duration_loss_from_durations(logw, d, torch.from_numpy(x_len.astype(np.int32)))
+    assert np.isclose(float(loss), float(g["dur_loss"]), rtol=1e-5)
+
+
+@pytest.mark.parametrize("cl", [0, 1 << 17], ids=["cluster4", "cluster2"])
+def test_long_text_reference_capture_on_clusters(cuda, cl):
+    """Token axis of 257..420 (add-blank text; what BASELINE config 4 stands for): mu_x captured from the
+    reference's GradTTS(params_v2) encoder, alignment and losses from its own compute_loss
+    (tests/golden/long_text_gradtts.npz).  The fused kernel runs this shape on thread-block clusters."""
+    from art_tts_b200 import _lib, alignment
+    g = np.load(os.path.join(GOLDEN, "long_text_gradtts.npz"))
+    _, x_len, y, y_len = long_text_inputs()
+    assert hashlib.sha256(y.tobytes()).hexdigest() == str(g["y_sha256"])
+    mu_x = g["mu_x"]
+    B, F, T_x = mu_x.shape
+    T_y = y.shape[2]
+    assert _lib.load().mas_from_prior_plan(B, F, T_x, T_y, cl) == 0
+    mask = rect_mask(x_len, y_len, T_x, T_y)
+    want_path = path_from_durations(g["durations"], y_len, T_y)
+    assert hashlib.sha256(want_path.tobytes()).hexdigest() == str(g["path_sha256"])
+    st = int(g["row_step"])
+    rows = g["log_prior_rows"]
+    m = mask[:, ::st, :].astype(bool)
+    path, dur, score, lp = fused(mu_x, y, x_len, y_len, cuda, return_score=True, return_log_prior=True, flags=cl)
+    lp_np = lp.cpu().numpy()
+    rel = np.abs(lp_np[:, ::st, :] - rows)[m] / np.abs(rows[m])
+    assert rel.max() <= 1e-5, rel.max()                                     # prior within 1e-5 relative
+    agree = (path.to(torch.uint8).cpu().numpy() == want_path).mean()
+    assert agree >= 0.999, agree                                            # >= 99.9 % of cells
+    assert np.allclose(score.cpu().numpy(), g["score"], rtol=1e-4)          # log-likelihood 1e-4 rel
+    assert (dur.cpu().numpy() == g["durations"]).mean() >= 0.99
+    self_path = oracle.maximum_path(lp_np, mask, n_threads=8)
+    assert np.array_equal(path.cpu().numpy(), self_path)                    # bit-exact on the kernel's own prior
+    d = torch.from_numpy(g["durations"]).to(cuda)
+    loss = alignment.duration_loss_from_durations(torch.from_numpy(g["logw"]).to(cuda), d,
+                                                  torch.from_numpy(x_len.astype(np.int32)))
     assert np.isclose(float(loss), float(g["dur_loss"]), rtol=1e-5)
 
 

@@ -8,7 +8,7 @@ import pytest
 
 import oracle
 from oracle import ref as oref
-from conftest import GOLDEN, cfg3_inputs, path_from_durations, rect_mask, seeded_case
+from conftest import GOLDEN, cfg3_inputs, long_text_inputs, path_from_durations, rect_mask, seeded_case
 
 
 def test_oracle_matches_reference_small_goldens(golden_small):
@@ -105,29 +105,34 @@ def test_generate_path_restatement_matches_reference_goldens():
         assert np.array_equal(got, want.astype(np.float32)), name
 
 
-def test_config3_size_capture_against_oracle():
-    """BASELINE config 3 at its stated size (B=64, T_x<=190, T_y<=872, params_v2): the oracle's
-    prior and MAS against what the reference's GradTTS.compute_loss produced."""
-    g = np.load(os.path.join(GOLDEN, "cfg3_gradtts.npz"))
-    x, x_len, y, y_len = cfg3_inputs()
+@pytest.mark.parametrize("fname,inputs", [("cfg3_gradtts.npz", cfg3_inputs), ("long_text_gradtts.npz", long_text_inputs)],
+                         ids=["config3", "long_text"])
+def test_config3_size_capture_against_oracle(fname, inputs):
+    """BASELINE config 3 at its stated size (B=64, T_x<=190, T_y<=872, params_v2), and a token axis of 257..420
+    (add-blank text: what config 4 stands for): the oracle's prior and MAS against what the reference's
+    GradTTS.compute_loss produced."""
+    g = np.load(os.path.join(GOLDEN, fname))
+    x, x_len, y, y_len = inputs()
     assert hashlib.sha256(x.tobytes()).hexdigest() == str(g["x_sha256"])
     assert hashlib.sha256(y.tobytes()).hexdigest() == str(g["y_sha256"])
     assert np.array_equal(x_len.astype(np.int32), g["x_lengths"])
     mu_x = g["mu_x"]
+    T_x, T_y = mu_x.shape[2], y.shape[2]
+    st = int(g["row_step"]) if "row_step" in g.files else 19
     lp = oracle.log_prior(mu_x, y)
     rows = g["log_prior_rows"]
-    sub = lp[:, ::19, :]
-    m = rect_mask(x_len, y_len, 190, 872)[:, ::19, :].astype(bool)
+    sub = lp[:, ::st, :]
+    m = rect_mask(x_len, y_len, T_x, T_y)[:, ::st, :].astype(bool)
     rel = np.abs(sub - rows)[m] / np.abs(rows[m])
     assert rel.max() <= 1e-5, rel.max()
-    mask = rect_mask(x_len, y_len, 190, 872)
+    mask = rect_mask(x_len, y_len, T_x, T_y)
     path, score = oracle.maximum_path(lp, mask, return_scores=True, n_threads=4)
-    want = path_from_durations(g["durations"], y_len, 872)
+    want = path_from_durations(g["durations"], y_len, T_y)
     assert hashlib.sha256(want.tobytes()).hexdigest() == str(g["path_sha256"])   # durations <-> path
     assert (path.astype(np.uint8) == want).mean() >= 0.999
     assert np.allclose(score, g["score"], rtol=1e-4)
     # duration loss from the reference's durations (tts.py:503-506)
-    x_mask = (np.arange(190)[None, None, :] < x_len[:, None, None]).astype(np.float32)
+    x_mask = (np.arange(T_x)[None, None, :] < x_len[:, None, None]).astype(np.float32)
     logw_ = oracle.duration_targets(want.astype(np.float32), x_mask)
     assert np.isclose(oracle.duration_loss(g["logw"], logw_, x_len), g["dur_loss"], rtol=1e-5)
 
