@@ -296,3 +296,48 @@ def alignment_losses(mu_x: torch.Tensor, logw: torch.Tensor, x_lengths, y: torch
     y_mask = (torch.arange(T_out, device=dev)[None, :] < seg_len[:, None]).unsqueeze(1).to(mu_x.dtype)
     attn = path_segment(fidx, offset, seg_len, T_x, T_out, mu_x.dtype) if return_attn else None
     return AlignmentLosses(dur_loss, prior_loss, mu_y, y_seg, y_mask, seg_len, dur, fidx, attn, offset)
+
+
+# ------------------------------------------------------------------ synthesis: durations -> alignment -> mu_y
+class InferenceAlignment(NamedTuple):
+    mu_y: torch.Tensor          # [B, F, y_max_length_]  (encoder_outputs of the reference = mu_y[:, :, :y_max_length])
+    attn: torch.Tensor          # [B, T_x, y_max_length_] dense alignment, entries {0,1}
+    y_mask: torch.Tensor        # [B, 1, y_max_length_]
+    y_lengths: torch.Tensor     # [B] int64
+    y_max_length: int
+
+
+@_lib.traced
+def inference_alignment(mu_x: torch.Tensor, logw: torch.Tensor, x_mask: torch.Tensor, length_scale: float = 1.0,
+                        x_durations: Optional[torch.Tensor] = None) -> InferenceAlignment:
+    """The alignment expansion of synthesis, tts.py:123-153 (ArtTTS.forward; the same text in GradTTS.forward):
+
+        w = exp(logw) * x_mask  (or the given x_durations);  w_ceil = ceil(w) * length_scale
+        y_lengths = clamp_min(sum(w_ceil), 1);  attn = generate_path(w_ceil, attn_mask);  mu_y = attn^T mu_x
+
+    mu_x [B,F,T_x], logw / x_mask [B,1,T_x] on a CUDA device.  `attn` comes from generate_path_kernel (the
+    reference's float cumsum semantics, also for a fractional length_scale), `mu_y` is a gather through the
+    frame index instead of the one-hot matmul (bit-identical values).  Like the reference, the size of the
+    result depends on the data: y_lengths.max() is read back once (one host synchronisation)."""
+    from . import utils
+    _lib.require_cuda(mu_x, "mu_x")
+    B, F, T_x = mu_x.shape
+    if x_durations is not None:
+        w = x_durations.to(device=mu_x.device, dtype=x_mask.dtype).unsqueeze(1) * x_mask
+    else:
+        w = torch.exp(logw) * x_mask
+    w_ceil = torch.ceil(w) * length_scale
+    y_lengths = torch.clamp_min(torch.sum(w_ceil, [1, 2]), 1).long()
+    y_max_length = int(y_lengths.max()) if B else 0
+    T_y = int(utils.fix_len_compatibility(y_max_length))
+    y_mask = utils.sequence_mask(y_lengths, T_y).unsqueeze(1).to(x_mask.dtype)
+    t_x = x_mask.reshape(B, -1).sum(1).to(torch.int32)
+    attn = utils.generate_path_lengths(w_ceil.squeeze(1), t_x, y_lengths, T_y, out_dtype=mu_x.dtype)
+    # token of every frame: from integer durations directly, else off the path (fractional length_scale)
+    dur = w_ceil.squeeze(1)
+    if float(length_scale).is_integer():
+        fidx = frame_index(dur.to(torch.int32), t_x, y_lengths, T_y)
+    else:
+        fidx = torch.where(attn.sum(1) > 0, attn.argmax(1), torch.full_like(attn.argmax(1), -1)).to(torch.int32)
+    mu_y = aligned_mu_y(mu_x, fidx, seg_len=y_lengths.to(torch.int32))
+    return InferenceAlignment(mu_y, attn, y_mask, y_lengths, y_max_length)

@@ -715,8 +715,10 @@ __global__ void __launch_bounds__(256) generate_path_kernel(const void *dur_in, 
     const int tx = t_x ? min(max(t_x[b], 0), T_x) : T_x;
     const int ty = t_y ? min(max(t_y[b], 0), T_y) : T_y;
     if (tid < 32) {
-        // cumsum by one warp, sequential over 32-token groups; fp32 durations are summed in
-        // fp32 left to right (== torch.cumsum on CPU), then y < cum  <=>  y < ceil(cum)
+        // cumsum by one warp, sequential over 32-token groups; fp32 durations are accumulated left to right in
+        // DOUBLE and every partial sum rounded to fp32 -- what torch.cumsum does on the host (ATen's CPU
+        // accumulation type of float is double; captured from the reference's forward() with a fractional
+        // length_scale, tests/golden/inference_arttts.npz) -- then y < cum  <=>  y < ceil(cum)
         const int lane = tid;
         if (dur_dtype == MAS_I32) {
             const int32_t *d = static_cast<const int32_t *>(dur_in) + (int64_t)b * T_x;
@@ -733,10 +735,10 @@ __global__ void __launch_bounds__(256) generate_path_kernel(const void *dur_in, 
             }
         } else if (lane == 0) {
             const float *d = static_cast<const float *>(dur_in) + (int64_t)b * T_x;
-            float cum = 0.0f;
+            double acc = 0.0;
             for (int x = 0; x < T_x; ++x) {
-                cum += d[x];
-                const float c = ceilf(cum);
+                acc += (double)d[x];
+                const float c = ceilf((float)acc);
                 start[x + 1] = (c <= 0.0f) ? 0 : (c >= (float)T_y ? T_y : (int)c);
             }
         }

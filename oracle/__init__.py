@@ -24,6 +24,7 @@ from .mas_oracle import (  # noqa: F401
     durations_from_path,
     frame_index,
     generate_path,
+    inference_alignment,
     log_prior,
     log_prior_f64,
     maximum_path,

@@ -181,10 +181,35 @@ def generate_path(duration, mask):
     duration = np.asarray(duration)
     mask = np.asarray(mask)
     b, t_x, t_y = mask.shape
-    cum = np.cumsum(duration, 1)
+    # torch.cumsum on the host accumulates float32 in double (ATen's CPU accumulation type) and rounds every
+    # partial sum to float32; integer durations are exact either way
+    cum = (np.cumsum(duration.astype(np.float64), 1).astype(duration.dtype)
+           if np.issubdtype(duration.dtype, np.floating) else np.cumsum(duration, 1))
     path = sequence_mask(cum.reshape(b * t_x), t_y).astype(mask.dtype).reshape(b, t_x, t_y)
     path = path - np.pad(path, ((0, 0), (1, 0), (0, 0)))[:, :-1]
     return path * mask
+
+
+def inference_alignment(mu_x, logw, x_mask, length_scale=1.0, x_durations=None):
+    """tts.py:123-153 on numpy arrays (same op sequence, fp32): returns (mu_y [B,F,T_y_], attn [B,T_x,T_y_],
+    y_lengths, y_max_length)."""
+    mu_x = np.asarray(mu_x, np.float32)
+    x_mask = np.asarray(x_mask, np.float32)
+    if x_durations is not None:
+        w = np.asarray(x_durations, np.float32)[:, None, :] * x_mask
+    else:
+        w = np.exp(np.asarray(logw, np.float32)) * x_mask
+    w_ceil = (np.ceil(w) * np.float32(length_scale)).astype(np.float32)
+    y_lengths = np.maximum(w_ceil.sum((1, 2), dtype=np.float32), 1).astype(np.int64)
+    y_max_length = int(y_lengths.max())
+    t_y = y_max_length
+    while t_y % 4:              # fix_len_compatibility (utils.py:13-17), two U-Net downsamplings
+        t_y += 1
+    y_mask = sequence_mask(y_lengths, t_y).astype(np.float32)[:, None, :]
+    attn_mask = x_mask[:, :, :, None] * y_mask[:, :, None, :]
+    attn = generate_path(w_ceil[:, 0], attn_mask[:, 0])
+    mu_y = np.matmul(attn.transpose(0, 2, 1), mu_x.transpose(0, 2, 1)).transpose(0, 2, 1)
+    return mu_y, attn, y_lengths, y_max_length
 
 
 # ------------------------------------------------------------------------------------------

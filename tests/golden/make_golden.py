@@ -19,6 +19,8 @@ Outputs (committed):
 
   generate_path.npz  the reference's own model.utils.generate_path (utils.py:26-43) on the inference
                      call site's inputs (tts.py:130-147): int64 / fp32 durations, length_scale 1.0 / 1.3
+  inference_arttts.npz   the alignment expansion of synthesis (tts.py:123-153) from ArtTTS.forward with the decoder
+                     replaced by the identity: mu_y and attn for given / predicted durations, length_scale 1, 1.3, 2
   long_text_gradtts.npz  token axis of 257..420 (add-blank text; what BASELINE config 4 stands for) through the same
                      GradTTS(params_v2) compute_loss: mu_x, durations, path hash, prior rows, losses
   cfg3_gradtts.npz   BASELINE config 3 at its stated size: GradTTS(params_v2) compute_loss, B=64,
@@ -30,6 +32,7 @@ Run:  python tests/golden/make_golden.py            (everything)
       python tests/golden/make_golden.py --only gp    (just generate_path.npz)
       python tests/golden/make_golden.py --only cfg3  (just cfg3_gradtts.npz)
       python tests/golden/make_golden.py --only long  (just long_text_gradtts.npz)
+      python tests/golden/make_golden.py --only infer (just inference_arttts.npz)
 """
 from __future__ import annotations
 
@@ -230,6 +233,46 @@ def cfg3_inputs(n_vocab=149, B=64, T_x=190, T_y=872, n_feats=80, seed=3):
     return x, x_lengths, y, y_lengths
 
 
+def inference_golden():
+    """The alignment expansion of synthesis (tts.py:123-153: durations -> y_lengths -> generate_path -> mu_y)
+    as the reference's own ArtTTS.forward runs it, decoder replaced by the identity: given durations and
+    predicted ones (exp(logw)), length_scale 1.0 and 1.3."""
+    import importlib
+
+    import torch
+    from model import ArtTTS
+
+    p1 = importlib.import_module("configs.params_v1")
+    torch.manual_seed(p1.random_seed)
+    a = ArtTTS(p1.n_ipa_feats, p1.n_spks, p1.spk_emb_dim, p1.n_enc_channels, p1.filter_channels,
+               p1.filter_channels_dp, p1.n_heads, p1.n_enc_layers, p1.enc_kernel, p1.enc_dropout,
+               p1.window_size, p1.n_feats, p1.dec_dim, p1.beta_min, p1.beta_max, p1.pe_scale)
+    a.eval()
+    B, T_x = 5, 48
+    rng = np.random.default_rng(11)
+    x_lengths = torch.tensor([48, 20, 35, 41, 1])
+    x = torch.randint(-1, 2, (B, p1.n_ipa_feats, T_x)).float()
+    enc = {}
+    h = a.encoder.register_forward_hook(lambda m, i, o: enc.update(mu_x=o[0], logw=o[1], x_mask=o[2]))
+    a.decoder.forward = lambda z, mask, mu, n_timesteps, stoc=False, spk=None: z
+    out = {"x_lengths": x_lengths.numpy().astype(np.int32)}
+    durs = torch.from_numpy(rng.integers(1, 9, (B, T_x)).astype(np.float32))
+    cases = {"given_ls1": (durs, 1.0), "given_ls13": (durs, 1.3), "pred_ls1": (None, 1.0), "pred_ls2": (None, 2.0)}
+    for name, (d, ls) in cases.items():
+        enc_out, dec_out, attn = a.forward(x, x_lengths, n_timesteps=1, length_scale=ls, x_durations=d)
+        out[f"{name}.length_scale"] = np.float32(ls)
+        out[f"{name}.mu_y"] = enc_out.numpy()                       # [B, F, y_max_length]
+        out[f"{name}.attn_packed"] = np.packbits(attn.squeeze(1).numpy().astype(np.uint8), axis=-1)
+        out[f"{name}.T_y"] = np.int32(attn.shape[-1])
+    h.remove()
+    out["mu_x"] = enc["mu_x"].detach().numpy()
+    out["logw"] = enc["logw"].detach().numpy()
+    out["x_mask"] = enc["x_mask"].detach().numpy()
+    out["x_durations"] = durs.numpy()
+    out["names"] = np.array(list(cases))
+    np.savez_compressed(os.path.join(HERE, "inference_arttts.npz"), **out)
+
+
 def long_text_inputs(n_vocab=149, n_feats=80, seed=44):
     """Seeded inputs of the long-token-axis capture (shared with tests/conftest.py::long_text_inputs, keep in
     sync): add-blank phoneme text of 257..420 tokens next to short utterances, t_y = 3 t_x + U{0..60}."""
@@ -321,7 +364,7 @@ def main():
     if "--only" in sys.argv:
         which = sys.argv[sys.argv.index("--only") + 1]
         {"loss": lambda: loss_block(shim), "gp": generate_path_golden, "cfg3": cfg3_golden,
-         "long": long_text_golden}[which]()
+         "long": long_text_golden, "infer": inference_golden}[which]()
         shutil.rmtree(shim, ignore_errors=True)
         return
 
@@ -473,6 +516,7 @@ def main():
     generate_path_golden()
     cfg3_golden()
     long_text_golden()
+    inference_golden()
     shutil.rmtree(shim, ignore_errors=True)
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):

@@ -140,3 +140,28 @@ def test_alignment_block_at_b1024_properties(cuda):
     ref = (0.5 * ((y - want) ** 2 + float(np.log(2 * np.pi))) * valid[:, None, :]).double().sum() / (valid.sum() * F)
     assert abs(out.prior_loss.item() - ref.item()) <= 1e-5 * abs(ref.item())
     assert torch.equal(out.durations.sum(1), ty)
+
+
+def test_inference_alignment_matches_reference_forward(cuda):
+    """tts.py:123-153 (durations -> y_lengths -> generate_path -> mu_y) against captures of the reference's own
+    ArtTTS.forward with the decoder replaced by the identity (tests/golden/inference_arttts.npz): given and
+    predicted durations, length_scale 1, 1.3 and 2."""
+    from art_tts_b200 import alignment
+    g = np.load(os.path.join(GOLDEN, "inference_arttts.npz"))
+    mu_x = torch.from_numpy(g["mu_x"]).to(cuda)
+    logw = torch.from_numpy(g["logw"]).to(cuda)
+    x_mask = torch.from_numpy(g["x_mask"]).to(cuda)
+    durs = torch.from_numpy(g["x_durations"]).to(cuda)
+    T_x = mu_x.shape[2]
+    for name in g["names"]:
+        given = str(name).startswith("given")
+        ls = float(g[f"{name}.length_scale"])
+        out = alignment.inference_alignment(mu_x, logw, x_mask, length_scale=ls, x_durations=durs if given else None)
+        T_y = int(g[f"{name}.T_y"])
+        want_attn = np.unpackbits(g[f"{name}.attn_packed"], axis=-1)[:, :, :T_y].astype(np.float32)
+        assert out.attn.shape == (mu_x.shape[0], T_x, T_y), name
+        assert np.array_equal(out.attn.cpu().numpy(), want_attn), name
+        want_mu_y = g[f"{name}.mu_y"]                       # [B, F, y_max_length]
+        assert out.y_max_length == want_mu_y.shape[2], name
+        assert np.array_equal(out.mu_y[:, :, :out.y_max_length].cpu().numpy(), want_mu_y), name
+        assert float(out.mu_y[:, :, out.y_max_length:].abs().sum()) == 0.0, name

@@ -189,3 +189,17 @@ def test_loss_block_restatement_matches_reference_compute_loss():
     for b in range(B):
         assert np.array_equal(attn[b, idx[b, :y_len[b]], np.arange(y_len[b])], np.ones(y_len[b]))
         assert (idx[b, y_len[b]:] == -1).all()
+
+
+def test_inference_alignment_restatement_matches_reference_forward():
+    """oracle.inference_alignment (tts.py:123-153) against the reference's own ArtTTS.forward captures."""
+    g = np.load(os.path.join(GOLDEN, "inference_arttts.npz"))
+    for name in g["names"]:
+        given = str(name).startswith("given")
+        mu_y, attn, y_len, y_max = oracle.inference_alignment(
+            g["mu_x"], g["logw"], g["x_mask"], float(g[f"{name}.length_scale"]),
+            g["x_durations"] if given else None)
+        T_y = int(g[f"{name}.T_y"])
+        want_attn = np.unpackbits(g[f"{name}.attn_packed"], axis=-1)[:, :, :T_y].astype(np.float32)
+        assert attn.shape == want_attn.shape and np.array_equal(attn, want_attn), name
+        assert np.array_equal(mu_y[:, :, :y_max], g[f"{name}.mu_y"]), name
