@@ -368,6 +368,17 @@ __device__ __forceinline__ void write_frame_idx(int32_t *fi, const int *first, c
 // bit comes from the same comparison beside the chain.  max(up, cur) is the reference's
 // `up > cur ? up : cur` on finite values (a NaN or a +0/-0 tie could differ), so the drop-in
 // kernel, whose contract is bit-exactness on any input, keeps the select.
+#ifdef MAS_TC_TRACE
+// per-tile event timestamps of ONE CTA (profiles/tc_trace.py): tr[g * 16 + event], set by mas_prior_tc_kernel
+static __device__ long long *g_tc_trace;
+#define MAS_TRACE(ev, g)                                                                       \
+    do {                                                                                       \
+        if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && g_tc_trace && (g) < 1500) g_tc_trace[(g) * 16 + (ev)] = clock64(); \
+    } while (0)
+#else
+#define MAS_TRACE(ev, g) ((void)0)
+#endif
+
 template <int XPL, bool DIAG, bool FMAX = false>
 __device__ __forceinline__ float dp_step2(float (&V)[XPL], uint32_t (&acc)[XPL], const float (&v)[XPL],
                                           float &left, int lane, int x0, int y, uint32_t bit,
@@ -468,9 +479,11 @@ __device__ __noinline__ float dp_forward2(const TileRing ring, uint32_t *bits, i
         const int gt = g0 + t;
         long long t0 = 0;
         if (wait_acc) t0 = clock64();
+        MAS_TRACE(11 + w, gt);
         mbar_wait(&ring.full[stage], phase);
         if (w == 1) mbar_wait(&edge_full[gt & 3], (uint32_t)(gt >> 2) & 1u);   // warp 0 finished this tile
         if (wait_acc) *wait_acc += clock64() - t0;
+        MAS_TRACE(7 + 2 * w, gt);
         const float *tile = ring.stages + stage * ring.stage_floats;
         float *etile = edge + ((gt & 3) << 5);
         const int y0 = t * kTileY;
@@ -483,6 +496,7 @@ __device__ __noinline__ float dp_forward2(const TileRing ring, uint32_t *bits, i
             dp_tile2<XPL, true, false, FMAX>(V, acc, left, tile, etile, w, lane, x0, y0, nsteps);
         }
         __syncwarp();
+        MAS_TRACE(8 + 2 * w, gt);
         if (lane == 0) {
             mbar_arrive(&ring.empty[stage]);
             if (w == 0) mbar_arrive(&edge_full[gt & 3]);   // release: lane 31's stores are ordered by __syncwarp

@@ -289,6 +289,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) mas_prior_tc_kernel(const Prior
     __syncthreads();
     tc_fence_after();
     const uint32_t tbase = __shfl_sync(kFull, *tslot, 0);
+#ifdef MAS_TC_TRACE
+    if (blockIdx.x == 0 && threadIdx.x == 0) g_tc_trace = a.stats ? a.stats + 148 * 32 : nullptr;
+    __syncthreads();
+#endif
 
     // ntiles = tiles this CTA works on, the first of them global tile t_lo (frames 32 t_lo ..).  One CTA per
     // utterance: all of them.  Cluster: the tiles that hold band cells of the CTA's tokens (mas_dp.cuh).
@@ -606,6 +610,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mas_prior_tc_kernel(const Prior
             fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core's reads
             __syncwarp();
             if (lane == 0) mbar_arrive(&slab_full[gg % kTcSlabs]);
+            MAS_TRACE(1, gg);
             l_fence.end();
             l_fin.end();
         };
@@ -645,6 +650,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mas_prior_tc_kernel(const Prior
                     for (int f = 0; f < F; ++f) cp_async4(dst + (f << 5) + lane, src + (int64_t)f * T_y, bytes);
                 }
                 asm volatile("cp.async.commit_group;" ::: "memory");
+                MAS_TRACE(0, g);
                 pend = g;
                 l_issue.end();
             }
@@ -733,6 +739,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) mas_prior_tc_kernel(const Prior
                             a_ok[i] = true;
                         }
                     tc_fence_after();
+                    MAS_TRACE(2, g);
+                    if (np == 2) MAS_TRACE(2, g + 1);
                     m_i.begin();
                     // Everything the issue loop uses is made provably warp-uniform first (uniform_u32): the
                     // operands of all 120 MMAs are then uniform-register immediates off a few registers.
@@ -795,6 +803,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) mas_prior_tc_kernel(const Prior
                         }
                     }
                     __syncwarp();
+                    MAS_TRACE(3, g);
+                    if (np == 2) MAS_TRACE(3, g + 1);
                     m_i.end();
                     t += np;
                     g += np;
@@ -931,6 +941,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mas_prior_tc_kernel(const Prior
                 const int mask = tile_mask(tx, ty, t_lo + t);
                 e_df.begin();
                 mbar_wait_relaxed(&d_full[b], (g / NB) & 1, 32);
+                if (q == 0) MAS_TRACE(4, g);
                 e_df.end();
                 tc_fence_after();
                 e_w.begin();
@@ -969,6 +980,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mas_prior_tc_kernel(const Prior
                 e_w.end();
                 e_re.begin();
                 if (g >= NS) mbar_wait_relaxed(&ring_empty[sidx], ((g / NS) - 1) & 1, 32);  // DP consumed tile g-NS
+                if (q == 0) MAS_TRACE(5, g);
                 e_re.end();
                 e_w.begin();
                 float *tile = stages + (size_t)sidx * ring.stage_floats;
@@ -1006,6 +1018,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mas_prior_tc_kernel(const Prior
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&ring_full[sidx]);   // this warp's rows of tile g are written
+                if (q == 0) MAS_TRACE(6, g);
                 e_w.end();
             }
             ++ka;
