@@ -25,6 +25,7 @@ FLAG_TMA = 1 << 16
 FLAG_CLUSTER2 = 1 << 17
 FLAG_ONE_DP_WARP = 1 << 18
 FLAG_PATH_ZEROED = 1 << 19
+FLAG_STAGGER_MMA = 1 << 20
 
 
 def flag_utt_per_cta(k: int) -> int:

@@ -63,7 +63,7 @@ static int env_int(const char *name, int dflt)
 // the library, so that plan queries (mas_plan, mas_from_prior_plan, mas_peer_durations_supported)
 // and the launches that follow can never disagree.
 struct Tuning {
-    int prior_tc, prior_tc_min_f, stages, dp2_min_tx, dp2_min_tx_one_wave, prior_spill, prior_stats, fma_per_smsp, extra_fma, fast3, fast_tma, tc_cluster;
+    int prior_tc, prior_tc_min_f, stages, dp2_min_tx, dp2_min_tx_one_wave, prior_spill, prior_stats, fma_per_smsp, extra_fma, fast3, fast_tma, tc_cluster, tc_stagger;
 };
 static const Tuning &tuning()
 {
@@ -78,6 +78,7 @@ static const Tuning &tuning()
         v.prior_stats = env_int("MAS_PRIOR_STATS", 0);
         v.fma_per_smsp = env_int("MAS_PRIOR_FMA_PER_SMSP", 2);
         if (v.fma_per_smsp < 1 || v.fma_per_smsp > 4) v.fma_per_smsp = 2;
+        v.tc_stagger = env_int("MAS_TC_STAGGER", 0);   // MMA issue order of the tensor-core kernel: 1 = staggered half-chains (measured slower)
         v.tc_cluster = env_int("MAS_TC_CLUSTER", 4);   // CTAs per utterance of the tensor-core kernel when T_x > 256: 4 (default), 2, 0 = off
         v.fast_tma = env_int("MAS_FAST_TMA", 0);   // TMA tensor-load staging of the drop-in kernel: opt-in (measured: no faster)
         v.fast3 = env_int("MAS_FAST3", 0);   // skewed-lane drop-in kernel: opt-in until its HBM staging beats the lock-step one
@@ -442,6 +443,7 @@ int from_prior_impl(const float *mu_x, const float *logs, const float *y, const 
         t.one = one_pattern(path_dtype);
         t.utt_per_cta = (flags >> 8) & 0xff;
         t.path_zeroed = (flags & MAS_FLAG_PATH_ZEROED) ? 1 : 0;
+        t.mma_stagger = (tuning().tc_stagger || (flags & MAS_FLAG_STAGGER_MMA)) ? 1 : 0;
         t.npeer = 0;
         if (want_peer) {   // fused all-gather of the durations (and frame index) over peer memory
             t.npeer = peer->n_peers;

@@ -154,6 +154,7 @@ struct PriorTcArgs {
     int32_t *peer_fi[kMaxPeers];   // and (optionally, else NULL) every rank's frame-index buffer
     int npeer;
     long long peer_row0, peer_stride, peer_fi_stride;
+    int mma_stagger;       // MMA issue order: 1 = staggered half-chains of consecutive tiles (MAS_FLAG_STAGGER_MMA, opt-in), 0 = tile pairs (default)
     int path_zeroed;       // MAS_FLAG_PATH_ZEROED: `path` is all zeros already, only the 1-cells are written
     int utt_per_cta;       // MAS_FLAG_UTT_PER_CTA(k): at least k utterances per persistent CTA (0/1: one CTA per SM)
     int B, F, T_x, T_y;

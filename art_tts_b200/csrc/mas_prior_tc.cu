@@ -566,6 +566,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) mas_prior_tc_kernel(const Prior
             l_cp.begin();
             asm volatile("cp.async.wait_group 0;" ::: "memory");
             l_cp.end();
+            // the slab is only needed now (the copy went to the staging buffer): waiting for it here instead of
+            // before the copy was issued puts the copy's latency under the wait
+            l_free.begin();
+            if (gg >= kTcSlabs) mbar_wait_relaxed(&slab_free[gg % kTcSlabs], ((gg / kTcSlabs) - 1) & 1);  // MMAs of tile gg-kTcSlabs done
+            l_free.end();
             l_fin.begin();
             __syncwarp();                 // every lane's copies of this slab have landed
             const float *st = staging + (size_t)(gg & 1) * Fp * kTileY + 4 * c;   // tile parity == owning loader
@@ -629,19 +634,25 @@ __global__ void __launch_bounds__(kTcThreads, 1) mas_prior_tc_kernel(const Prior
             for (int t = 0; t < ntiles; ++t, ++g) {
                 if ((g & 1) != lp) continue;
                 if (pend >= 0) finish(pend);   // my previous tile: its copy has had a whole trip to land
-                const int s = g % kTcSlabs;
-                l_free.begin();
-                if (g >= kTcSlabs) mbar_wait_relaxed(&slab_free[s], ((g / kTcSlabs) - 1) & 1);  // MMAs of tile g-kTcSlabs done
-                l_free.end();
                 float *dst = staging + (size_t)lp * Fp * kTileY;
                 const int y0 = (t_lo + t) * kTileY;
                 l_issue.begin();
                 if (vec16) {
                     const int left = ty - (y0 + 4 * c);
                     const uint32_t bytes = left >= 4 ? 16u : (left > 0 ? 4u * left : 0u);
-                    const float *src = yb + (bytes ? y0 + 4 * c : 0);
+                    // 32-bit element offsets off a pinned base and a pinned stride (ptxas otherwise re-reads the
+                    // kernel parameters and carries 64-bit products per copy: ~25 cycles of issue per cp.async)
+                    const float *yp = yb;
+                    uint32_t stride = 4u * (uint32_t)T_y;
+                    asm volatile("" : "+l"(yp), "+r"(stride));
+                    uint32_t off = (uint32_t)r * (uint32_t)T_y + (bytes ? (uint32_t)(y0 + 4 * c) : 0u);
+                    float *d = dst + (r << 5) + 4 * c;
 #pragma unroll 5
-                    for (int f = r; f < F; f += 4) cp_async16(dst + (f << 5) + 4 * c, src + (int64_t)f * T_y, bytes);
+                    for (int f = r; f < F; f += 4) {
+                        cp_async16(d, yp + off, bytes);
+                        off += stride;
+                        d += 128;
+                    }
                 } else {
                     const int y = y0 + lane;
                     const uint32_t bytes = y < ty ? 4u : 0u;
@@ -705,6 +716,106 @@ __global__ void __launch_bounds__(kTcThreads, 1) mas_prior_tc_kernel(const Prior
                 bool a_ok[2] = {false, false}, a_rel[2] = {false, false};
                 // last tile whose band still reaches into M tile 0 (tokens < 128)
                 const int t0_last = a.lp_out ? ntiles - 1 : min(ntiles - 1, ((xlo + 127 - tx + ty) >> 5) - t_lo);   // tap: every tile
+                if (a.mma_stagger) {
+                    // STAGGERED issue (profiles/r2_tc_tile_timeline.txt).  Issuing the tiles in pairs made tile g+2
+                    // wait for the epilogue to drain tile g, i.e. for the whole pair (g, g+1) to finish in the
+                    // tensor pipe: with three accumulator buffers issue and execution never overlapped (7.8 k cycles
+                    // per pair, the pipe busy 5.8 k of them).  Here step s interleaves the SECOND half of tile s-1's
+                    // MMA chain with the FIRST half of tile s's: still four independent accumulators in flight, but
+                    // the tiles finish one at a time, half a step apart, and the buffer tile s needs (tile s-3's) was
+                    // drained a whole step ago.  The chains themselves are unchanged (same terms, same order).
+                    const int nacc = 3 * ksteps, half = nacc >> 1;     // MMAs per accumulator, first-half length
+                    const uint32_t bdhi = (uint32_t)(tc_bdesc(0) >> 32);
+                    const uint32_t ahi0 = uniform_u32(tbase + L.col_ahi), alo0 = uniform_u32(tbase + L.col_alo);
+                    const uint32_t fpu = uniform_u32((uint32_t)Fp);
+                    uint32_t dX[2] = {0u, 0u}, bXh = 0u, bXl = 0u;    // tile s-1: accumulators, slab descriptors (hi / lo part)
+                    int amX = 0;
+                    for (int s = 0; s <= ntiles; ++s) {
+                        const bool hasY = s < ntiles;
+                        const int gY = g + s, gX = g + s - 1;
+                        uint32_t dY[2] = {0u, 0u}, bYh = 0u, bYl = 0u;
+                        int amY = 0;
+                        if (hasY) {
+                            const int sl = gY % kTcSlabs, b = gY % NB;
+                            m_s.begin();
+                            mbar_wait(&slab_full[sl], (gY / kTcSlabs) & 1);
+                            m_s.end();
+                            m_d.begin();
+                            if (gY >= NB) mbar_wait(&d_empty[b], ((gY / NB) - 1) & 1);  // epilogue drained tile gY-NB
+                            m_d.end();
+                            const uint32_t sbm = smem_u32(slabs + (size_t)sl * slab_floats);
+                            bYh = uniform_u32((uint32_t)tc_bdesc(sbm));
+                            bYl = uniform_u32((uint32_t)tc_bdesc(sbm + (uint32_t)part_floats * 4u));
+                            amY = (int)uniform_u32((uint32_t)tile_mask(tx, ty, t_lo + s));
+                            dY[0] = uniform_u32(tbase + L.col_d + (b * 2) * 32);
+                            dY[1] = uniform_u32(tbase + L.col_d + (b * 2) * 32 + 32);
+#pragma unroll
+                            for (int i = 0; i < 2; ++i)
+                                if (!a_ok[i] && ((amY >> i) & 1)) {
+                                    m_a.begin();
+                                    mbar_wait(&a_ready[i], ka & 1);   // this half of mu_x is in TMEM
+                                    m_a.end();
+                                    a_ok[i] = true;
+                                }
+                        }
+                        tc_fence_after();
+                        MAS_TRACE(2, gY);
+                        m_i.begin();
+                        // MMA number n (0 .. 3 ksteps - 1) of an accumulator's chain: pass n / ksteps (0: a_lo b_hi,
+                        // 1: a_hi b_lo, 2: a_hi b_hi), k step n % ksteps
+                        auto issue = [&](auto ks_tag, auto mx_tag, auto my_tag) {
+                            constexpr int KS = decltype(ks_tag)::value;       // 0 = run-time k-step count
+                            constexpr int MX = decltype(mx_tag)::value, MY = decltype(my_tag)::value;   // -1 = run-time mask
+                            const int nk = KS ? KS : ksteps;
+                            const int mx = MX >= 0 ? MX : amX, my = MY >= 0 ? MY : amY;
+                            const int n1 = 3 * nk, h = n1 >> 1;
+#pragma unroll
+                            for (int j = 0; j < (KS ? (3 * KS + 1) / 2 : 1 << 30); ++j) {
+                                if (!KS && j >= n1 - h) break;
+                                if (j < h && my) {            // first half of tile s
+                                    const int pass = j / nk, k = j - pass * nk;
+                                    const uint32_t ab = ((pass == 0) ? alo0 : ahi0) + 8 * k;
+                                    const uint32_t bb = ((pass == 1) ? bYl : bYh) + (uint32_t)(64 * k);
+                                    if (my & 1) tc_mma_ts2(dY[0], ab, bb, bdhi, idesc, (uint32_t)(j != 0));
+                                    if (my & 2) tc_mma_ts2(dY[1], ab + fpu, bb, bdhi, idesc, (uint32_t)(j != 0));
+                                }
+                                if (mx) {                     // second half of tile s-1
+                                    const int n = h + j;
+                                    const int pass = n / nk, k = n - pass * nk;
+                                    const uint32_t ab = ((pass == 0) ? alo0 : ahi0) + 8 * k;
+                                    const uint32_t bb = ((pass == 1) ? bXl : bXh) + (uint32_t)(64 * k);
+                                    if (mx & 1) tc_mma_ts2(dX[0], ab, bb, bdhi, idesc, 1u);
+                                    if (mx & 2) tc_mma_ts2(dX[1], ab + fpu, bb, bdhi, idesc, 1u);
+                                }
+                            }
+                        };
+                        if (elect_one()) {
+                            using K10 = std::integral_constant<int, 10>;
+                            using R = std::integral_constant<int, -1>;
+                            if (ksteps != 10) issue(std::integral_constant<int, 0>{}, R{}, R{});
+                            else if (amX == 3 && amY == 3) issue(K10{}, std::integral_constant<int, 3>{}, std::integral_constant<int, 3>{});
+                            else if (amX == 1 && amY == 1) issue(K10{}, std::integral_constant<int, 1>{}, std::integral_constant<int, 1>{});
+                            else if (amX == 2 && amY == 2) issue(K10{}, std::integral_constant<int, 2>{}, std::integral_constant<int, 2>{});
+                            else issue(K10{}, R{}, R{});
+                        }
+                        __syncwarp();
+                        if (s >= 1 && elect_one()) {
+                            tc_commit(&slab_free[gX % kTcSlabs]);   // slab reusable once these MMAs have read it
+                            tc_commit(&d_full[gX % NB]);            // tile s-1 complete: ready for the epilogue warps
+                        }
+                        __syncwarp();
+                        MAS_TRACE(3, gX < 0 ? 0 : gX);
+                        m_i.end();
+                        if (!a_rel[0] && s >= 1 && s - 1 >= t0_last) {   // no later tile touches tokens < 128
+                            if (!a_ok[0]) mbar_wait(&a_ready[0], ka & 1);
+                            if (elect_one()) tc_commit(&a_free[0]);
+                            __syncwarp();
+                            a_rel[0] = a_ok[0] = true;
+                        }
+                        dX[0] = dY[0]; dX[1] = dY[1]; bXh = bYh; bXl = bYl; amX = amY;
+                    }
+                    g += ntiles;
+                } else
                 for (int t = 0; t < ntiles;) {
                     // a pair of tiles (g, g+1): up to four independent accumulators in flight
                     // (accumulator c = 2*e + i: tile e of the pair, M tile i); everything the issue

@@ -395,8 +395,8 @@ def test_fused_matches_reference_model_capture(cuda, fname):
         assert (fi[b, y_len[b]:] == -1).all()
 
 
-# MAS_FLAG_NO_TENSOR / MAS_FLAG_FORCE_TENSOR
-ENGINES = {"auto": 0, "cuda_core": 16, "tensor_core": 32}
+# MAS_FLAG_NO_TENSOR / MAS_FLAG_FORCE_TENSOR (/ + MAS_FLAG_STAGGER_MMA: the other MMA issue order of the tensor-core engine)
+ENGINES = {"auto": 0, "cuda_core": 16, "tensor_core": 32, "tensor_core_staggered": 32 | (1 << 20)}
 
 
 def select_engine(monkeypatch, engine):
@@ -570,14 +570,15 @@ def test_fused_cluster_random_batches(cuda, cl):
         y = rng.standard_normal((B, F, T_y)).astype(np.float32)
         mask = rect_mask(x_len, y_len, T_x, T_y)
         upc = int(rng.choice([0, 2, 5]))
+        st = (1 << 20) if it % 2 else 0          # every other batch: the staggered MMA issue order
         path, dur, score, lp = fused(mu_x, y, x_len, y_len, cuda, return_score=True, return_log_prior=True,
-                                     flags=CLUSTERS[cl] | (upc << 8))
+                                     flags=CLUSTERS[cl] | (upc << 8) | st)
         lp_np = lp.cpu().numpy()
         want, wsc = oracle.maximum_path(lp_np, mask, n_threads=8, return_scores=True)
         assert np.array_equal(path.cpu().numpy(), want), (it, T_x, T_y, B, F, upc)
         assert np.array_equal(dur.cpu().numpy(), want.sum(-1).astype(np.int32)), (it, T_x, T_y, B, F, upc)
         assert np.allclose(score.cpu().numpy(), wsc, rtol=1e-5), (it, T_x, T_y, B, F, upc)
-        p2, d2 = fused(mu_x, y, x_len, y_len, cuda, flags=CLUSTERS[cl] | (upc << 8))
+        p2, d2 = fused(mu_x, y, x_len, y_len, cuda, flags=CLUSTERS[cl] | (upc << 8) | st)
         assert torch.equal(p2, path) and torch.equal(d2, dur), (it, T_x, T_y, B, F, upc)
 
 
