@@ -8,7 +8,7 @@ sys.path.insert(0, ROOT)
 os.environ["MAS_PRIOR_STATS"] = "1"
 from art_tts_b200 import build as _b
 lib = os.path.join(_b.LIBDIR, "libmas_trace.so")
-_b.build(extra=["-DMAS_TC_TRACE"], out=lib)
+_b.build(extra=["-DMAS_TC_TRACE"] + os.environ.get("MAS_TRACE_EXTRA", "").split(), out=lib)
 os.environ["MAS_LIB_PATH"] = lib
 import numpy as np, torch
 import bench
