@@ -757,3 +757,32 @@ def test_peer_gather_single_rank_and_refusal(cuda, T_x, T_y):
     buf.fill_(-7)
     fused(mu_x, y, x_len, y_len, cuda)        # no description: plain call, nothing written
     assert (buf == -7).all()
+
+
+def test_path_out_and_pre_cleared_path(cuda):
+    """maximum_path_from_prior(path_out=...): the path is written into the caller's tensor; with FLAG_PATH_ZEROED the
+    kernel skips the clearing and only writes the 1-cells -- same result on a cleared buffer, and a dirty buffer keeps
+    its dirt outside the 1-cells (proof that nothing was cleared).  Shape / dtype mismatches are refused."""
+    from art_tts_b200 import _lib, monotonic_align
+    rng = np.random.default_rng(12)
+    B, F, T_x, T_y = 9, 80, 150, 500
+    x_len = rng.integers(20, T_x + 1, B).astype(np.int32)
+    y_len = np.minimum(T_y, 3 * x_len + rng.integers(0, 50, B)).astype(np.int32)
+    mu_x = torch.from_numpy(rng.standard_normal((B, F, T_x)).astype(np.float32)).to(cuda)
+    y = torch.from_numpy(rng.standard_normal((B, F, T_y)).astype(np.float32)).to(cuda)
+    tx, ty = torch.from_numpy(x_len), torch.from_numpy(y_len)
+    ref, dref = monotonic_align.maximum_path_from_prior(mu_x, None, y, tx, ty)
+    out = torch.full((B, T_x, T_y), 7.0, device=cuda)
+    p, d = monotonic_align.maximum_path_from_prior(mu_x, None, y, tx, ty, path_out=out)
+    assert p.data_ptr() == out.data_ptr() and torch.equal(out, ref) and torch.equal(d, dref)
+    out.zero_()
+    p, d = monotonic_align.maximum_path_from_prior(mu_x, None, y, tx, ty, path_out=out, flags=_lib.FLAG_PATH_ZEROED)
+    assert torch.equal(out, ref) and torch.equal(d, dref)
+    out.fill_(7.0)
+    monotonic_align.maximum_path_from_prior(mu_x, None, y, tx, ty, path_out=out, flags=_lib.FLAG_PATH_ZEROED)
+    torch.cuda.synchronize()
+    assert torch.equal(out[ref == 1], torch.ones_like(out[ref == 1])) and bool((out[ref == 0] == 7.0).all())
+    with pytest.raises(ValueError):
+        monotonic_align.maximum_path_from_prior(mu_x, None, y, tx, ty, path_out=out[:, :, :-4])
+    with pytest.raises(ValueError):
+        monotonic_align.maximum_path_from_prior(mu_x, None, y, tx, ty, path_out=out.to(torch.float16))
