@@ -388,6 +388,12 @@ def run_ours(args):
     # strong scaling: steps in flight on several streams at every N (N=1 included: the same pipeline, so
     # that the driver's efficiency compares like with like; it hides the persistent kernel's tail)
     nstreams = max(1, args.streams) if strong else 1
+    sms_all = torch.cuda.get_device_properties(dev).multi_processor_count
+    # a shard that fits the SMs once (128 utterances per GPU at N=8) and a run long enough to amortise the
+    # longer CTAs: 8 utterances per CTA on 10 streams (profiles/r2_strong_shard_sweep.txt: 0.0399 vs 0.0418 ms)
+    long_cta = strong and fused and args.utt_per_cta < 0 and args.streams == 6 and len(tx_np) <= sms_all and args.steps >= 80
+    if long_cta:
+        nstreams = 10
     if world > 1:
         for _ in range(8):   # bring up every NCCL channel/connection before anything is timed
             w = torch.empty(world * 8, dtype=torch.int32, device=dev)
@@ -452,7 +458,7 @@ def run_ours(args):
 
     if strong and nstreams > 1 and fused:
         sms = torch.cuda.get_device_properties(dev).multi_processor_count
-        upc = args.utt_per_cta if args.utt_per_cta >= 0 else (4 if B <= 2 * sms else 1)
+        upc = args.utt_per_cta if args.utt_per_cta >= 0 else (8 if long_cta else 4 if B <= 2 * sms else 1)
         if upc > 1:
             pipe_flags[0] = _lib.flag_utt_per_cta(upc)
         pipeline["utterances_per_cta"] = max(1, upc)
