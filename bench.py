@@ -707,7 +707,7 @@ def run_ours(args):
                 h_score.copy_(score, non_blocking=True)
             torch.cuda.current_stream().synchronize()   # the caller reads the result every step
 
-        e_ms, _ = timed_serial(e2e_step, max(3, args.steps // 2), 2)
+        e_ms, _ = timed_serial(e2e_step, max(3, args.steps // 2), 3)
         tot = torch.tensor([float(moved[0]), float(d2h)], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(tot)
