@@ -30,7 +30,14 @@
 //               the next utterance's mu_x in registers and, the moment its last MMA has retired,
 //               split it into tf32 hi/lo and tcgen05.st it into TMEM; also produce -0.5|mu|^2
 //   warp 12     backtrack warp (one utterance behind, second direction-bit buffer): path ones,
-//               durations, frame index, peer-memory rows of the fused all-gather
+//               durations, frame index, peer-memory rows of the fused all-gather; clears the dense path of
+//               the last of several utterances of a CTA while its tiles run
+//
+// Token axes of 257..512 (template parameter CS = 2 or 4): one thread-block CLUSTER per utterance, CTA h owns
+// the tokens [h xs, (h+1) xs) with the same fourteen roles; the recurrence and the backtrack cross CTAs through
+// distributed shared memory (mas_dp.cuh dp_forward_chain / backtrack_bits_window), the direction words live in
+// the caller's workspace.  DESIGN.md 4.3 / 4.3c have the measurements (role cycles, per-tile timeline,
+// what bounds the kernel) behind every choice below.
 #include <algorithm>
 #include <type_traits>
 
