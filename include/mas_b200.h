@@ -74,9 +74,9 @@ enum {
  * utterance instead of throughput).  Same results; A/B measurements and tests. */
 #define MAS_FLAG_ONE_DP_WARP (1 << 18)
 /* mas_from_prior_f32 (tensor-core engine; the others ignore it and clear the path themselves): `path` already holds
- * zeros in every element -- the caller cleared it, e.g. with cudaMemsetAsync on another stream while the previous
- * step's kernel was running (copy engine, no SM time) -- so the kernel only writes the 1-cells.  Clearing is 2/3 of
- * the kernel's algorithmic bytes and, done by the SMs, stalls the tile pipeline of every utterance. */
+ * zeros in every element (the caller cleared it, or re-uses a buffer whose 1-cells it reset) -- the kernel only
+ * writes the 1-cells.  Measured (profiles/zero_overlap.py): the kernel's own clearing hides in the slack of
+ * its pipeline, so this saves nothing at B = 1024; it exists for callers that own pre-cleared buffers anyway. */
 #define MAS_FLAG_PATH_ZEROED (1 << 19)
 /* mas_from_prior_f32 (tensor-core engine): issue the MMAs as staggered half-chains of consecutive tiles instead of
  * tile pairs (same chains, same results; A/B measurements and tests). */
